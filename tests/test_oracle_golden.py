@@ -1,0 +1,113 @@
+"""Pins oracle/torch_oracle.py against outputs of the REAL reference (tests/golden/*.npz,
+made by oracle/gen_golden.py) and, when /root/reference is present, against the live reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as O
+
+REF_PRESENT = os.path.isdir(os.environ.get("RADAR_DEPTH_REFERENCE", "/root/reference"))
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def _check_grads(g, res, rtol=3e-3):  # fp32 noise through 12-sample BNs at the 2x3 bottleneck
+    names = [str(n) for n in g["grad_names"]]
+    assert names == list(res["grads"].keys())
+    for i, k in enumerate(names):
+        gr = res["grads"][k]
+        ref_norm = float(g["grad_norms"][i])
+        got = float(gr.double().norm())
+        assert abs(got - ref_norm) <= rtol * max(ref_norm, 1e-6) + 1e-7, (k, got, ref_norm)
+        head = gr.reshape(-1)[:8].numpy()
+        np.testing.assert_allclose(head, g["grad_heads"][i][: head.size], rtol=1e-2, atol=5e-4 * max(ref_norm, 1e-3))  # fp32-vs-fp64 noise measured at 1e-4*norm
+
+
+@pytest.mark.parametrize("name,cin", [("latefusion_train_b2_64x96", 4), ("latefusion_train_b2_90x160", 4),
+                                      ("latefusion2_c5_train_b2_64x96", 5)])
+def test_latefusion_train_matches_reference_golden(golden_dir, name, cin):
+    g = _load(golden_dir, name)
+    b, h, w = int(g["b"]), int(g["h"]), int(g["w"])
+    sd = O.synth_state_dict(O.latefusion_entries(cin))
+    inputs, target = O.synth_batch(b, h, w)
+    if cin == 5:
+        gen = torch.Generator().manual_seed(99)
+        inputs = torch.cat((inputs, torch.rand(b, 1, h, w, generator=gen) * 40), dim=1)
+    res = O.train_step(sd, inputs, target, "latefusion")
+    np.testing.assert_allclose(res["pred"].numpy(), g["pred"], rtol=1e-4, atol=1e-4)
+    assert abs(float(res["loss"]) - float(g["loss"])) < 1e-4       # north_star loss tolerance
+    _check_grads(g, res)
+    flat = np.concatenate([res["new_buffers"][str(k)].reshape(-1).numpy() for k in g["buf_names"]])
+    np.testing.assert_allclose(flat, g["buf_values"], rtol=1e-5, atol=1e-6)
+    assert int(res["new_buffers"]["bn1.num_batches_tracked"]) == int(g["nbt"])
+
+
+def test_latefusion_eval_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "latefusion_eval_b1_64x96")
+    sd = O.synth_state_dict(O.latefusion_entries(4))
+    inputs, target = O.synth_batch(1, 64, 96)
+    with torch.no_grad():
+        pred = O.latefusion_forward(sd, inputs, (64, 96), training=False)
+    np.testing.assert_allclose(pred.numpy(), g["pred"], rtol=1e-4, atol=1e-4)
+    assert abs(float(O.masked_l1(pred, target)) - float(g["loss"])) < 1e-4
+
+
+def test_latefusion_full_size_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "latefusion_train_b2_352x1216")
+    sd = O.synth_state_dict(O.latefusion_entries(4))
+    inputs, target = O.synth_batch(2, 352, 1216)
+    res = O.train_step(sd, inputs, target, "latefusion")
+    np.testing.assert_allclose(res["pred"][..., ::8, ::8].numpy(), g["pred"], rtol=1e-4, atol=1e-4)
+    assert abs(float(res["loss"]) - float(g["loss"])) < 1e-4
+    _check_grads(g, res)
+
+
+def test_multistage_fixs_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "multistage_fixs_train_b2_64x96")
+    sd = O.synth_state_dict(O.multistage_entries())
+    inputs, target = O.synth_batch(2, 64, 96)
+    res = O.train_step(sd, inputs, target, "multistage_fixs")
+    np.testing.assert_allclose(res["stage1"].numpy(), g["stage1"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(res["stage2"].numpy(), g["stage2"], rtol=1e-4, atol=1e-4)
+    assert abs(float(res["loss"]) - float(g["loss"])) < 1e-4
+    assert float(res["mask"].sum()) == float(g["mask_sum"])
+    assert abs(float(res["radar_filtered"].sum()) - float(g["radar_filtered_sum"])) < 1e-3
+    _check_grads(g, res)
+
+
+def test_losses_and_filter_match_reference_golden(golden_dir):
+    g = _load(golden_dir, "losses_filter")
+    pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+    l1 = O.masked_l1(pred, torch.from_numpy(g["tgt"]))
+    sm = O.smoothness(pred, torch.from_numpy(g["img"]))
+    (l1 + sm).backward()
+    assert abs(float(l1) - float(g["l1"])) < 1e-5
+    assert abs(float(sm) - float(g["smooth"])) < 1e-6
+    np.testing.assert_allclose(pred.grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
+    rf, mask = O.filter_layer(torch.from_numpy(g["sparse"]), pred.detach())
+    np.testing.assert_array_equal(mask.numpy(), g["mask"])
+    np.testing.assert_array_equal(rf.numpy(), g["radar_filtered"])
+
+
+def test_unpool_is_zero_stuffing():
+    x = torch.arange(12.0).reshape(1, 2, 2, 3)
+    u = O.unpool(x)
+    assert u.shape == (1, 2, 4, 6)
+    assert torch.equal(u[:, :, ::2, ::2], x) and float(u.sum()) == float(x.sum())
+
+
+@pytest.mark.skipif(not REF_PRESENT, reason="live reference only exists in the build container")
+def test_key_order_and_shapes_match_live_reference():
+    from oracle.gen_golden import import_reference
+    ref = import_reference()
+    m = ref.models.ResNet_latefusion(18, "upproj", (64, 96), 4, pretrained=False)
+    ent = O.latefusion_entries(4)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ent.keys()) and len(ent) == 325
+    for k, (shape, _) in ent.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert len(O.multistage_entries()) == 652
