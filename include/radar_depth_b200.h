@@ -1,0 +1,206 @@
+/* radar_depth_b200.h -- C ABI of libradar_depth_b200.so (sm_100a).
+ *
+ * This library is the device side of the radar_depth hot path:
+ * ResNet_latefusion / ResNet_latefusion2 forward+backward (reference model/models.py:519-664,
+ * model/multistage_model.py:123-276), Filter_layer (multistage_model.py:87-119) and the
+ * MaskedL1 / Smoothness losses (evaluation/criteria_new.py:8-54).  The reference owns no kernels:
+ * every entry point below replaces a torch.nn / ATen call the reference issues (the call site is
+ * cited next to each function).  The host side (radar_depth_b200/model/*.py) mirrors the reference's
+ * nn.Module constructors and sequences these calls.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers, ints, a cudaStream_t passed as void*; no torch types.
+ *  - every function returns 0 on success or a negative RD_E* code; rd_last_error() gives the text.
+ *  - nothing allocates, frees or synchronises the device; the caller owns every buffer.
+ *  - activations are NHWC "views": base pointer + pixel pitch (elements) + channel offset, so that
+ *    concatenations (reference torch.cat, models.py:652) are just adjacent channel ranges.
+ *  - act_dtype: RD_BF16 (throughput mode) or RD_F32 (parity mode: fp32 activations and a 3-term
+ *    bf16 split on the tensor cores, ~fp32 accuracy).
+ */
+#ifndef RADAR_DEPTH_B200_H_
+#define RADAR_DEPTH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_OK 0
+#define RD_EINVAL (-1)   /* bad argument / unsupported shape */
+#define RD_ECUDA (-2)    /* CUDA runtime error (text in rd_last_error) */
+#define RD_EDEVICE (-3)  /* device-side protocol error (barrier timeout) */
+
+#define RD_BF16 0
+#define RD_F32 1
+
+#define RD_MAX_TAPS 32
+#define RD_MAX_GROUPS 16
+#define RD_MAX_PHASES 4
+
+const char* rd_last_error(void);
+int rd_version(void);
+/* sizeof() of the parameter blocks below, for binding self-checks. */
+int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params */
+/* reads and clears the device-side error word (0 = none).  Synchronises the stream. */
+int rd_device_error(void* stream);
+
+/* NHWC view of a [B, H, W, C] slice living inside a [B, H, W, pitch] buffer. */
+typedef struct rd_view {
+    void* ptr;
+    int32_t pitch; /* elements per pixel in the underlying buffer (multiple of 8) */
+    int32_t coff;  /* first channel of the slice (multiple of 8) */
+} rd_view;
+
+typedef struct rd_tap {
+    int32_t a_shift; /* slot offset of this tap inside the staged input tile (includes the parity-plane base) */
+    int32_t phase;   /* output phase this tap accumulates into */
+    int32_t first;   /* 1 = first tap of its phase (clears the accumulator on the first channel block) */
+    int32_t pad_;
+} rd_tap;
+
+/* Implicit-GEMM convolution on tcgen05 (forward convs, data gradients, sub-pixel UpProj convs).
+ * Replaces nn.Conv2d / F.conv_transpose2d calls: models.py:539,559,573,582,191,194,198,27 and torchvision
+ * conv3x3/conv1x1 (models.py:8,88,91,605-608) and their autograd data-gradient counterparts.
+ *
+ * out[b, oy*OS+phy, ox*OS+phx, n] = sum_taps sum_c  T(src)[b, (oy+sy)*S+py, (ox+sx)*S+px, c] * W[tap][c][n]
+ * where T is the optional fused per-channel affine+activation of the producer's BatchNorm
+ * (models.py:540,546 etc.: relu(bn(z)) is never materialised).                                   */
+typedef struct rd_conv_params {
+    /* source */
+    rd_view src;
+    int32_t srcH, srcW, Cin; /* Cin multiple of 16 */
+    int32_t S;               /* 1, or 2 = source staged as 4 parity planes (stride-2 convs) */
+    const float* ld_scale;   /* [Cin] or NULL: fused y = act(x*scale+shift) on load */
+    const float* ld_shift;
+    float ld_slope;          /* negative-side slope of act: 0 relu, 0.2 leaky, 1 identity */
+    int32_t B;
+    /* tile geometry in base output pixels */
+    int32_t Hb, Wb;          /* base output size (before phase interleave) */
+    int32_t Ht, Wt, Wl;      /* tile rows, valid cols, local row width in slots */
+    int32_t plane_rows, plane_slots;
+    int32_t sy_min, sx_min;  /* plane-coordinate offset of slot 0 relative to the tile origin */
+    int32_t MB;              /* 128-row accumulator blocks per tile */
+    int32_t tiles_y, tiles_x;
+    /* tap program */
+    int32_t P, OS, ntaps, ngroups;
+    int32_t phase_y[RD_MAX_PHASES], phase_x[RD_MAX_PHASES];
+    rd_tap taps[RD_MAX_TAPS];
+    int32_t grp_first[RD_MAX_GROUPS], grp_n[RD_MAX_GROUPS];
+    /* weights, packed by rd_pack_weights: [nblk][Cin/16][tap][part][2][N][8] bf16 */
+    const void* wpk;
+    int32_t N;               /* output channels per CTA (multiple of 16, <= 256) */
+    int32_t nblk;            /* number of N blocks (grid.y) */
+    /* destination */
+    rd_view dst;
+    int32_t dstH, dstW;
+    /* epilogue */
+    int32_t epi;             /* 0 store(+addend)+sum/sumsq stats; 1 activation-gradient mask + sum g / sum g*z stats */
+    rd_view addend;          /* ptr NULL = none; same spatial size as dst */
+    rd_view zsrc;            /* epi 1: producer's pre-BN output z, same spatial size as dst */
+    const float* ep_scale;   /* epi 1: [nblk*N] BN scale/shift of the layer being differentiated */
+    const float* ep_shift;
+    float ep_slope;
+    double* stats;           /* [2][stats_stride] or NULL */
+    int32_t stats_stride;
+    /* pipeline */
+    int32_t IS, WS;          /* input / weight ring depths */
+    int32_t istage_bytes, wstage_bytes;
+    int32_t act_dtype;       /* RD_BF16 / RD_F32 */
+    int32_t max_ctas;        /* persistent grid cap (0 = one CTA per tile) */
+} rd_conv_params;
+
+int rd_conv_fprop(const rd_conv_params* p, void* stream);
+
+/* Weight gradient of the same convolutions on tcgen05 (replaces autograd's conv weight-gradient kernels for
+ * every nn.Conv2d above).  Contraction runs over pixels: both operands are staged pixel-linear and fed
+ * to the tensor core as MN-major matrices; each tap has its own TMEM accumulator [co x ci]; CTAs split the
+ * pixel tiles and reduce with vector fp32 atomics into dw[tap][Cout][Cin].
+ *   dw[tap][co][ci] += sum_pixels gy[b, oy*Sg+gpy, ox*Sg+gpx, co] * T(x)[b, (oy+sy)*Sx+py, (ox+sx)*Sx+px, ci]  */
+typedef struct rd_wtap {
+    int32_t g_off;   /* slot offset of the gradient parity plane of this tap */
+    int32_t x_shift; /* slot offset into the staged source tile (includes its parity-plane base) */
+} rd_wtap;
+
+typedef struct rd_wgrad_params {
+    rd_view gy;
+    int32_t gH, gW, Cout, Sg;
+    rd_view x;
+    int32_t xH, xW, Cin, Sx;
+    const float* ld_scale; /* fused BN+activation on x (NULL = raw) */
+    const float* ld_shift;
+    float ld_slope;
+    int32_t B;
+    int32_t Hb, Wb, Ht, Wt, Wl;
+    int32_t KS;                 /* gradient slots per plane (multiple of 16, >= Ht*Wl) */
+    int32_t x_plane_rows, x_plane_slots, sy_min, sx_min;
+    int32_t tiles_y, tiles_x;
+    int32_t ntaps, tg_size, ntg;  /* taps per CTA and number of tap groups */
+    rd_wtap taps[RD_MAX_TAPS];
+    int32_t Mc, ncob;            /* output-channel rows per CTA (<=128, multiple of 8) and block count */
+    int32_t Nc, ncib;            /* input-channel columns per CTA (multiple of 16) and block count */
+    float* dw;                   /* [ntaps][Cout][Cin] fp32, accumulated with atomics (caller zeroes) */
+    int32_t NS, stage_bytes, g_bytes;
+    int32_t act_dtype;
+    int32_t max_ctas;            /* pixel-split CTAs (grid.x) */
+} rd_wgrad_params;
+
+int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);
+
+/* ---- HBM-bound kernels (rd_elementwise.cuh).  npix = B*H*W of the tensors involved. ---- */
+
+/* NCHW fp32 [B,C,H,W] -> space-to-depth NHWC [B,ceil(H/2),ceil(W/2),4*Cs] (channel = parity*Cs + c).  Replaces the
+ * x[:, :3] / x[:, 3:] slicing at models.py:633,643 and multistage_model.py:236-241. */
+int rd_input_pack(const float* x, void* out, int B, int C, int H, int W, int Cs, int act_dtype, void* stream);
+
+/* nn.BatchNorm2d statistics -> fused scale/shift (+ running-stat update in training).  models.py:540 etc. */
+int rd_bn_finalize(const double* sum, const double* sumsq, double count, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, int C, int training,
+                   float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                   void* stream);
+/* BatchNorm2d backward reductions -> dgamma/dbeta (accumulated) and dz = A*g + B*z + C coefficients. */
+int rd_bn_bwd_finalize(const double* sum_g, const double* sum_gz, double count, const float* gamma,
+                       const float* save_mean, const float* save_invstd, int C, int training, float* dgamma,
+                       float* dbeta, float* coefA, float* coefB, float* coefC, void* stream);
+/* out = act(z*sc+sh + identity): residual join of BasicBlock (models.py:104-110) / UpProjModule (models.py:205-208). */
+int rd_bn_add_act(rd_view z, const float* sc, const float* sh, rd_view idv, const float* id_sc, const float* id_sh,
+                  rd_view out, long long npix, int C, float slope, int act_dtype, void* stream);
+/* g = dout*act'(out) + BN-backward statistics of the joined branches. */
+int rd_join_bwd(rd_view dout, rd_view out, rd_view z, rd_view zid, rd_view g, long long npix, int C, float slope,
+                double* sum_g, double* sum_gz, double* sum_gzid, int act_dtype, void* stream);
+int rd_bn_bwd_apply(rd_view g, rd_view z, rd_view dz, const float* coefA, const float* coefB, const float* coefC,
+                    long long npix, int C, int act_dtype, void* stream);
+int rd_grad_stats(rd_view g, rd_view z, long long npix, int C, double* sum_g, double* sum_gz, int act_dtype, void* stream);
+
+/* nn.MaxPool2d(3,2,1) over act(bn(z)) (models.py:546-547,564-565), both stems at once; stores the arg-max. */
+int rd_maxpool_fwd(rd_view z, const float* sc, const float* sh, int B, int H, int W, int C, int split, float slope_a,
+                   float slope_b, rd_view outa, rd_view outb, uint8_t* amax, int Ho, int Wo, int act_dtype, void* stream);
+int rd_maxpool_bwd(rd_view dpa, rd_view dpb, const uint8_t* amax, rd_view z, const float* sc, const float* sh, int B,
+                   int H, int W, int C, int split, float slope_a, float slope_b, int Ho, int Wo, rd_view g,
+                   double* sum_g, double* sum_gz, int act_dtype, void* stream);
+
+/* conv3 (3x3, 16->1, models.py:587,661) and nn.Upsample(bilinear, align_corners=True) (models.py:588,662). */
+int rd_head_conv_fwd(rd_view x, const float* w, int B, int H, int W, float* out, int act_dtype, void* stream);
+int rd_head_conv_bwd(const float* dc3, rd_view x, const float* w, int B, int H, int W, rd_view dx, float* dw,
+                     int act_dtype, void* stream);
+int rd_bilinear_fwd(const float* in, int B, int Hi, int Wi, float* out, int Ho, int Wo, void* stream);
+int rd_bilinear_bwd(const float* dout, int B, int Hi, int Wi, float* din, int Ho, int Wo, void* stream);
+
+/* MaskedL1Loss (criteria_new.py:44-54).  acc = 2 doubles of scratch (sum, count), zeroed by the call. */
+int rd_l1_fwd(const float* pred, const float* target, long long n, double* acc, float* loss, void* stream);
+int rd_l1_bwd(const float* pred, const float* target, long long n, const double* acc, const float* gout,
+              float* gpred, int accumulate, void* stream);
+
+/* Filter_layer (multistage_model.py:87-119). */
+int rd_sid_filter(const float* radar, const float* depth, long long n, float* radar_f, float* mask, void* stream);
+
+/* Packed bf16 weights from the flat fp32 parameter arena via a gather table; gradient scatter back; fused SGD
+ * (torch.optim.SGD as configured at main.py:285-290). */
+int rd_pack_weights(const float* src, const int32_t* idx, void* out, long long n, void* stream);
+int rd_unpack_grads(const float* dw, const int32_t* idx, float* grad, long long n, void* stream);
+int rd_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADAR_DEPTH_B200_H_ */

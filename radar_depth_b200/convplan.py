@@ -1,0 +1,429 @@
+"""Host-side planning of the tcgen05 convolution programs.
+
+Every convolution on the hot path -- 7x7/3x3/1x1 stride 1|2 (reference models.py:539,559,88-91,605-608,573,582),
+the 5x5 convs on the zero-stuffed Unpool output (models.py:13-27,191,198) -- is described ONCE as a ``GConv``:
+
+    out[b, OS*y + a] = sum over taps t with phase a:   X[b, (y + s_t)*S + pl_t, :] @ W_t          (2-D indices)
+
+with ``W_t`` given as an int32 index matrix ``widx[Cx, N]`` into the flat fp32 parameter arena (-1 = structural
+zero).  From that single description this module derives
+
+  * the forward program      (``plan_fprop(g)``),
+  * the data-gradient program (``plan_fprop(g.transposed())``: swap S<->OS, phase<->plane, negate shifts, transpose W),
+  * the weight-gradient program (``plan_wgrad(g)``),
+  * the gather table that packs bf16 weight tiles from the parameter arena, and the scatter table that routes
+    the weight-gradient accumulators back to OIHW ``.grad`` layout,
+
+plus a slow torch reference (``gconv_reference`` / ``gconv_wgrad_reference``) used by the tests to validate both
+the descriptions (against F.conv2d on CPU) and the kernels (on the GPU).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+SMEM_BUDGET = 232448
+FPROP_HEADER = 16384
+WGRAD_HEADER = 10240
+NUM_SMS = 148
+
+
+@dataclass
+class GTap:
+    ph: Tuple[int, int]      # output phase (y, x) in [0, OS)
+    pl: Tuple[int, int]      # source parity plane (y, x) in [0, S)
+    s: Tuple[int, int]       # shift in plane coordinates
+    widx: np.ndarray         # int32 [Cx, N] indices into the flat parameter arena, -1 = zero
+
+
+@dataclass
+class GConv:
+    Cx: int
+    N: int
+    S: int
+    OS: int
+    taps: List[GTap]
+    name: str = ""
+
+    def transposed(self) -> "GConv":
+        """Data-gradient form: dX = sum_t dOut[...] @ W_t^T."""
+        taps = [GTap(ph=t.pl, pl=t.ph, s=(-t.s[0], -t.s[1]), widx=np.ascontiguousarray(t.widx.T)) for t in self.taps]
+        return GConv(Cx=self.N, N=self.Cx, S=self.OS, OS=self.S, taps=taps, name=self.name + ".T")
+
+    def sorted_taps(self) -> Tuple[List[GTap], List[Tuple[int, int]]]:
+        phases = sorted({t.ph for t in self.taps})
+        taps = sorted(self.taps, key=lambda t: (phases.index(t.ph), t.pl, t.s))
+        return taps, phases
+
+
+# ------------------------------------------------------------------------------------------ builders
+def _oihw_index(off: int, Cout: int, Cin: int, kh: int, kw: int, ky: int, kx: int) -> np.ndarray:
+    """[Cin, Cout] matrix of flat indices of W[co][ci][ky][kx] (OIHW at arena offset ``off``)."""
+    co = np.arange(Cout, dtype=np.int64)[None, :]
+    ci = np.arange(Cin, dtype=np.int64)[:, None]
+    return (off + ((co * Cin + ci) * kh + ky) * kw + kx).astype(np.int32)
+
+
+def gconv_standard(off: int, Cout: int, Cin: int, k: int, stride: int, pad: int, name: str = "") -> GConv:
+    """nn.Conv2d(Cin, Cout, k, stride, pad, bias=False)."""
+    assert stride in (1, 2)
+    taps = []
+    for ky in range(k):
+        for kx in range(k):
+            dy, dx = ky - pad, kx - pad
+            if stride == 1:
+                pl, s = (0, 0), (dy, dx)
+            else:
+                pl, s = (dy & 1, dx & 1), (dy >> 1, dx >> 1)
+            taps.append(GTap(ph=(0, 0), pl=pl, s=s, widx=_oihw_index(off, Cout, Cin, k, k, ky, kx)))
+    return GConv(Cx=Cin, N=Cout, S=stride, OS=1, taps=taps, name=name)
+
+
+def gconv_stem(off_rgb: int, off_depth: int, cin_depth: int, name: str = "stem") -> GConv:
+    """conv1 (3->64, 7x7 s2 p3, models.py:539) and conv1_depth (cin_depth->16, models.py:559 /
+    multistage_model.py:163-164) fused into ONE stride-1 4x4-tap convolution over the space-to-depth input
+    produced by rd_input_pack: channel = parity*Cs + c, Cs = 4 (4 input channels) or 8 (5 input channels)."""
+    C = 3 + cin_depth
+    Cs = 4 if C <= 4 else 8
+    Cx, N = 4 * Cs, 80
+    taps = []
+    for sy in range(-2, 2):
+        for sx in range(-2, 2):
+            widx = np.full((Cx, N), -1, dtype=np.int32)
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * sy + py + 3, 2 * sx + px + 3
+                    if not (0 <= ky < 7 and 0 <= kx < 7):
+                        continue
+                    q = py * 2 + px
+                    for c in range(C):
+                        if c < 3:
+                            n = np.arange(64)
+                            widx[q * Cs + c, :64] = off_rgb + ((n * 3 + c) * 7 + ky) * 7 + kx
+                        else:
+                            n = np.arange(16)
+                            widx[q * Cs + c, 64:] = off_depth + ((n * cin_depth + (c - 3)) * 7 + ky) * 7 + kx
+            taps.append(GTap(ph=(0, 0), pl=(0, 0), s=(sy, sx), widx=widx))
+    return GConv(Cx=Cx, N=N, S=1, OS=1, taps=taps, name=name)
+
+
+def gconv_upproj(off_upper: int, off_bottom: int, Cin: int, Cout: int, name: str = "") -> GConv:
+    """Both 5x5 p2 convs of an UpProjModule (upper_branch.conv1 | bottom_branch.conv, models.py:191,198) applied to
+    Unpool(x) (models.py:13-27), as 4 sub-pixel convolutions on the un-stuffed x with N = 2*Cout."""
+    taps = []
+    for a in range(2):
+        for b in range(2):
+            for ky in range(5):
+                if (a + ky - 2) % 2:
+                    continue
+                for kx in range(5):
+                    if (b + kx - 2) % 2:
+                        continue
+                    w = np.concatenate([_oihw_index(off_upper, Cout, Cin, 5, 5, ky, kx),
+                                        _oihw_index(off_bottom, Cout, Cin, 5, 5, ky, kx)], axis=1)
+                    taps.append(GTap(ph=(a, b), pl=(0, 0), s=((a + ky - 2) // 2, (b + kx - 2) // 2), widx=w))
+    return GConv(Cx=Cin, N=2 * Cout, S=1, OS=2, taps=taps, name=name)
+
+
+# ------------------------------------------------------------------------------------------ references
+def _gather_source(x, t: GTap, S: int, Hb: int, Wb: int):
+    """x: [B,H,W,C] torch tensor -> [B,Hb,Wb,C] of X[(y+sy)*S+py, (x+sx)*S+px] with zeros out of range."""
+    import torch
+    B, H, W, C = x.shape
+    ys = (torch.arange(Hb, device=x.device) + t.s[0]) * S + t.pl[0]
+    xs = (torch.arange(Wb, device=x.device) + t.s[1]) * S + t.pl[1]
+    vy = (ys >= 0) & (ys < H)
+    vx = (xs >= 0) & (xs < W)
+    g = x[:, ys.clamp(0, H - 1)][:, :, xs.clamp(0, W - 1)]
+    return g * (vy[:, None] & vx[None, :]).to(x.dtype)[None, :, :, None]
+
+
+def _tap_weight(wflat, t: GTap):
+    import torch
+    idx = torch.from_numpy(t.widx.astype(np.int64)).to(wflat.device)
+    w = wflat[idx.clamp(min=0)]
+    return w * (idx >= 0).to(wflat.dtype)
+
+
+def gconv_reference(g: GConv, x, wflat, dst_hw):
+    """Slow exact evaluation of a GConv with torch ops.  x: [B,H,W,Cx]; returns [B,dstH,dstW,N].  Output positions
+    belonging to phases without taps are left at zero."""
+    import torch
+    B = x.shape[0]
+    dH, dW = dst_hw
+    Hb, Wb = -(-dH // g.OS), -(-dW // g.OS)
+    out = torch.zeros(B, Hb * g.OS, Wb * g.OS, g.N, dtype=x.dtype, device=x.device)
+    for t in g.taps:
+        out[:, t.ph[0]::g.OS, t.ph[1]::g.OS] += _gather_source(x, t, g.S, Hb, Wb) @ _tap_weight(wflat, t)
+    return out[:, :dH, :dW]
+
+
+def gconv_wgrad_reference(g: GConv, x, dout, nparams: int):
+    """Flat gradient (length nparams) of sum(out * dout) w.r.t. the parameter arena."""
+    import torch
+    B, dH, dW, _ = dout.shape
+    Hb, Wb = -(-dH // g.OS), -(-dW // g.OS)
+    pad = torch.zeros(B, Hb * g.OS, Wb * g.OS, g.N, dtype=dout.dtype, device=dout.device)
+    pad[:, :dH, :dW] = dout
+    grad = torch.zeros(nparams, dtype=x.dtype, device=x.device)
+    for t in g.taps:
+        xs = _gather_source(x, t, g.S, Hb, Wb).reshape(-1, g.Cx)
+        go = pad[:, t.ph[0]::g.OS, t.ph[1]::g.OS].reshape(-1, g.N)
+        dw = xs.t() @ go                                    # [Cx, N]
+        idx = torch.from_numpy(t.widx.astype(np.int64)).to(x.device)
+        m = idx >= 0
+        grad.index_add_(0, idx[m], dw[m])
+    return grad
+
+
+# ------------------------------------------------------------------------------------------ fprop planning
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+@dataclass
+class FpropPlan:
+    g: GConv
+    params: "_lib.ConvParams"          # geometry / program filled in; pointers bound at call time
+    pack_idx: np.ndarray               # int32 gather table for the packed weights of this conv
+    wpk_elems: int
+    ntiles: int
+    info: dict = field(default_factory=dict)
+
+
+def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes):
+    best = None
+    MBmax = max(1, 512 // (P * N))
+    planes = S * S
+    for MB in range(1, MBmax + 1):
+        M = MB * 128
+        for Wl in range(halo_x + 1, min(Wb + halo_x, M) + 1):
+            Wt = Wl - halo_x
+            Ht = min(M // Wl, Hb)
+            if Ht < 1:
+                continue
+            if MB > 1 and Ht * Wl <= (MB - 1) * 128:
+                continue                                   # a smaller MB covers this tile
+            plane_rows = Ht + halo_y
+            plane_slots = _round_up(M + halo_y * Wl + halo_x, 8)
+            istage = _round_up(parts * 2 * planes * plane_slots * 16, 128)
+            if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > SMEM_BUDGET:
+                continue
+            ty, tx = -(-Hb // Ht), -(-Wb // Wt)
+            # cycle model per tile: tensor pipe vs loader, plus the (serialised) epilogue
+            mma = MB * ntaps * max(N, 32) / 2.0 * (3 if parts == 2 else 1)
+            load = planes * plane_slots * 2 * 0.35 * parts
+            epi = MB * P * (N / 16.0) * 40.0
+            per_tile = max(mma, load) * ncblk + epi + 600.0
+            return_tiles = ty * tx
+            cost = return_tiles * per_tile
+            if best is None or cost < best[0]:
+                best = (cost, dict(MB=MB, Wl=Wl, Wt=Wt, Ht=Ht, plane_rows=plane_rows, plane_slots=plane_slots,
+                                   istage=istage, tiles_y=ty, tiles_x=tx))
+    if best is None:
+        raise ValueError("no feasible tile for this convolution")
+    return best[1]
+
+
+def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, n_per_cta: Optional[int] = None,
+               tile_override: Optional[dict] = None) -> FpropPlan:
+    assert g.Cx % 16 == 0 and g.N % 16 == 0, (g.Cx, g.N)
+    parts = 2 if act_dtype == _lib.RD_F32 else 1
+    taps, phases = g.sorted_taps()
+    P = len(phases)
+    ntaps = len(taps)
+    assert ntaps <= _lib.RD_MAX_TAPS
+    if n_per_cta is None:
+        n_per_cta = min(g.N, 128)
+        while g.N % n_per_cta:
+            n_per_cta -= 16
+    N = n_per_cta
+    assert g.N % N == 0 and P * N <= 512
+    nblk = g.N // N
+    ncblk = g.Cx // 16
+    dH, dW = dst_hw
+    Hb, Wb = -(-dH // g.OS), -(-dW // g.OS)
+    sy = [t.s[0] for t in taps]
+    sx = [t.s[1] for t in taps]
+    sy_min, sx_min = min(sy), min(sx)
+    halo_y, halo_x = max(sy) - sy_min, max(sx) - sx_min
+    # weight groups
+    tap_bytes = parts * N * 32
+    wcap = 36864
+    max_g = max(1, wcap // tap_bytes)
+    ngroups = -(-ntaps // max_g)
+    assert ngroups <= _lib.RD_MAX_GROUPS
+    base, rem = divmod(ntaps, ngroups)
+    grp_n = [base + (1 if i < rem else 0) for i in range(ngroups)]
+    wstage = _round_up(max(grp_n) * tap_bytes, 128)
+    geo = tile_override or _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage)
+    if tile_override:
+        geo = dict(geo)
+        geo.setdefault("Wl", geo["Wt"] + halo_x)
+        geo.setdefault("MB", -(-geo["Ht"] * geo["Wl"] // 128))
+        M = geo["MB"] * 128
+        geo["plane_rows"] = geo["Ht"] + halo_y
+        geo["plane_slots"] = _round_up(M + halo_y * geo["Wl"] + halo_x, 8)
+        geo["istage"] = _round_up(parts * 2 * g.S * g.S * geo["plane_slots"] * 16, 128)
+        geo["tiles_y"], geo["tiles_x"] = -(-Hb // geo["Ht"]), -(-Wb // geo["Wt"])
+    istage = geo["istage"]
+    # ring depths within the shared-memory budget
+    avail = SMEM_BUDGET - FPROP_HEADER
+    IS = 2
+    WS = 2
+    while True:
+        grown = False
+        if WS < 4 and FPROP_HEADER + IS * istage + (WS + 1) * wstage <= SMEM_BUDGET:
+            WS += 1
+            grown = True
+        if IS < 3 and FPROP_HEADER + (IS + 1) * istage + WS * wstage <= SMEM_BUDGET:
+            IS += 1
+            grown = True
+        if not grown:
+            break
+    assert IS * istage + WS * wstage <= avail
+
+    p = _lib.ConvParams()
+    p.Cin, p.S, p.B = g.Cx, g.S, B
+    p.srcH, p.srcW = src_hw
+    p.Hb, p.Wb = Hb, Wb
+    p.Ht, p.Wt, p.Wl = geo["Ht"], geo["Wt"], geo["Wl"]
+    p.plane_rows, p.plane_slots = geo["plane_rows"], geo["plane_slots"]
+    p.sy_min, p.sx_min = sy_min, sx_min
+    p.MB = geo["MB"]
+    p.tiles_y, p.tiles_x = geo["tiles_y"], geo["tiles_x"]
+    p.P, p.OS, p.ntaps, p.ngroups = P, g.OS, ntaps, ngroups
+    for i, ph in enumerate(phases):
+        p.phase_y[i], p.phase_x[i] = ph
+    seen = set()
+    for i, t in enumerate(taps):
+        pi = phases.index(t.ph)
+        q = t.pl[0] * g.S + t.pl[1]
+        p.taps[i].a_shift = q * geo["plane_slots"] + (t.s[0] - sy_min) * geo["Wl"] + (t.s[1] - sx_min)
+        p.taps[i].phase = pi
+        p.taps[i].first = 0 if pi in seen else 1
+        seen.add(pi)
+    first = 0
+    for i, n in enumerate(grp_n):
+        p.grp_first[i], p.grp_n[i] = first, n
+        first += n
+    p.N, p.nblk = N, nblk
+    p.dstH, p.dstW = dH, dW
+    p.IS, p.WS, p.istage_bytes, p.wstage_bytes = IS, WS, istage, wstage
+    p.act_dtype = act_dtype
+    ntiles = geo["tiles_y"] * geo["tiles_x"] * B
+    p.max_ctas = max(1, NUM_SMS // nblk)
+    # gather table [nblk][ncblk][tap][part][j][n][k]
+    Wst = np.stack([t.widx for t in taps], axis=0)                       # [T, Cx, Ntot]
+    Wst = Wst.reshape(ntaps, ncblk, 2, 8, nblk, N).transpose(4, 1, 0, 2, 5, 3)   # [nblk, ncblk, T, j, n, k]
+    if parts == 2:
+        lo = np.where(Wst >= 0, Wst | (1 << 30), -1)
+        Wst = np.stack([Wst, lo], axis=3)                                # [nblk, ncblk, T, part, j, n, k]
+    pack_idx = np.ascontiguousarray(Wst).reshape(-1).astype(np.int32)
+    assert pack_idx.size == nblk * ncblk * ntaps * parts * 2 * N * 8
+    return FpropPlan(g=g, params=p, pack_idx=pack_idx, wpk_elems=int(pack_idx.size), ntiles=ntiles,
+                     info=dict(geo=geo, IS=IS, WS=WS, grp_n=grp_n, P=P, N=N, nblk=nblk))
+
+
+# ------------------------------------------------------------------------------------------ wgrad planning
+@dataclass
+class WgradPlan:
+    g: GConv
+    params: "_lib.WgradParams"
+    dw_elems: int                      # ntaps * N * Cx fp32 accumulators
+    scatter: Tuple[np.ndarray, np.ndarray]   # (param flat index, index into this conv's dw block)
+    info: dict = field(default_factory=dict)
+
+
+def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
+               nc: Optional[int] = None) -> WgradPlan:
+    """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient."""
+    assert g.Cx % 16 == 0 and g.N % 8 == 0
+    parts = 2 if act_dtype == _lib.RD_F32 else 1
+    taps, phases = g.sorted_taps()
+    ntaps = len(taps)
+    gH, gW = g_hw
+    Hb, Wb = -(-gH // g.OS), -(-gW // g.OS)
+    sy = [t.s[0] for t in taps]
+    sx = [t.s[1] for t in taps]
+    sy_min, sx_min = min(sy), min(sx)
+    halo_y, halo_x = max(sy) - sy_min, max(sx) - sx_min
+    Mc = min(_round_up(g.N, 8), 128)
+    ncob = -(-g.N // Mc)
+    if nc is None:
+        nc = min(g.Cx, 64)
+        while g.Cx % nc:
+            nc -= 16
+    Nc = nc
+    ncib = g.Cx // Nc
+    tg_cap = max(1, 512 // Nc)
+    ntg = -(-ntaps // tg_cap)
+    tg_size = -(-ntaps // ntg)
+    # tile search: KS slots per plane, minimise staged bytes per useful pixel subject to >= 2 stages
+    best = None
+    for KS in (32, 64, 96, 128, 192, 256, 384, 512):
+        if KS > max(ks_target, 32):
+            continue
+        for Wl in range(halo_x + 1, min(Wb + halo_x, KS) + 1):
+            Wt = Wl - halo_x
+            Ht = min(KS // Wl, Hb)
+            if Ht < 1:
+                continue
+            xrows = Ht + halo_y
+            xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
+            GPS = g.OS * g.OS * KS
+            XPS = g.S * g.S * xslots
+            g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
+            stage = _round_up(g_bytes + parts * (Nc // 8) * XPS * 16, 128)
+            # the M=128 operand always spans 16 chunk planes; rows past Mc are junk but must stay inside smem
+            pad = max(0, ((parts - 1) * (Mc // 8) + 16) * GPS * 16 - stage)
+            if WGRAD_HEADER + 2 * stage + pad > SMEM_BUDGET:
+                continue
+            ty, tx = -(-Hb // Ht), -(-Wb // Wt)
+            load = (Mc // 8) * GPS + (Nc // 8) * XPS
+            mma = (KS // 16) * tg_size * max(Nc, 32) / 2.0 * (3 if parts == 2 else 1)
+            cost = ty * tx * (max(mma, load * 0.35 * parts) + 300.0)
+            if best is None or cost < best[0]:
+                best = (cost, dict(KS=KS, Wl=Wl, Wt=Wt, Ht=Ht, xrows=xrows, xslots=xslots, g_bytes=g_bytes,
+                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad))
+    if best is None:
+        raise ValueError("no feasible wgrad tile")
+    geo = best[1]
+    NS = 2
+    while NS < 4 and WGRAD_HEADER + (NS + 1) * geo["stage"] + geo["pad"] <= SMEM_BUDGET:
+        NS += 1
+    p = _lib.WgradParams()
+    p.gH, p.gW, p.Cout, p.Sg = gH, gW, g.N, g.OS
+    p.xH, p.xW = x_hw
+    p.Cin, p.Sx = g.Cx, g.S
+    p.B = B
+    p.Hb, p.Wb, p.Ht, p.Wt, p.Wl = Hb, Wb, geo["Ht"], geo["Wt"], geo["Wl"]
+    p.KS = geo["KS"]
+    p.x_plane_rows, p.x_plane_slots = geo["xrows"], geo["xslots"]
+    p.sy_min, p.sx_min = sy_min, sx_min
+    p.tiles_y, p.tiles_x = geo["tiles_y"], geo["tiles_x"]
+    p.ntaps, p.tg_size, p.ntg = ntaps, tg_size, ntg
+    for i, t in enumerate(taps):
+        p.taps[i].g_off = (t.ph[0] * g.OS + t.ph[1]) * geo["KS"]
+        q = t.pl[0] * g.S + t.pl[1]
+        p.taps[i].x_shift = q * geo["xslots"] + (t.s[0] - sy_min) * geo["Wl"] + (t.s[1] - sx_min)
+    p.Mc, p.ncob, p.Nc, p.ncib = Mc, ncob, Nc, ncib
+    p.NS, p.stage_bytes, p.g_bytes = NS, geo["stage"], geo["g_bytes"]
+    p.act_dtype = act_dtype
+    ntiles = geo["tiles_y"] * geo["tiles_x"] * B
+    ctas_other = ncob * ncib * ntg
+    p.max_ctas = max(1, min(ntiles, -(-2 * NUM_SMS // ctas_other)))
+    # scatter table: dw[(t*N + n)*Cx + c]  ->  parameter widx_t[c, n]
+    pi, di = [], []
+    for ti, t in enumerate(taps):
+        c, n = np.nonzero(t.widx >= 0)
+        pi.append(t.widx[c, n].astype(np.int64))
+        di.append(((ti * g.N + n) * g.Cx + c).astype(np.int64))
+    scatter = (np.concatenate(pi), np.concatenate(di))
+    return WgradPlan(g=g, params=p, dw_elems=ntaps * g.N * g.Cx, scatter=scatter,
+                     info=dict(geo=geo, NS=NS, Mc=Mc, Nc=Nc, tg_size=tg_size, ntg=ntg, ntiles=ntiles))

@@ -1,0 +1,129 @@
+// radar_depth_b200.cu -- the single translation unit behind libradar_depth_b200.so: extern "C" launchers
+// (declared in include/radar_depth_b200.h) around the sm_100a kernels in rd_*.cuh.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <algorithm>
+
+#include "rd_common.cuh"
+#include "rd_conv_fprop.cuh"
+#include "rd_conv_wgrad.cuh"
+#include "rd_elementwise.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return RD_OK;
+    return fail(RD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RD_REQUIRE(cond, msg) do { if (!(cond)) return fail(RD_EINVAL, std::string("rd: ") + (msg) + " [" #cond "]"); } while (0)
+
+constexpr int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rd_last_error(void) { return g_err.c_str(); }
+int rd_version(void) { return 1; }
+
+int rd_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(rd_conv_params);
+        case 1: return (int)sizeof(rd_wgrad_params);
+        default: return -1;
+    }
+}
+
+int rd_device_error(void* stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    unsigned int code = 0;
+    if (e == cudaSuccess) {
+        cudaMemcpyFromSymbol(&code, rd::g_rd_device_error, sizeof(code));
+        unsigned int zero = 0;
+        cudaMemcpyToSymbol(rd::g_rd_device_error, &zero, sizeof(zero));
+    } else {
+        g_err = std::string("stream sync: ") + cudaGetErrorString(e);
+        return RD_ECUDA;
+    }
+    return (int)code;
+}
+
+int rd_conv_fprop(const rd_conv_params* p, void* stream) {
+    RD_REQUIRE(p != nullptr, "null params");
+    RD_REQUIRE(p->Cin > 0 && p->Cin % 16 == 0 && p->Cin <= 1024, "Cin must be a multiple of 16 (<= 1024)");
+    RD_REQUIRE(p->N >= 16 && p->N <= 256 && p->N % 16 == 0, "N must be a multiple of 16 in [16,256]");
+    RD_REQUIRE(p->S == 1 || p->S == 2, "S must be 1 or 2");
+    RD_REQUIRE(p->P >= 1 && p->P <= RD_MAX_PHASES && p->MB >= 1, "bad phase / block count");
+    RD_REQUIRE(p->P * p->MB * p->N <= 512, "accumulators exceed 512 TMEM columns");
+    RD_REQUIRE(p->ntaps >= 1 && p->ntaps <= RD_MAX_TAPS && p->ngroups >= 1 && p->ngroups <= RD_MAX_GROUPS, "bad tap program");
+    RD_REQUIRE(p->IS >= 1 && p->IS <= rd::kMaxStages && p->WS >= 1 && p->WS <= rd::kMaxStages, "bad ring depth");
+    RD_REQUIRE(p->src.pitch % 8 == 0 && p->src.coff % 8 == 0 && p->dst.pitch % 8 == 0 && p->dst.coff % 8 == 0, "views must be 8-channel aligned");
+    RD_REQUIRE(p->Wl >= p->Wt && p->Ht * p->Wl <= p->MB * 128, "tile does not fit its accumulator blocks");
+    const int parts = (p->act_dtype == RD_F32) ? 2 : 1;
+    const int PS = p->S * p->S * p->plane_slots;
+    RD_REQUIRE(p->istage_bytes >= parts * 2 * PS * 16 && p->istage_bytes % 128 == 0, "istage_bytes too small / misaligned");
+    int max_shift = 0, max_grp = 0;
+    for (int t = 0; t < p->ntaps; ++t) {
+        RD_REQUIRE(p->taps[t].a_shift >= 0 && p->taps[t].phase >= 0 && p->taps[t].phase < p->P, "bad tap");
+        if (p->taps[t].a_shift > max_shift) max_shift = p->taps[t].a_shift;
+    }
+    RD_REQUIRE(max_shift + p->MB * 128 <= PS, "tap shift reads past the staged tile");
+    int covered = 0;
+    for (int g = 0; g < p->ngroups; ++g) {
+        RD_REQUIRE(p->grp_first[g] == covered && p->grp_n[g] >= 1, "tap groups must partition the tap list in order");
+        covered += p->grp_n[g];
+        if (p->grp_n[g] > max_grp) max_grp = p->grp_n[g];
+    }
+    RD_REQUIRE(covered == p->ntaps, "tap groups must cover all taps");
+    RD_REQUIRE(p->wstage_bytes >= max_grp * parts * p->N * 32 && p->wstage_bytes % 128 == 0, "wstage_bytes too small / misaligned");
+    RD_REQUIRE(p->epi == 0 || (p->epi == 1 && p->zsrc.ptr && p->ep_scale && p->ep_shift), "epi 1 needs zsrc / scale / shift");
+    RD_REQUIRE(p->stats == nullptr || p->stats_stride >= p->nblk * p->N, "stats_stride too small");
+    const long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes;
+    RD_REQUIRE(smem <= kMaxSmem, "shared memory budget exceeded");
+    const int ntiles = p->tiles_y * p->tiles_x * p->B;
+    RD_REQUIRE(ntiles > 0 && p->nblk >= 1, "empty problem");
+    int gx = ntiles;
+    if (p->max_ctas > 0 && gx > p->max_ctas) gx = p->max_ctas;
+    dim3 grid(gx, p->nblk, 1), block(rd::kFpropThreads, 1, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->act_dtype == RD_BF16) {
+        static bool once = false;
+        if (!once) { int rc = set_smem(rd::conv_fprop_kernel<rd::bf16, 1>, kMaxSmem); if (rc) return rc; once = true; }
+        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(*p);
+    } else if (p->act_dtype == RD_F32) {
+        static bool once = false;
+        if (!once) { int rc = set_smem(rd::conv_fprop_kernel<float, 3>, kMaxSmem); if (rc) return rc; once = true; }
+        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(*p);
+    } else {
+        return fail(RD_EINVAL, "rd: bad act_dtype");
+    }
+    return check_cuda(cudaGetLastError(), "conv_fprop launch");
+}
+
+#include "rd_api_rest.inc"
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// rd_conv_fprop.cuh -- implicit-GEMM convolution on tcgen05 (forward convs, data gradients, sub-pixel UpProj).
+//
+// One CTA computes, for a tile of Ht x Wt base output pixels of one image, P output phases x N output channels.
+// The source tile (with halo) is staged ONCE per 16-channel block into shared memory in a "chunk-planar,
+// pixel-linear" layout   [part][8-channel chunk][slot] x 16 B   (slot = row*Wl + col of the halo tile).
+// In that layout every filter tap is a pure linear shift of the slot index, so the A operand of each
+// tcgen05.mma is just a shared-memory matrix descriptor (SWIZZLE_NONE, K-major) whose start address is
+// offset by the tap -- no im2col expansion, no per-tap re-gather: shared-memory fill traffic is 1x instead
+// of taps x.  Accumulator rows are the tile's slots (including Wl-Wt junk columns that are never stored).
+// Stride-2 convolutions stage the source as 4 parity planes (same trick per plane).  The 5x5 convs on the
+// zero-stuffed Unpool output (models.py:13-27,191,198) and stride-2 data gradients run as 4 output phases,
+// each with its own tap list, on the UN-stuffed source.
+//
+// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7 source-tile loaders
+// (fused BatchNorm affine + ReLU/LeakyReLU + bf16 cast, optional hi/lo split for parity mode), warp 8 lane 0
+// UMMA issuer, warp 9 lane 0 weight bulk-copy issuer.  Two mbarrier rings (source tile stages, weight
+// stages) plus a TMEM full/empty pair; the kernel is persistent over tiles.
+#pragma once
+#include "rd_common.cuh"
+#include "rd_tile.cuh"
+#include "../../include/radar_depth_b200.h"
+
+namespace rd {
+
+constexpr int kFpropThreads = 320;
+constexpr int kSmemHeader = 16384;      // barriers, tmem slot, stats, BN vectors
+constexpr int kOffTmemSlot = 256;
+constexpr int kOffStats = 1024;         // float[512]
+constexpr int kOffEpScale = 3072;       // float[256]
+constexpr int kOffEpShift = 4096;       // float[256]
+constexpr int kOffLdScale = 5120;       // float[1024]
+constexpr int kOffLdShift = 9216;       // float[1024]
+constexpr int kMaxStages = 8;
+
+// Butterfly sum over the 32 lanes of 16 per-lane values.  Afterwards lane L holds the full sum of element
+// ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)  (both lanes of an even/odd pair hold the same).
+__device__ __forceinline__ float reduce16_lanes(float* v, int lane) {
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float send = up ? v[i] : v[i + 8];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            v[i] = (up ? v[i + 8] : v[i]) + recv;
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float send = up ? v[i] : v[i + 4];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            v[i] = (up ? v[i + 4] : v[i]) + recv;
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float send = up ? v[i] : v[i + 2];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            v[i] = (up ? v[i + 2] : v[i]) + recv;
+        }
+    }
+    {
+        const bool up = lane & 2;
+        float send = up ? v[0] : v[1];
+        float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        v[0] = (up ? v[1] : v[0]) + recv;
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+__device__ __forceinline__ int reduce16_owner_channel(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+template <typename T, int SPLIT>
+__global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __grid_constant__ rd_conv_params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* in_full = bars;                       // [kMaxStages]
+    uint64_t* in_empty = bars + kMaxStages;
+    uint64_t* w_full = bars + 2 * kMaxStages;
+    uint64_t* w_empty = bars + 3 * kMaxStages;
+    uint64_t* tmem_full = bars + 4 * kMaxStages;
+    uint64_t* tmem_empty = bars + 4 * kMaxStages + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
+    float* stats_s = reinterpret_cast<float*>(smem + kOffStats);
+    float* ep_sc = reinterpret_cast<float*>(smem + kOffEpScale);
+    float* ep_sh = reinterpret_cast<float*>(smem + kOffEpShift);
+    float* ld_sc = reinterpret_cast<float*>(smem + kOffLdScale);
+    float* ld_sh = reinterpret_cast<float*>(smem + kOffLdShift);
+    uint8_t* a_ring = smem + kSmemHeader;
+    uint8_t* w_ring = a_ring + (size_t)p.IS * p.istage_bytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = blockIdx.y;                       // N block
+    constexpr int PARTS = (SPLIT == 3) ? 2 : 1;
+    const int ncblk = p.Cin >> 4;
+    const int tiles_per_img = p.tiles_y * p.tiles_x;
+    const int ntiles = tiles_per_img * p.B;
+
+    // ---- one-time setup
+    if (tid == 0) {
+        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], 4); mbar_init(&in_empty[i], 1); }
+        for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 512; i += kFpropThreads) stats_s[i] = 0.f;
+    if (p.ld_scale) {
+        for (int i = tid; i < p.Cin; i += kFpropThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
+    }
+    if (p.epi == 1) {
+        for (int i = tid; i < p.N; i += kFpropThreads) { ep_sc[i] = p.ep_scale[nb * p.N + i]; ep_sh[i] = p.ep_shift[nb * p.N + i]; }
+    }
+    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        // ================= source tile loaders =================
+        PipeState st(p.IS);
+        const int ltid = tid - 128;
+        TileSrc ts;
+        ts.ptr = p.src.ptr; ts.pitch = p.src.pitch; ts.coff = p.src.coff; ts.H = p.srcH; ts.W = p.srcW; ts.S = p.S;
+        ts.plane_slots = p.plane_slots; ts.plane_rows = p.plane_rows; ts.Wl = p.Wl; ts.oy0 = p.sy_min; ts.ox0 = p.sx_min;
+        ts.vrows = p.plane_rows; ts.vcols = p.Wl;
+        ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int img = tile / tiles_per_img;
+            const int trem = tile - img * tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * p.Ht, x0 = tx * p.Wt;
+            for (int c = 0; c < ncblk; ++c) {
+                mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
+                stage_tile<T, SPLIT>(ts, a_ring + (size_t)st.stage * p.istage_bytes, img, y0, x0, c * 16, 2, ltid, 128);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&in_full[st.stage]);
+                st.advance();
+            }
+        }
+    } else if (warp == 9) {
+        // ================= weight bulk-copy issuer =================
+        if (lane == 0) {
+            PipeState st(p.WS);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
+            const size_t tap_bytes = (size_t)PARTS * p.N * 32;                      // [part][2][N][8] bf16
+            const size_t cblk_bytes = tap_bytes * p.ntaps;
+            const size_t nblk_bytes = cblk_bytes * ncblk;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < ncblk; ++c) {
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        mbar_wait(&w_empty[st.stage], st.phase ^ 1, 0x200 + st.stage);
+                        const uint32_t bytes = (uint32_t)(tap_bytes * p.grp_n[g]);
+                        mbar_arrive_expect_tx(&w_full[st.stage], bytes);
+                        bulk_g2s(w_ring + (size_t)st.stage * p.wstage_bytes,
+                                 wsrc + nb * nblk_bytes + c * cblk_bytes + p.grp_first[g] * tap_bytes, bytes,
+                                 &w_full[st.stage]);
+                        st.advance();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 8) {
+        // ================= UMMA issuer =================
+        if (lane == 0) {
+            PipeState si(p.IS), sw(p.WS);
+            const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+            const uint32_t PS = (uint32_t)(p.S * p.S * p.plane_slots);
+            const uint32_t a_lbo = PS * 16u;
+            const uint32_t b_lbo = (uint32_t)p.N * 16u;
+            const uint32_t tap_bytes = (uint32_t)PARTS * p.N * 32u;
+            uint32_t tile_iter = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+                mbar_wait(tmem_empty, (tile_iter & 1) ^ 1, 0x300);
+                tc_fence_after();
+                for (int c = 0; c < ncblk; ++c) {
+                    mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_ring + (size_t)si.stage * p.istage_bytes);
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
+                        tc_fence_after();
+                        const uint32_t w_base = smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes);
+                        for (int tl = 0; tl < p.grp_n[g]; ++tl) {
+                            const rd_tap tp = p.taps[p.grp_first[g] + tl];
+                            const uint32_t fresh = (c == 0 && tp.first) ? 1u : 0u;
+                            for (int mb = 0; mb < p.MB; ++mb) {
+                                const uint32_t d = tmem_base + (uint32_t)((tp.phase * p.MB + mb) * p.N);
+                                const uint32_t a_hi = a_base + ((uint32_t)(tp.a_shift + mb * 128) << 4);
+                                const uint32_t b_hi = w_base + (uint32_t)tl * tap_bytes;
+                                const uint64_t da = make_smem_desc(a_hi, a_lbo, 128);
+                                const uint64_t db = make_smem_desc(b_hi, b_lbo, 128);
+                                umma_bf16(d, da, db, idesc, fresh ? 0u : 1u);
+                                if (SPLIT == 3) {
+                                    const uint64_t da_lo = make_smem_desc(a_hi + 2u * a_lbo, a_lbo, 128);
+                                    const uint64_t db_lo = make_smem_desc(b_hi + (uint32_t)p.N * 32u, b_lbo, 128);
+                                    umma_bf16(d, da, db_lo, idesc, 1u);
+                                    umma_bf16(d, da_lo, db, idesc, 1u);
+                                }
+                            }
+                        }
+                        umma_commit(&w_empty[sw.stage]);
+                        sw.advance();
+                    }
+                    umma_commit(&in_empty[si.stage]);
+                    si.advance();
+                }
+                umma_commit(tmem_full);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 0-3) =================
+        T* dst = reinterpret_cast<T*>(p.dst.ptr);
+        const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
+        const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
+        const bool want_stats = p.stats != nullptr;
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+            const int img = tile / tiles_per_img;
+            const int trem = tile - img * tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * p.Ht, x0 = tx * p.Wt;
+            mbar_wait(tmem_full, tile_iter & 1, 0x400);
+            tc_fence_after();
+            for (int cc = 0; cc < (p.N >> 4); ++cc) {
+                float s1[16], s2[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+                for (int ph = 0; ph < p.P; ++ph) {
+                    for (int mb = 0; mb < p.MB; ++mb) {
+                        const int m = mb * 128 + warp * 32 + lane;
+                        const int ly = m / p.Wl, lx = m - ly * p.Wl;
+                        const int oy = y0 + ly, ox = x0 + lx;
+                        const int fy = oy * p.OS + p.phase_y[ph], fx = ox * p.OS + p.phase_x[ph];
+                        const bool valid = ly < p.Ht && lx < p.Wt && oy < p.Hb && ox < p.Wb && fy < p.dstH && fx < p.dstW;
+                        float v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ph * p.MB + mb) * p.N + cc * 16), v);
+                        if (valid) {
+                            const size_t pix = ((size_t)img * p.dstH + fy) * p.dstW + fx;
+                            const int ch = nb * p.N + cc * 16;
+                            if (addend) {
+                                float a[16];
+                                const T* ap = addend + pix * p.addend.pitch + p.addend.coff + ch;
+                                Act<T>::load8(ap, a); Act<T>::load8(ap + 8, a + 8);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] += a[i];
+                            }
+                            if (p.epi == 1) {
+                                float z[16];
+                                const T* zp = zsrc + pix * p.zsrc.pitch + p.zsrc.coff + ch;
+                                Act<T>::load8(zp, z); Act<T>::load8(zp + 8, z + 8);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float y = fmaf(z[i], ep_sc[cc * 16 + i], ep_sh[cc * 16 + i]);
+                                    const float g = y > 0.f ? v[i] : v[i] * p.ep_slope;
+                                    v[i] = g;
+                                    s1[i] += g;
+                                    s2[i] += g * z[i];
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] += v[i] * v[i]; }
+                            }
+                            T* dp = dst + pix * p.dst.pitch + p.dst.coff + ch;
+                            Act<T>::store8(dp, v); Act<T>::store8(dp + 8, v + 8);
+                        }
+                    }
+                }
+                if (want_stats) {
+                    const float r1 = reduce16_lanes(s1, lane);
+                    const float r2 = reduce16_lanes(s2, lane);
+                    if ((lane & 1) == 0) {
+                        const int chn = cc * 16 + reduce16_owner_channel(lane);
+                        atomicAdd(&stats_s[chn], r1);
+                        atomicAdd(&stats_s[256 + chn], r2);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (want_stats) {
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            for (int i = tid; i < p.N; i += 128) {
+                atomicAdd(&p.stats[nb * p.N + i], (double)stats_s[i]);
+                atomicAdd(&p.stats[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace rd

@@ -1,0 +1,159 @@
+// rd_conv_wgrad.cuh -- convolution weight gradient on tcgen05.
+//
+// dw[tap][co][ci] = sum over pixels of gy[pixel][co] * x[pixel + tap][ci].  The contraction index is the pixel,
+// so the gradient tile (A, M = output channels) and the source halo tile (B, N = input channels) are both
+// staged in the same chunk-planar pixel-linear layout as the forward kernel and handed to tcgen05.mma as
+// MN-major SWIZZLE_NONE operands: the 8 channels of a 16-byte unit are 8 consecutive M (or N) indices, the
+// slot index is K.  A tap is again only a start-address shift of the B descriptor.  Every tap owns a TMEM
+// accumulator [128 x Nc]; a CTA walks its share of the pixel tiles with the accumulators resident and
+// finally adds them into dw with vector fp32 reductions (REDG.128).
+//
+// Warp roles (288 threads): warps 0-3 epilogue, warps 4-7 loaders (gy raw; x with fused BN+activation),
+// warp 8 lane 0 UMMA issuer (also owns TMEM alloc/dealloc).
+#pragma once
+#include "rd_common.cuh"
+#include "rd_tile.cuh"
+#include "../../include/radar_depth_b200.h"
+
+namespace rd {
+
+constexpr int kWgradThreads = 288;
+constexpr int kWgSmemHeader = 10240;     // barriers + tmem slot + BN scale/shift (2 x 1024 floats)
+constexpr int kWgOffTmemSlot = 256;
+constexpr int kWgOffLdScale = 1024;
+constexpr int kWgOffLdShift = 5120;
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+template <typename T, int SPLIT>
+__global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ rd_wgrad_params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + 8;
+    uint64_t* tmem_full = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgOffTmemSlot);
+    float* ld_sc = reinterpret_cast<float*>(smem + kWgOffLdScale);
+    float* ld_sh = reinterpret_cast<float*>(smem + kWgOffLdShift);
+    uint8_t* ring = smem + kWgSmemHeader;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cob = blockIdx.y;
+    const int cib = blockIdx.z / p.ntg;
+    const int tg = blockIdx.z - cib * p.ntg;
+    const int t0 = tg * p.tg_size;
+    const int T_n = min(p.tg_size, p.ntaps - t0);
+    const int co0 = cob * p.Mc, ci0 = cib * p.Nc;
+    const int tiles_per_img = p.tiles_y * p.tiles_x;
+    const int ntiles = tiles_per_img * p.B;
+    const int g_chunks = p.Mc >> 3, x_chunks = p.Nc >> 3;
+    const int GPS = p.Sg * p.Sg * p.KS;
+    const int XPS = p.Sx * p.Sx * p.x_plane_slots;
+
+    if (tid == 0) {
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (p.ld_scale) {
+        for (int i = tid; i < p.Cin; i += kWgradThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        // ================= loaders =================
+        PipeState st(p.NS);
+        const int ltid = tid - 128;
+        TileSrc tg_, tx_;
+        tg_.ptr = p.gy.ptr; tg_.pitch = p.gy.pitch; tg_.coff = p.gy.coff; tg_.H = p.gH; tg_.W = p.gW; tg_.S = p.Sg;
+        tg_.plane_slots = p.KS; tg_.plane_rows = p.Ht; tg_.Wl = p.Wl; tg_.oy0 = 0; tg_.ox0 = 0;
+        tg_.vrows = p.Ht; tg_.vcols = p.Wt; tg_.sc = nullptr; tg_.sh = nullptr; tg_.slope = 1.f;
+        tx_.ptr = p.x.ptr; tx_.pitch = p.x.pitch; tx_.coff = p.x.coff; tx_.H = p.xH; tx_.W = p.xW; tx_.S = p.Sx;
+        tx_.plane_slots = p.x_plane_slots; tx_.plane_rows = p.x_plane_rows; tx_.Wl = p.Wl; tx_.oy0 = p.sy_min; tx_.ox0 = p.sx_min;
+        tx_.vrows = p.x_plane_rows; tx_.vcols = p.Wl;
+        tx_.sc = p.ld_scale ? ld_sc : nullptr; tx_.sh = ld_sh; tx_.slope = p.ld_slope;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int img = tile / tiles_per_img;
+            const int trem = tile - img * tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * p.Ht, x0 = tx * p.Wt;
+            mbar_wait(&empty[st.stage], st.phase ^ 1, 0x500 + st.stage);
+            uint8_t* sbase = ring + (size_t)st.stage * p.stage_bytes;
+            stage_tile<T, SPLIT>(tg_, sbase, img, y0, x0, co0, g_chunks, ltid, 128);
+            stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, img, y0, x0, ci0, x_chunks, ltid, 128);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st.stage]);
+            st.advance();
+        }
+    } else if (warp == 8) {
+        // ================= UMMA issuer =================
+        if (lane == 0) {
+            PipeState st(p.NS);
+            const uint32_t idesc = make_idesc_bf16(128, p.Nc, 1, 1);
+            const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = (uint32_t)XPS * 16u;
+            const int KG = p.KS >> 4;
+            bool first_tile = true;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
+                tc_fence_after();
+                const uint32_t g_base = smem_u32(ring + (size_t)st.stage * p.stage_bytes);
+                const uint32_t x_base = g_base + (uint32_t)p.g_bytes;
+                for (int kg = 0; kg < KG; ++kg) {
+                    const uint32_t acc = (first_tile && kg == 0) ? 0u : 1u;
+                    for (int tl = 0; tl < T_n; ++tl) {
+                        const rd_wtap tp = p.taps[t0 + tl];
+                        const uint32_t a = g_base + ((uint32_t)(tp.g_off + kg * 16) << 4);
+                        const uint32_t b = x_base + ((uint32_t)(tp.x_shift + kg * 16) << 4);
+                        const uint32_t d = tmem_base + (uint32_t)(tl * p.Nc);
+                        const uint64_t da = make_smem_desc(a, 128, g_sbo);
+                        const uint64_t db = make_smem_desc(b, 128, x_sbo);
+                        umma_bf16(d, da, db, idesc, acc);
+                        if (SPLIT == 3) {
+                            const uint64_t da_lo = make_smem_desc(a + (uint32_t)g_chunks * g_sbo, 128, g_sbo);
+                            const uint64_t db_lo = make_smem_desc(b + (uint32_t)x_chunks * x_sbo, 128, x_sbo);
+                            umma_bf16(d, da, db_lo, idesc, 1u);
+                            umma_bf16(d, da_lo, db, idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(&empty[st.stage]);
+                st.advance();
+                first_tile = false;
+            }
+            umma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 0-3): TMEM -> fp32 reductions into dw =================
+        const bool has_work = (int)blockIdx.x < ntiles;
+        mbar_wait(tmem_full, 0, 0x600);
+        tc_fence_after();
+        const int row = warp * 32 + lane;                 // output channel within the block
+        const bool valid = has_work && row < p.Mc && (co0 + row) < p.Cout;
+        for (int tl = 0; tl < T_n; ++tl) {
+            float* out = p.dw + ((size_t)(t0 + tl) * p.Cout + (co0 + row)) * p.Cin + ci0;
+            for (int cc = 0; cc < (p.Nc >> 4); ++cc) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * p.Nc + cc * 16), v);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) red_add_v4(out + cc * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace rd

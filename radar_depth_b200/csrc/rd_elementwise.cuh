@@ -1,0 +1,586 @@
+// rd_elementwise.cuh -- the HBM-bound kernels around the tensor-core convolutions: input packing, BatchNorm
+// statistics finalisation, residual joins, BatchNorm backward, max-pool, head conv + bilinear, losses,
+// SID radar filter, weight packing / gradient unpacking, fused SGD.  All NHWC, 8 channels (16 B for bf16)
+// per thread per access; reductions go warp -> shared -> one fp64 atomic per channel per block.
+#pragma once
+#include "rd_common.cuh"
+
+namespace rd {
+
+struct VView { void* ptr; int pitch; int coff; };   // same as rd_view, device-side
+
+template <typename T>
+__device__ __forceinline__ const T* vptr(const VView& v, size_t pix, int c) {
+    return reinterpret_cast<const T*>(v.ptr) + pix * v.pitch + v.coff + c;
+}
+template <typename T>
+__device__ __forceinline__ T* vptr_w(const VView& v, size_t pix, int c) {
+    return reinterpret_cast<T*>(v.ptr) + pix * v.pitch + v.coff + c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// input_pack: NCHW fp32 [B,C,H,W] -> space-to-depth NHWC [B,ceil(H/2),ceil(W/2),4*Cs], channel = (py*2+px)*Cs + c.
+// Replaces the reference's x[:, :3] / x[:, 3:] slicing (models.py:633,643) and makes both 7x7 stride-2 stems a
+// single stride-1 4x4-tap convolution over 16 (or 32) channels.
+template <typename T>
+__global__ void input_pack_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cs) {
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+    const size_t total = (size_t)B * H2 * W2 * 4;      // one thread per (pixel, parity)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i & 3);
+        const size_t pix = i >> 2;
+        const int ox = (int)(pix % W2);
+        const int oy = (int)((pix / W2) % H2);
+        const int b = (int)(pix / ((size_t)W2 * H2));
+        const int iy = oy * 2 + (q >> 1), ix = ox * 2 + (q & 1);
+        const bool ok = iy < H && ix < W;
+        T* o = out + pix * (size_t)(4 * Cs) + q * Cs;
+        for (int c = 0; c < Cs; ++c) {
+            float v = 0.f;
+            if (ok && c < C) v = x[(((size_t)b * C + c) * H + iy) * W + ix];
+            Act<T>::st(o + c, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bn_finalize: batch statistics -> fused scale/shift, saved mean/invstd, running-stat update.
+// nn.BatchNorm2d train/eval semantics (reference models.py:540 etc.): biased variance
+// normalises, unbiased variance goes into running_var, momentum 0.1, eps 1e-5, num_batches_tracked += 1.
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, long long* nbt, int C, int training,
+                                   float momentum, float eps, float* scale, float* shift, float* save_mean,
+                                   float* save_invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt) *nbt += 1;
+    if (c >= C) return;
+    float mean, invstd;
+    if (training) {
+        const double m = sum[c] / count;
+        double var = sumsq[c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    } else {
+        mean = running_mean[c];
+        invstd = rsqrtf(running_var[c] + eps);
+    }
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+}
+
+// bn_bwd_finalize: from sum(g), sum(g*z) -> dgamma, dbeta (accumulated into the gradient arena) and the three
+// coefficients of dz = A*g + Bz*z + Cc  (autograd of nn.BatchNorm2d in training mode).
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gz, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                       const float* __restrict__ save_invstd, int C, int training, float* dgamma,
+                                       float* dbeta, float* coefA, float* coefB, float* coefC) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double sg = sum_g[c], sgz = sum_gz[c];
+    const double mu = save_mean[c], r = save_invstd[c], g = gamma[c];
+    const double dg = r * (sgz - mu * sg);
+    dgamma[c] += (float)dg;
+    dbeta[c] += (float)sg;
+    if (training) {
+        coefA[c] = (float)(g * r);
+        coefB[c] = (float)(-g * r * r * dg / count);
+        coefC[c] = (float)(-g * r * sg / count + g * r * r * mu * dg / count);
+    } else {   // eval mode: statistics are constants
+        coefA[c] = (float)(g * r);
+        coefB[c] = 0.f;
+        coefC[c] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level per-channel reduction helper: each thread owns one 8-channel group (fixed for its lifetime) and
+// NA accumulators per channel; smem partials then one fp64 atomic per channel per block.
+template <int NA>
+__device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, int C, float* red_s, double* const* outs) {
+    // red_s: [NA][C] floats, zeroed here
+    for (int i = threadIdx.x; i < NA * C; i += blockDim.x) red_s[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&red_s[a * C + cg * 8 + k], acc[a][k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < NA * C; i += blockDim.x) {
+        const int a = i / C, c = i - a * C;
+        atomicAdd(outs[a] + c, (double)red_s[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bn_add_act: out = act( z*sc + sh + identity )   -- the residual join of BasicBlock (models.py:104-110) and
+// UpProjModule (models.py:205-208).  identity is either a materialised activation (id_sc == nullptr) or another
+// raw conv output with its own BN (downsample branch / bottom branch).  With idv.ptr == nullptr: plain BN+act.
+template <typename T>
+__global__ void bn_add_act_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, VView idv,
+                                  const float* __restrict__ id_sc, const float* __restrict__ id_sh, VView out,
+                                  size_t npix, int C, float slope) {
+    const int groups = C >> 3;
+    const size_t total = npix * groups;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / groups;
+        const int c = (int)(i - pix * groups) * 8;
+        float v[8], r[8];
+        Act<T>::load8(vptr<T>(z, pix, c), v);
+        if (idv.ptr) Act<T>::load8(vptr<T>(idv, pix, c), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float y = fmaf(v[k], sc[c + k], sh[c + k]);
+            if (idv.ptr) y += id_sc ? fmaf(r[k], id_sc[c + k], id_sh[c + k]) : r[k];
+            v[k] = y > 0.f ? y : y * slope;
+        }
+        Act<T>::store8(vptr_w<T>(out, pix, c), v);
+    }
+}
+
+// join_bwd: g = dout * act'(out);  stats: sum g, sum g*z (main BN) and optionally sum g*zid (identity-branch BN).
+// Writes g (may alias dout).  Autograd of the residual join + ReLU.
+template <typename T>
+__global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
+                                double* sum_g, double* sum_gz, double* sum_gzid) {
+    extern __shared__ float red_s[];
+    const int groups = C >> 3;
+    const int cg = threadIdx.x % groups;
+    const int ppb = blockDim.x / groups;               // pixels per block-iteration
+    const int pl = threadIdx.x / groups;
+    float acc[3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    if (pl < ppb) {
+        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += (size_t)gridDim.x * ppb) {
+            float d[8], o[8], zz[8], zi[8];
+            const int c = cg * 8;
+            Act<T>::load8(vptr<T>(dout, pix, c), d);
+            Act<T>::load8(vptr<T>(outv, pix, c), o);
+            Act<T>::load8(vptr<T>(z, pix, c), zz);
+            if (zid.ptr) Act<T>::load8(vptr<T>(zid, pix, c), zi);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gg = o[k] > 0.f ? d[k] : d[k] * slope;
+                d[k] = gg;
+                acc[0][k] += gg;
+                acc[1][k] += gg * zz[k];
+                if (zid.ptr) acc[2][k] += gg * zi[k];
+            }
+            Act<T>::store8(vptr_w<T>(g, pix, c), d);
+        }
+    }
+    double* outs[3] = {sum_g, sum_gz, sum_gzid};
+    if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs);
+    else block_channel_reduce<2>(acc, cg, C, red_s, outs);
+}
+
+// bn_bwd_apply: dz = A*g + Bz*z + Cc (per channel).  dz may alias g.
+template <typename T>
+__global__ void bn_bwd_apply_kernel(VView g, VView z, VView dz, const float* __restrict__ A, const float* __restrict__ Bz,
+                                    const float* __restrict__ Cc, size_t npix, int C) {
+    const int groups = C >> 3;
+    const size_t total = npix * groups;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / groups;
+        const int c = (int)(i - pix * groups) * 8;
+        float gv[8], zv[8];
+        Act<T>::load8(vptr<T>(g, pix, c), gv);
+        Act<T>::load8(vptr<T>(z, pix, c), zv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[k] = fmaf(A[c + k], gv[k], fmaf(Bz[c + k], zv[k], Cc[c + k]));
+        Act<T>::store8(vptr_w<T>(dz, pix, c), gv);
+    }
+}
+
+// grad_stats: sum g, sum g*z over a tensor whose gradient g is already final (no activation mask), e.g. the
+// BN that follows conv_fusion / conv2 when the gradient arrives from an elementwise producer.
+template <typename T>
+__global__ void grad_stats_kernel(VView g, VView z, size_t npix, int C, double* sum_g, double* sum_gz) {
+    extern __shared__ float red_s[];
+    const int groups = C >> 3;
+    const int cg = threadIdx.x % groups;
+    const int ppb = blockDim.x / groups;
+    const int pl = threadIdx.x / groups;
+    float acc[2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    if (pl < ppb) {
+        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += (size_t)gridDim.x * ppb) {
+            float d[8], zz[8];
+            Act<T>::load8(vptr<T>(g, pix, cg * 8), d);
+            Act<T>::load8(vptr<T>(z, pix, cg * 8), zz);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc[0][k] += d[k]; acc[1][k] += d[k] * zz[k]; }
+        }
+    }
+    double* outs[2] = {sum_g, sum_gz};
+    block_channel_reduce<2>(acc, cg, C, red_s, outs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// maxpool 3x3 s2 p1 over act(bn(z)) (models.py:546-547,564-565).  Channels [0,split) use slope_a (ReLU),
+// [split,C) slope_b (LeakyReLU 0.2) and go to a second destination.  The arg-max (first maximum in row-major
+// window order, ATen's tie rule -- SURVEY Appendix B) is stored as one byte per output element.
+template <typename T>
+__global__ void maxpool_fwd_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W,
+                                   int C, int split, float slope_a, float slope_b, VView outa, VView outb,
+                                   uint8_t* __restrict__ amax, int Ho, int Wo) {
+    const int groups = C >> 3;
+    const size_t total = (size_t)B * Ho * Wo * groups;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / groups;
+        const int c = (int)(i - pix * groups) * 8;
+        const int ox = (int)(pix % Wo);
+        const int oy = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((size_t)Wo * Ho));
+        const float slope = c < split ? slope_a : slope_b;
+        float best[8];
+        int bi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+        bool any = false;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy * 2 - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox * 2 - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                float v[8];
+                Act<T>::load8(vptr<T>(z, ((size_t)b * H + iy) * W + ix, c), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float y = fmaf(v[k], sc[c + k], sh[c + k]);
+                    y = y > 0.f ? y : y * slope;
+                    y = Act<T>::round(y);     // compare what a materialised activation would hold
+                    if (!any || y > best[k] || y != y) { best[k] = y; bi[k] = dy * 3 + dx; }
+                }
+                any = true;
+            }
+        }
+        if (c < split) Act<T>::store8(vptr_w<T>(outa, pix, c), best);
+        else Act<T>::store8(vptr_w<T>(outb, pix, c - split), best);
+        uint2 packed;
+        packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+        packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+        *reinterpret_cast<uint2*>(amax + pix * C + c) = packed;
+    }
+}
+
+// maxpool_bwd: g[b,iy,ix,c] = act'(y) * sum over the <=4 windows containing (iy,ix) whose arg-max is this pixel
+// of dpool; plus the BN-backward statistics sum g, sum g*z.  blockDim must be a multiple of C/8.
+template <typename T>
+__global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restrict__ amax, VView z,
+                                   const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
+                                   int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
+                                   double* sum_gz) {
+    extern __shared__ float red_s[];
+    const int groups = C >> 3;
+    const int cg = threadIdx.x % groups;
+    const int ppb = blockDim.x / groups;
+    const int pl = threadIdx.x / groups;
+    const int c = cg * 8;
+    const float slope = c < split ? slope_a : slope_b;
+    float acc[2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    const size_t npix = (size_t)B * H * W;
+    if (pl < ppb) {
+        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += (size_t)gridDim.x * ppb) {
+            const int ix = (int)(pix % W);
+            const int iy = (int)((pix / W) % H);
+            const int b = (int)(pix / ((size_t)W * H));
+            float gsum[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gsum[k] = 0.f;
+            // windows (oy,ox) with oy*2-1 <= iy <= oy*2+1
+            const int oy_lo = iy >> 1, oy_hi = (iy + 1) >> 1;
+            const int ox_lo = ix >> 1, ox_hi = (ix + 1) >> 1;
+            for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+                if (oy >= Ho) continue;
+                const int dy = iy - (oy * 2 - 1);
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                    if (ox >= Wo) continue;
+                    const int dx = ix - (ox * 2 - 1);
+                    const int code = dy * 3 + dx;
+                    const size_t op = ((size_t)b * Ho + oy) * Wo + ox;
+                    const uint2 am = *reinterpret_cast<const uint2*>(amax + op * C + c);
+                    float d[8];
+                    if (c < split) Act<T>::load8(vptr<T>(dpa, op, c), d);
+                    else Act<T>::load8(vptr<T>(dpb, op, c - split), d);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int a = (int)(((k < 4 ? am.x : am.y) >> ((k & 3) * 8)) & 0xFF);
+                        if (a == code) gsum[k] += d[k];
+                    }
+                }
+            }
+            float zz[8];
+            Act<T>::load8(vptr<T>(z, pix, c), zz);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float y = fmaf(zz[k], sc[c + k], sh[c + k]);
+                const float gg = y > 0.f ? gsum[k] : gsum[k] * slope;
+                gsum[k] = gg;
+                acc[0][k] += gg;
+                acc[1][k] += gg * zz[k];
+            }
+            Act<T>::store8(vptr_w<T>(g, pix, c), gsum);
+        }
+    }
+    double* outs[2] = {sum_g, sum_gz};
+    block_channel_reduce<2>(acc, cg, C, red_s, outs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: conv3 3x3 16->1 (models.py:587,661) as a bandwidth kernel, fp32 output at decoder resolution.
+template <typename T>
+__global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16][3][3] OIHW with O=1*/, int B, int H, int W,
+                                     float* __restrict__ out) {
+    __shared__ float ws[144];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const size_t total = (size_t)B * H * W;
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(pix % W);
+        const int oy = (int)((pix / W) % H);
+        const int b = (int)(pix / ((size_t)W * H));
+        float acc = 0.f;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = oy + dy - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = ox + dx - 1;
+                if (ix < 0 || ix >= W) continue;
+                float v[16];
+                const size_t ip = ((size_t)b * H + iy) * W + ix;
+                Act<T>::load8(vptr<T>(x, ip, 0), v);
+                Act<T>::load8(vptr<T>(x, ip, 8), v + 8);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc = fmaf(v[c], ws[c * 9 + dy * 3 + dx], acc);
+            }
+        }
+        out[pix] = acc;
+    }
+}
+
+// head_conv_bwd: dx[p][c] = sum_tap dc3[p - tap] * w[c][tap];  dw[c][tap] += sum_p dc3[p] * x[p + tap][c].
+template <typename T>
+__global__ void head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w, int B, int H, int W,
+                                     VView dx, float* dw /*[144]*/) {
+    __shared__ float ws[144];
+    __shared__ float dws[144];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) { ws[i] = w[i]; dws[i] = 0.f; }
+    __syncthreads();
+    const size_t total = (size_t)B * H * W;
+    float wacc[9][16];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) wacc[t][c] = 0.f;
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(pix % W);
+        const int oy = (int)((pix / W) % H);
+        const int b = (int)(pix / ((size_t)W * H));
+        // data gradient at this pixel (gather form) and weight gradient (this pixel's x against shifted dc3)
+        float xv[16], dxa[16];
+        Act<T>::load8(vptr<T>(x, pix, 0), xv);
+        Act<T>::load8(vptr<T>(x, pix, 8), xv + 8);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dxa[c] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int dx_ = 0; dx_ < 3; ++dx_) {
+                // output pixel q = p - (dy-1, dx-1) used input p with tap (dy,dx)
+                const int qy = oy - (dy - 1), qx = ox - (dx_ - 1);
+                if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
+                const float d = dc3[((size_t)b * H + qy) * W + qx];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    dxa[c] = fmaf(d, ws[c * 9 + dy * 3 + dx_], dxa[c]);
+                    wacc[dy * 3 + dx_][c] = fmaf(d, xv[c], wacc[dy * 3 + dx_][c]);
+                }
+            }
+        }
+        Act<T>::store8(vptr_w<T>(dx, pix, 0), dxa);
+        Act<T>::store8(vptr_w<T>(dx, pix, 8), dxa + 8);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float s = warp_sum(wacc[t][c]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&dws[c * 9 + t], s);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) atomicAdd(&dw[i], dws[i]);
+}
+
+// bilinear, align_corners=True (models.py:588,662): src = dst * (in-1)/(out-1).
+__global__ void bilinear_fwd_kernel(const float* __restrict__ in, int B, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
+    const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    const size_t total = (size_t)B * Ho * Wo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        const int oy = (int)((i / Wo) % Ho);
+        const int b = (int)(i / ((size_t)Wo * Ho));
+        const float sy = ry * oy, sx = rx * ox;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const float* p = in + (size_t)b * Hi * Wi;
+        const float v = (1.f - ly) * ((1.f - lx) * p[(size_t)y0 * Wi + x0] + lx * p[(size_t)y0 * Wi + x1]) +
+                        ly * ((1.f - lx) * p[(size_t)y1 * Wi + x0] + lx * p[(size_t)y1 * Wi + x1]);
+        out[i] = v;
+    }
+}
+
+// bilinear_bwd (gather form, deterministic): din[b,iy,ix] = sum over output pixels whose 2x2 footprint holds it.
+__global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, float* __restrict__ din, int Ho, int Wo) {
+    const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    const size_t total = (size_t)B * Hi * Wi;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % Wi);
+        const int iy = (int)((i / Wi) % Hi);
+        const int b = (int)(i / ((size_t)Wi * Hi));
+        // candidate output rows: those with floor(ry*oy) in {iy-1, iy}
+        int oy_lo, oy_hi, ox_lo, ox_hi;
+        if (ry > 0.f) { oy_lo = max(0, (int)floorf((iy - 1) / ry) - 1); oy_hi = min(Ho - 1, (int)ceilf((iy + 1) / ry) + 1); }
+        else { oy_lo = 0; oy_hi = Ho - 1; }
+        if (rx > 0.f) { ox_lo = max(0, (int)floorf((ix - 1) / rx) - 1); ox_hi = min(Wo - 1, (int)ceilf((ix + 1) / rx) + 1); }
+        else { ox_lo = 0; ox_hi = Wo - 1; }
+        float acc = 0.f;
+        const float* p = dout + (size_t)b * Ho * Wo;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            const float sy = ry * oy;
+            const int y0 = (int)sy;
+            const int y1 = min(y0 + 1, Hi - 1);
+            const float ly = sy - y0;
+            float wy = 0.f;
+            if (y0 == iy) wy += 1.f - ly;
+            if (y1 == iy) wy += ly;
+            if (wy == 0.f) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                const float sx = rx * ox;
+                const int x0 = (int)sx;
+                const int x1 = min(x0 + 1, Wi - 1);
+                const float lx = sx - x0;
+                float wx = 0.f;
+                if (x0 == ix) wx += 1.f - lx;
+                if (x1 == ix) wx += lx;
+                if (wx == 0.f) continue;
+                acc = fmaf(wy * wx, p[(size_t)oy * Wo + ox], acc);
+            }
+        }
+        din[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaskedL1Loss (criteria_new.py:44-54): mean |target - pred| over target > 0.  No boolean gather, no host sync:
+// acc[0] += sum, acc[1] += count (fp64), then a 1-thread finalize writes the fp32 scalar.
+__global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* acc) {
+    float s = 0.f, cnt = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = target[i];
+        if (t > 0.f) { s += fabsf(t - pred[i]); cnt += 1.f; }
+    }
+    s = warp_sum(s);
+    cnt = warp_sum(cnt);
+    __shared__ float ss[32], sc_[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { ss[w] = s; sc_[w] = cnt; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        s = l < nw ? ss[l] : 0.f;
+        cnt = l < nw ? sc_[l] : 0.f;
+        s = warp_sum(s);
+        cnt = warp_sum(cnt);
+        if (l == 0) { atomicAdd(&acc[0], (double)s); atomicAdd(&acc[1], (double)cnt); }
+    }
+}
+__global__ void l1_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] / acc[1]); }   // 0/0 -> NaN like the reference
+
+// grad_pred = gout * (-sign(target - pred)) / count on valid pixels, 0 elsewhere.
+__global__ void l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n,
+                              const double* __restrict__ acc, const float* __restrict__ gout, float* __restrict__ gpred,
+                              int accumulate) {
+    const float k = (*gout) / (float)acc[1];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = target[i];
+        float g = 0.f;
+        if (t > 0.f) {
+            const float d = t - pred[i];
+            g = d > 0.f ? -k : (d < 0.f ? k : 0.f);
+        }
+        gpred[i] = accumulate ? gpred[i] + g : g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing: out[i] = bf16(part(src[idx[i]]))  with idx < 0 -> 0; bit 30 of idx selects the lo part of the
+// bf16 hi/lo split (parity mode).  One launch packs every layer (the table is built once on the host).
+__global__ void pack_weights_kernel(const float* __restrict__ src, const int* __restrict__ idx, bf16* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = idx[i];
+        float v = 0.f;
+        if (e >= 0) {
+            const float w = src[e & 0x3FFFFFFF];
+            const float hi = __bfloat162float(__float2bfloat16_rn(w));
+            v = (e & 0x40000000) ? (w - hi) : w;
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+// Gradient unpacking: grad[i] (+)= dw[idx[i]] (idx < 0: leave untouched).
+__global__ void unpack_grads_kernel(const float* __restrict__ dw, const int* __restrict__ idx, float* __restrict__ grad, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = idx[i];
+        if (e >= 0) grad[i] += dw[e];
+    }
+}
+
+// Fused SGD with momentum + weight decay over the flat parameter arena (torch.optim.SGD as at main.py:285-290).
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, size_t n, float lr,
+                           float momentum, float wd, int first) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = g[i] + wd * p[i];
+        const float b = first ? d : momentum * mom[i] + d;
+        mom[i] = b;
+        p[i] -= lr * b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SID radar filter (multistage_model.py:87-119): thr = exp(d*ln(18/5)/100 + ln 5); mask = |d - radar| <= thr.
+__global__ void sid_filter_kernel(const float* __restrict__ radar, const float* __restrict__ depth, size_t n,
+                                  float* __restrict__ radar_f, float* __restrict__ mask) {
+    const float k = 0.012809338454620642f;   // ln(18/5)/100
+    const float l5 = 1.6094379124341003f;    // ln 5
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = depth[i], r = radar[i];
+        const float thr = expf(d * k + l5);
+        const float m = fabsf(d - r) <= thr ? 1.f : 0.f;
+        mask[i] = m;
+        radar_f[i] = r * m;
+    }
+}
+
+}  // namespace rd

@@ -1,0 +1,121 @@
+"""Host-side planning logic (no GPU): the GConv descriptions reproduce torch's convolutions exactly, their
+transposes reproduce autograd's data gradients, and the weight-gradient reference reproduces autograd's
+weight gradients.  These are the semantics the tcgen05 programs are derived from."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from radar_depth_b200 import convplan as cp
+from radar_depth_b200 import _lib
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("k,stride,pad,H,W", [(3, 1, 1, 9, 13), (3, 2, 1, 10, 14), (3, 2, 1, 9, 13), (1, 2, 0, 9, 12),
+                                              (1, 1, 0, 5, 7), (5, 1, 2, 8, 9), (7, 2, 3, 12, 16)])
+def test_standard_conv_forward_dgrad_wgrad(k, stride, pad, H, W):
+    torch.manual_seed(0)
+    Cin, Cout, B = 16, 32, 2
+    w = torch.randn(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, None, stride, pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    g = cp.gconv_standard(0, Cout, Cin, k, stride, pad)
+    wflat = w.detach().reshape(-1)
+    out = cp.gconv_reference(g, _nhwc(x.detach()), wflat, y.shape[-2:])
+    assert torch.allclose(_nchw(out), y.detach(), atol=1e-10)
+    dx = cp.gconv_reference(g.transposed(), _nhwc(dy), wflat, (H, W))
+    assert torch.allclose(_nchw(dx), x.grad, atol=1e-10)
+    dw = cp.gconv_wgrad_reference(g, _nhwc(x.detach()), _nhwc(dy), wflat.numel())
+    assert torch.allclose(dw.reshape(w.shape), w.grad, atol=1e-9)
+
+
+@pytest.mark.parametrize("cin_depth,H,W", [(1, 16, 24), (2, 16, 24), (1, 18, 22)])
+def test_stem_matches_two_7x7_stride2_convs(cin_depth, H, W):
+    torch.manual_seed(1)
+    B, C = 2, 3 + cin_depth
+    w_rgb = torch.randn(64, 3, 7, 7, dtype=torch.float64, requires_grad=True)
+    w_d = torch.randn(16, cin_depth, 7, 7, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(B, C, H, W, dtype=torch.float64, requires_grad=True)
+    y = torch.cat([F.conv2d(x[:, :3], w_rgb, None, 2, 3), F.conv2d(x[:, 3:], w_d, None, 2, 3)], 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wflat = torch.cat([w_rgb.detach().reshape(-1), w_d.detach().reshape(-1)])
+    g = cp.gconv_stem(0, w_rgb.numel(), cin_depth)
+    Cs = g.Cx // 4
+    # space-to-depth input, channel = parity*Cs + c (what rd_input_pack writes)
+    xs = torch.zeros(B, H // 2, W // 2, g.Cx, dtype=torch.float64)
+    for py in range(2):
+        for px in range(2):
+            xs[..., (py * 2 + px) * Cs:(py * 2 + px) * Cs + C] = x.detach()[:, :, py::2, px::2].permute(0, 2, 3, 1)
+    out = cp.gconv_reference(g, xs, wflat, y.shape[-2:])
+    assert torch.allclose(_nchw(out), y.detach(), atol=1e-10)
+    dw = cp.gconv_wgrad_reference(g, xs, _nhwc(dy), wflat.numel())
+    assert torch.allclose(dw[:w_rgb.numel()].reshape(w_rgb.shape), w_rgb.grad, atol=1e-9)
+    assert torch.allclose(dw[w_rgb.numel():].reshape(w_d.shape), w_d.grad, atol=1e-9)
+    # data gradient in space-to-depth form
+    dxs = cp.gconv_reference(g.transposed(), _nhwc(dy), wflat, (H // 2, W // 2))
+    for py in range(2):
+        for px in range(2):
+            got = dxs[..., (py * 2 + px) * Cs:(py * 2 + px) * Cs + C].permute(0, 3, 1, 2)
+            assert torch.allclose(got, x.grad[:, :, py::2, px::2], atol=1e-10)
+
+
+@pytest.mark.parametrize("H,W", [(5, 7), (4, 6)])
+def test_upproj_subpixel_equals_5x5_on_unpooled(H, W):
+    torch.manual_seed(2)
+    B, Cin, Cout = 2, 32, 16
+    wu = torch.randn(Cout, Cin, 5, 5, dtype=torch.float64, requires_grad=True)
+    wb = torch.randn(Cout, Cin, 5, 5, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    u = torch.zeros(B, Cin, 2 * H, 2 * W, dtype=torch.float64)
+    u = u.clone()
+    u[:, :, ::2, ::2] = x            # Unpool, models.py:13-27
+    y = torch.cat([F.conv2d(u, wu, None, 1, 2), F.conv2d(u, wb, None, 1, 2)], 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wflat = torch.cat([wu.detach().reshape(-1), wb.detach().reshape(-1)])
+    g = cp.gconv_upproj(0, wu.numel(), Cin, Cout)
+    assert len(g.taps) == 25
+    out = cp.gconv_reference(g, _nhwc(x.detach()), wflat, (2 * H, 2 * W))
+    assert torch.allclose(_nchw(out), y.detach(), atol=1e-10)
+    dx = cp.gconv_reference(g.transposed(), _nhwc(dy), wflat, (H, W))
+    assert torch.allclose(_nchw(dx), x.grad, atol=1e-10)
+    dw = cp.gconv_wgrad_reference(g, _nhwc(x.detach()), _nhwc(dy), wflat.numel())
+    assert torch.allclose(dw[:wu.numel()].reshape(wu.shape), wu.grad, atol=1e-9)
+    assert torch.allclose(dw[wu.numel():].reshape(wb.shape), wb.grad, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", [_lib.RD_BF16, _lib.RD_F32])
+def test_plans_are_self_consistent(dtype):
+    """Every hot-path conv shape at 352x1216 plans within TMEM / smem limits."""
+    shapes = [("l1", cp.gconv_standard(0, 64, 64, 3, 1, 1), (88, 304), (88, 304)),
+              ("l2.0", cp.gconv_standard(0, 128, 64, 3, 2, 1), (88, 304), (44, 152)),
+              ("l4", cp.gconv_standard(0, 512, 512, 3, 1, 1), (11, 38), (11, 38)),
+              ("ds", cp.gconv_standard(0, 256, 128, 1, 2, 0), (44, 152), (22, 76)),
+              ("fusion", cp.gconv_standard(0, 512, 640, 1, 1, 0), (11, 38), (11, 38)),
+              ("d16", cp.gconv_standard(0, 16, 16, 3, 1, 1), (88, 304), (88, 304)),
+              ("stem", cp.gconv_stem(0, 64 * 3 * 49, 1), (176, 608), (176, 608)),
+              ("up1", cp.gconv_upproj(0, 128 * 256 * 25, 256, 128), (11, 38), (22, 76)),
+              ("up4", cp.gconv_upproj(0, 16 * 32 * 25, 32, 16), (88, 304), (176, 608))]
+    for name, g, src, dst in shapes:
+        for gg, s, d in ((g, src, dst), (g.transposed(), dst, src)):
+            pl = cp.plan_fprop(gg, 2, s, d, dtype)
+            p = pl.params
+            assert p.P * p.MB * p.N <= 512, name
+            assert cp.FPROP_HEADER + p.IS * p.istage_bytes + p.WS * p.wstage_bytes <= cp.SMEM_BUDGET, name
+            assert pl.pack_idx.size == pl.wpk_elems
+            mx = max(p.taps[i].a_shift for i in range(p.ntaps))
+            assert mx + p.MB * 128 <= p.S * p.S * p.plane_slots, name
+        wp = cp.plan_wgrad(g, 2, src, dst, dtype)
+        q = wp.params
+        assert q.tg_size * q.Nc <= 512 and cp.WGRAD_HEADER + q.NS * q.stage_bytes + wp.info['geo']['pad'] <= cp.SMEM_BUDGET, name
+        assert len(set(wp.scatter[0].tolist())) == wp.scatter[0].size       # each parameter has one source
