@@ -1,0 +1,536 @@
+"""Forward / backward schedule of ResNet_latefusion (reference model/models.py:519-664; ResNet_latefusion2 in
+model/multistage_model.py:123-276 is the same graph with a 2-channel depth stem) on the sm_100a kernels.
+
+The engine owns
+  * a flat fp32 parameter arena (the nn.Parameters of the module become views of it) and a flat gradient arena
+    (``param.grad`` become views of it): one bucket for the fused SGD step and the NCCL all-reduce;
+  * packed bf16 weight tiles for every convolution program (re-packed from the arena at the start of every
+    forward, one gather kernel for the whole network);
+  * NHWC activation buffers, BatchNorm vectors and fp64 statistic slots, all allocated once per input shape so that
+    the launch sequence is static (CUDA-graph capturable);
+  * two launch programs (lists of pre-bound C-ABI calls): forward and backward.
+
+What is fused where (vs. the reference's one-library-call-per-module execution):
+  * both 7x7 stems are one 4x4-tap convolution over the space-to-depth input;
+  * relu(bn(conv(x))) is never materialised: convs store the raw output z and emit per-channel sum / sum-of-squares
+    from their epilogue; the consumer applies the BN affine + activation while staging its operand;
+  * Unpool + the two 5x5 convs of an UpProj block are one 4-phase sub-pixel program with N = 2*Cout;
+  * activation-gradient masks and BatchNorm-backward reductions live in the data-gradient epilogues;
+  * torch.cat (models.py:652) is a channel offset into one 640-channel buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, convplan as cp
+from ._lib import RD_BF16, RD_F32, View
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _p(t: torch.Tensor, off: int = 0) -> int:
+    return t.data_ptr() + off * t.element_size()
+
+
+def _v(t: torch.Tensor, coff: int = 0) -> View:
+    return View(t.data_ptr(), t.shape[-1], coff)
+
+
+NULLV = View(None, 0, 0)
+
+
+class BNGroup:
+    """Per-channel vectors of one or more BatchNorm2d layers laid side by side over a fused channel range."""
+
+    def __init__(self, eng: "LatefusionEngine", members: List[Tuple[str, int, int]]):
+        self.members = members                                   # (bn name, first channel, channels)
+        self.C = sum(m[2] for m in members)
+        d = eng.device
+        self.vec = torch.zeros(7, self.C, dtype=torch.float32, device=d)    # scale shift mean invstd A B C
+        self.scale, self.shift, self.mean, self.invstd, self.cA, self.cB, self.cC = self.vec.unbind(0)
+        self.fstats = eng.alloc_stats(2 * self.C).view(2, self.C)
+        self.bstats = eng.alloc_stats(3 * self.C).view(3, self.C)
+
+
+class Launch:
+    __slots__ = ("fn", "args", "name")
+
+    def __init__(self, name, fn, args):
+        self.name, self.fn, self.args = name, fn, args
+
+
+class LatefusionEngine:
+    def __init__(self, module: torch.nn.Module, in_channels: int, output_size, act_dtype: int = RD_BF16):
+        self.module = module
+        self.in_channels = in_channels
+        self.output_size = tuple(int(v) for v in output_size)
+        self.act_dtype = act_dtype
+        self.tdtype = torch.bfloat16 if act_dtype == RD_BF16 else torch.float32
+        self.lib = _lib.load()
+        self.device = None
+        self.flat = None
+        self.gflat = None
+        self.offs: Dict[str, Tuple[int, tuple]] = {}
+        self.cfg = None
+        self._stats_chunks: List[torch.Tensor] = []
+        self._keep = []                    # keeps ctypes structs / tensors referenced by launches alive
+
+    # ------------------------------------------------------------------ parameter arena
+    def params_adopted(self) -> bool:
+        if self.flat is None:
+            return False
+        base, end = self.flat.data_ptr(), self.flat.data_ptr() + self.flat.numel() * 4
+        for _, p in self.module.named_parameters(recurse=True):
+            if not (p.is_cuda and base <= p.data_ptr() < end):
+                return False
+        for b in self.module.buffers():
+            if not b.is_cuda:
+                return False
+        return True
+
+    def adopt(self, device) -> None:
+        """Flatten the module's parameters into one fp32 arena; parameters become views of it."""
+        self.device = torch.device(device)
+        named = [(n, p) for n, p in self.module.named_parameters()]
+        offs, total = OrderedDict(), 0
+        for n, p in named:
+            offs[n] = (total, tuple(p.shape))
+            total += (p.numel() + 3) // 4 * 4                   # keep every parameter 16-byte aligned
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        gflat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for n, p in named:
+                off, shape = offs[n]
+                flat[off:off + p.numel()].copy_(p.detach().reshape(-1).to(self.device, torch.float32))
+                p.data = flat[off:off + p.numel()].view(shape)
+                p.grad = None
+        for b in list(self.module.buffers()):
+            if not b.is_cuda or b.device != self.device:
+                raise RuntimeError("move the module to the CUDA device before the first forward (model.cuda())")
+        self.flat, self.gflat, self.offs, self.nparams = flat, gflat, offs, total
+        self.cfg = None
+
+    def bind_grads(self) -> None:
+        for n, p in self.module.named_parameters():
+            off, shape = self.offs[n]
+            if p.grad is None or p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
+                p.grad = self.gflat[off:off + p.numel()].view(shape)
+
+    def grads_bound(self) -> bool:
+        for n, p in self.module.named_parameters():
+            if p.grad is None:
+                return False
+            off, _ = self.offs[n]
+            if p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
+                return False
+        return True
+
+    # ------------------------------------------------------------------ allocation helpers
+    def alloc_stats(self, n: int) -> torch.Tensor:
+        off = self._stats_used
+        self._stats_used += n
+        assert self._stats_used <= self.stats.numel()
+        return self.stats[off:off + n]
+
+    def act(self, B, H, W, Cc) -> torch.Tensor:
+        return torch.zeros(B, H, W, Cc, dtype=self.tdtype, device=self.device)
+
+    # ------------------------------------------------------------------ configuration for one input shape
+    def configure(self, B: int, H: int, W: int) -> None:
+        key = (B, H, W)
+        if self.cfg is not None and self.cfg["key"] == key:
+            return
+        o = {k: v[0] for k, v in self.offs.items()}
+        self._keep = []
+        self.stats = torch.zeros(1 << 16, dtype=torch.float64, device=self.device)
+        self._stats_used = 0
+        self.convs = []                    # (name, GConv, fplan, dplan, wplan)
+        self._wpk_tables: List[np.ndarray] = []
+        self._wpk_total = 0
+        self._dw_total = 0
+        self._scatter_p: List[np.ndarray] = []
+        self._scatter_d: List[np.ndarray] = []
+        self.fwd: List[Launch] = []
+        self.bwd: List[Launch] = []
+        self.fwd_eval: List[Launch] = []
+        lib = self.lib
+        act = self.act_dtype
+        cin_d = self.in_channels - 3
+        Cs = 4 if self.in_channels <= 4 else 8
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        H4, W4 = (H2 + 1) // 2, (W2 + 1) // 2
+
+        # -------- helpers that register a conv and emit launches
+        def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True):
+            fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act)
+            f_off = self._wpk_total
+            self._wpk_tables.append(fplan.pack_idx)
+            self._wpk_total += fplan.wpk_elems
+            dplan, d_off = None, None
+            if need_dgrad:
+                dplan = cp.plan_fprop(g.transposed(), B, dst_hw, src_hw, act)
+                d_off = self._wpk_total
+                self._wpk_tables.append(dplan.pack_idx)
+                self._wpk_total += dplan.wpk_elems
+            wplan, w_off = None, None
+            if need_wgrad:
+                wplan = cp.plan_wgrad(g, B, src_hw, dst_hw, act)
+                w_off = self._dw_total
+                self._scatter_p.append(wplan.scatter[0])
+                self._scatter_d.append(wplan.scatter[1] + w_off)
+                self._dw_total += wplan.dw_elems
+            rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off)
+            self.convs.append(rec)
+            return rec
+
+        self._pending = []                 # launches whose weight / dw pointers are patched after arenas exist
+
+        def emit_conv(prog, rec, which, src: View, dst: View, ld=None, epi=0, addend=None, zsrc=None, ep=None,
+                      stats=None, tag=""):
+            plan = rec["fplan"] if which == "f" else rec["dplan"]
+            p = type(plan.params).from_buffer_copy(plan.params)
+            p.src, p.dst = src, dst
+            if ld is not None:
+                p.ld_scale, p.ld_shift, p.ld_slope = _p(ld[0]), _p(ld[1]), float(ld[2])
+            else:
+                p.ld_scale, p.ld_shift, p.ld_slope = None, None, 1.0
+            p.epi = epi
+            p.addend = addend if addend is not None else NULLV
+            p.zsrc = zsrc if zsrc is not None else NULLV
+            if ep is not None:
+                p.ep_scale, p.ep_shift, p.ep_slope = _p(ep[0]), _p(ep[1]), float(ep[2])
+            if stats is not None:
+                p.stats, p.stats_stride = _p(stats), stats.shape[1]
+            self._pending.append((p, "wpk", rec["f_off"] if which == "f" else rec["d_off"]))
+            self._keep.append(p)
+            prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),)))
+            return p
+
+        def emit_wgrad(prog, rec, gy: View, x: View, ld=None):
+            plan = rec["wplan"]
+            p = type(plan.params).from_buffer_copy(plan.params)
+            p.gy, p.x = gy, x
+            if ld is not None:
+                p.ld_scale, p.ld_shift, p.ld_slope = _p(ld[0]), _p(ld[1]), float(ld[2])
+            else:
+                p.ld_scale, p.ld_shift, p.ld_slope = None, None, 1.0
+            self._pending.append((p, "dw", rec["w_off"]))
+            self._keep.append(p)
+            prog.append(Launch(f"wgrad:{rec['name']}", lib.rd_conv_wgrad, (C.byref(p),)))
+
+        def bn_buffers(name):
+            m = self.module.get_submodule(name)
+            return m.running_mean, m.running_var, m.num_batches_tracked
+
+        def emit_bn_fwd(grp: BNGroup, count: float):
+            for (name, c0, Cn) in grp.members:
+                rm, rv, nbt = bn_buffers(name)
+                go, bo = o[name + ".weight"], o[name + ".bias"]
+                common = (_p(self.flat, go), _p(self.flat, bo), _p(rm), _p(rv))
+                tail = (_p(grp.scale, c0), _p(grp.shift, c0), _p(grp.mean, c0), _p(grp.invstd, c0))
+                self.fwd.append(Launch("bn_fin:" + name, lib.rd_bn_finalize,
+                                       (_p(grp.fstats[0], c0), _p(grp.fstats[1], c0), float(count)) + common +
+                                       (_p(nbt), Cn, 1, BN_MOMENTUM, BN_EPS) + tail))
+                self.fwd_eval.append(Launch("bn_fin_eval:" + name, lib.rd_bn_finalize,
+                                            (None, None, float(count)) + common + (None, Cn, 0, BN_MOMENTUM, BN_EPS) + tail))
+
+        def emit_bn_bwd(grp: BNGroup, midx: int, sum_g_ptr: int, sum_gz_ptr: int, count: float):
+            name, c0, Cn = grp.members[midx]
+            go, bo = o[name + ".weight"], o[name + ".bias"]
+            self.bwd.append(Launch("bn_bwd_fin:" + name, lib.rd_bn_bwd_finalize,
+                                   (sum_g_ptr, sum_gz_ptr, float(count), _p(self.flat, go), _p(grp.mean, c0),
+                                    _p(grp.invstd, c0), Cn, 1, _p(self.gflat, go), _p(self.gflat, bo),
+                                    _p(grp.cA, c0), _p(grp.cB, c0), _p(grp.cC, c0))))
+
+        def both(launch: Launch):          # identical in train and eval forward
+            self.fwd.append(launch)
+            self.fwd_eval.append(launch)
+
+        def emit_conv_fwd(rec, src, dst, ld, stats, count_grp: Optional[BNGroup]):
+            emit_conv(self.fwd, rec, "f", src, dst, ld=ld, stats=stats)
+            emit_conv(self.fwd_eval, rec, "f", src, dst, ld=ld, stats=None, tag="(eval)")
+
+        # ============================== buffers + forward program ==============================
+        self.x_in = torch.zeros(B, self.in_channels, H, W, dtype=torch.float32, device=self.device)
+        xs = self.act(B, H2, W2, 4 * Cs)
+        both(Launch("input_pack", lib.rd_input_pack, (_p(self.x_in), _p(xs), B, self.in_channels, H, W, Cs, act)))
+
+        # ---- stem
+        stem = reg("stem", cp.gconv_stem(o["conv1.weight"], o["conv1_depth.weight"], cin_d), (H2, W2), (H2, W2),
+                   need_dgrad=(self.in_channels > 4))
+        z_stem = self.act(B, H2, W2, 80)
+        g_stem = BNGroup(self, [("bn1", 0, 64), ("bn1_depth", 64, 16)])
+        n_stem = float(B * H2 * W2)
+        emit_conv_fwd(stem, _v(xs), _v(z_stem), None, g_stem.fstats, g_stem)
+        emit_bn_fwd(g_stem, n_stem)
+        p_rgb, p_d = self.act(B, H4, W4, 64), self.act(B, H4, W4, 16)
+        amax = torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device)
+        both(Launch("maxpool", lib.rd_maxpool_fwd,
+                    (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0, 0.2, _v(p_rgb), _v(p_d),
+                     _p(amax), H4, W4, act)))
+
+        # ---- encoders
+        enc_specs = [("", (64, 128, 256, 512), 64, p_rgb, 0), ("_depth", (16, 32, 64, 128), 16, p_d, 512)]
+        h32, w32 = H4, W4
+        for _ in range(3):
+            h32, w32 = (h32 + 1) // 2, (w32 + 1) // 2
+        concat = self.act(B, h32, w32, 640)
+        d_concat = self.act(B, h32, w32, 640)
+        blocks_all = []
+        for suffix, widths, cin0, x0, cat_off in enc_specs:
+            x_cur, cin = x0, cin0
+            h, w = H4, W4
+            blks = []
+            for li, cw in enumerate(widths, start=1):
+                for bi in range(2):
+                    pfx = f"layer{li}{suffix}.{bi}"
+                    stride = 2 if (li > 1 and bi == 0) else 1
+                    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+                    ci = cin if bi == 0 else cw
+                    c1 = reg(pfx + ".conv1", cp.gconv_standard(o[pfx + ".conv1.weight"], cw, ci, 3, stride, 1), (h, w), (ho, wo))
+                    c2 = reg(pfx + ".conv2", cp.gconv_standard(o[pfx + ".conv2.weight"], cw, cw, 3, 1, 1), (ho, wo), (ho, wo))
+                    ds = None
+                    if stride == 2:
+                        ds = reg(pfx + ".downsample.0", cp.gconv_standard(o[pfx + ".downsample.0.weight"], cw, ci, 1, 2, 0), (h, w), (ho, wo))
+                    n = float(B * ho * wo)
+                    z1, z2 = self.act(B, ho, wo, cw), self.act(B, ho, wo, cw)
+                    b1 = BNGroup(self, [(pfx + ".bn1", 0, cw)])
+                    b2 = BNGroup(self, [(pfx + ".bn2", 0, cw)])
+                    emit_conv_fwd(c1, _v(x_cur), _v(z1), None, b1.fstats, b1)
+                    emit_bn_fwd(b1, n)
+                    emit_conv_fwd(c2, _v(z1), _v(z2), (b1.scale, b1.shift, 0.0), b2.fstats, b2)
+                    emit_bn_fwd(b2, n)
+                    zd, bd = None, None
+                    if ds is not None:
+                        zd = self.act(B, ho, wo, cw)
+                        bd = BNGroup(self, [(pfx + ".downsample.1", 0, cw)])
+                        emit_conv_fwd(ds, _v(x_cur), _v(zd), None, bd.fstats, bd)
+                        emit_bn_fwd(bd, n)
+                    last = (li == 4 and bi == 1)
+                    if last:
+                        out_t, out_v = concat, _v(concat, cat_off)
+                    else:
+                        out_t = self.act(B, ho, wo, cw)
+                        out_v = _v(out_t)
+                    idv = _v(zd) if zd is not None else (_v(x_cur) if isinstance(x_cur, torch.Tensor) else x_cur)
+                    both(Launch("join:" + pfx, lib.rd_bn_add_act,
+                                (_v(z2), _p(b2.scale), _p(b2.shift), idv, _p(bd.scale) if bd else None,
+                                 _p(bd.shift) if bd else None, out_v, int(B * ho * wo), cw, 0.0, act)))
+                    blks.append(dict(pfx=pfx, c1=c1, c2=c2, ds=ds, b1=b1, b2=b2, bd=bd, z1=z1, z2=z2, zd=zd, x_in=x_cur,
+                                     out_v=out_v, hw_in=(h, w), hw=(ho, wo), cw=cw, ci=ci, n=n, last=last, cat_off=cat_off))
+                    x_cur, h, w = out_t, ho, wo
+                cin = cw
+            blocks_all.append(blks)
+
+        # ---- fusion 1x1s
+        nf = float(B * h32 * w32)
+        cf = reg("conv_fusion", cp.gconv_standard(o["conv_fusion.weight"], 512, 640, 1, 1, 0), (h32, w32), (h32, w32))
+        zf = self.act(B, h32, w32, 512)
+        bf = BNGroup(self, [("bn_fusion", 0, 512)])
+        emit_conv_fwd(cf, _v(concat), _v(zf), None, bf.fstats, bf)
+        emit_bn_fwd(bf, nf)
+        cc2 = reg("conv2", cp.gconv_standard(o["conv2.weight"], 256, 512, 1, 1, 0), (h32, w32), (h32, w32))
+        zc2 = self.act(B, h32, w32, 256)
+        bc2 = BNGroup(self, [("bn2", 0, 256)])
+        emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2.fstats, bc2)
+        emit_bn_fwd(bc2, nf)
+
+        # ---- decoder (UpProj x4)
+        dec = []
+        d_in_t, d_in_ld = zc2, (bc2.scale, bc2.shift, 1.0)
+        h, w, cin = h32, w32, 256
+        for li in range(1, 5):
+            pfx = f"decoder.layer{li}"
+            co = cin // 2
+            ho, wo = 2 * h, 2 * w
+            up = reg(pfx + ".up5x5", cp.gconv_upproj(o[pfx + ".upper_branch.conv1.weight"], o[pfx + ".bottom_branch.conv.weight"], cin, co),
+                     (h, w), (ho, wo))
+            c3 = reg(pfx + ".upper_branch.conv2", cp.gconv_standard(o[pfx + ".upper_branch.conv2.weight"], co, co, 3, 1, 1), (ho, wo), (ho, wo))
+            zcat, zu2, out_t = self.act(B, ho, wo, 2 * co), self.act(B, ho, wo, co), self.act(B, ho, wo, co)
+            gcat = BNGroup(self, [(pfx + ".upper_branch.batchnorm1", 0, co), (pfx + ".bottom_branch.batchnorm", co, co)])
+            bu2 = BNGroup(self, [(pfx + ".upper_branch.batchnorm2", 0, co)])
+            n = float(B * ho * wo)
+            emit_conv_fwd(up, _v(d_in_t), _v(zcat), d_in_ld, gcat.fstats, gcat)
+            emit_bn_fwd(gcat, n)
+            emit_conv_fwd(c3, _v(zcat, 0), _v(zu2), (gcat.scale, gcat.shift, 0.0), bu2.fstats, bu2)
+            emit_bn_fwd(bu2, n)
+            both(Launch("join:" + pfx, lib.rd_bn_add_act,
+                        (_v(zu2), _p(bu2.scale), _p(bu2.shift), _v(zcat, co), _p(gcat.scale, co), _p(gcat.shift, co),
+                         _v(out_t), int(B * ho * wo), co, 0.0, act)))
+            dec.append(dict(pfx=pfx, up=up, c3=c3, zcat=zcat, zu2=zu2, out=out_t, gcat=gcat, bu2=bu2, co=co, cin=cin,
+                            x_in=d_in_t, x_ld=d_in_ld, hw_in=(h, w), hw=(ho, wo), n=n))
+            d_in_t, d_in_ld = out_t, None
+            h, w, cin = ho, wo, co
+        Hd, Wd = h, w
+        self.Hd, self.Wd = Hd, Wd
+
+        # ---- head
+        OH, OW = self.output_size
+        c3map = torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device)
+        self.pred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
+        w3 = _p(self.flat, o["conv3.weight"])
+        both(Launch("head_conv", lib.rd_head_conv_fwd, (_v(d_in_t), w3, B, Hd, Wd, _p(c3map), act)))
+        both(Launch("bilinear", lib.rd_bilinear_fwd, (_p(c3map), B, Hd, Wd, _p(self.pred), OH, OW)))
+
+        # ============================== backward program ==============================
+        bw = self.bwd
+        self.dpred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
+        dc3 = torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device)
+        bw.append(Launch("bilinear_bwd", lib.rd_bilinear_bwd, (_p(self.dpred), B, Hd, Wd, _p(dc3), OH, OW)))
+        d_out = self.act(B, Hd, Wd, dec[-1]["co"])
+        bw.append(Launch("head_conv_bwd", lib.rd_head_conv_bwd,
+                         (_p(dc3), _v(dec[-1]["out"]), w3, B, Hd, Wd, _v(d_out), _p(self.gflat, o["conv3.weight"]), act)))
+        for li in range(3, -1, -1):
+            L = dec[li]
+            co, (ho, wo), n = L["co"], L["hw"], L["n"]
+            npix = int(B * ho * wo)
+            gcat, bu2 = L["gcat"], L["bu2"]
+            g_t = self.act(B, ho, wo, co)
+            dzcat = self.act(B, ho, wo, 2 * co)
+            dzu2 = self.act(B, ho, wo, co)
+            bw.append(Launch("join_bwd:" + L["pfx"], lib.rd_join_bwd,
+                             (_v(d_out), _v(L["out"]), _v(L["zu2"]), _v(L["zcat"], co), _v(g_t), npix, co, 0.0,
+                              _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), act)))
+            emit_bn_bwd(bu2, 0, _p(bu2.bstats[0]), _p(bu2.bstats[1]), n)
+            emit_bn_bwd(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)
+            bw.append(Launch("bn_bwd_apply:bottom", lib.rd_bn_bwd_apply,
+                             (_v(g_t), _v(L["zcat"], co), _v(dzcat, co), _p(gcat.cA, co), _p(gcat.cB, co), _p(gcat.cC, co), npix, co, act)))
+            bw.append(Launch("bn_bwd_apply:u2", lib.rd_bn_bwd_apply,
+                             (_v(g_t), _v(L["zu2"]), _v(dzu2), _p(bu2.cA), _p(bu2.cB), _p(bu2.cC), npix, co, act)))
+            emit_wgrad(bw, L["c3"], _v(dzu2), _v(L["zcat"], 0), ld=(gcat.scale, gcat.shift, 0.0))
+            emit_conv(bw, L["c3"], "d", _v(dzu2), _v(dzcat, 0), epi=1, zsrc=_v(L["zcat"], 0), ep=(gcat.scale, gcat.shift, 0.0),
+                      stats=gcat.bstats[:2])
+            emit_bn_bwd(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)
+            bw.append(Launch("bn_bwd_apply:u1", lib.rd_bn_bwd_apply,
+                             (_v(dzcat, 0), _v(L["zcat"], 0), _v(dzcat, 0), _p(gcat.cA), _p(gcat.cB), _p(gcat.cC), npix, co, act)))
+            emit_wgrad(bw, L["up"], _v(dzcat), _v(L["x_in"]), ld=L["x_ld"])
+            if li > 0:
+                hin, win = L["hw_in"]
+                d_prev = self.act(B, hin, win, L["cin"])
+                emit_conv(bw, L["up"], "d", _v(dzcat), _v(d_prev))
+                d_out = d_prev
+            else:
+                g_c2 = self.act(B, h32, w32, 256)
+                emit_conv(bw, L["up"], "d", _v(dzcat), _v(g_c2), epi=1, zsrc=_v(zc2), ep=(bc2.scale, bc2.shift, 1.0),
+                          stats=bc2.bstats[:2])
+        npf = int(B * h32 * w32)
+        emit_bn_bwd(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)
+        bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
+                         (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act)))
+        emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
+        g_f = self.act(B, h32, w32, 512)
+        emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2])
+        emit_bn_bwd(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)
+        bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
+                         (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act)))
+        emit_wgrad(bw, cf, _v(g_f), _v(concat))
+        emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
+
+        dpool = []
+        for blks in blocks_all:
+            d_out_v = _v(d_concat, blks[-1]["cat_off"])
+            for Bk in reversed(blks):
+                cw, (ho, wo), (hi, wi), n = Bk["cw"], Bk["hw"], Bk["hw_in"], Bk["n"]
+                npix = int(B * ho * wo)
+                b1, b2, bd = Bk["b1"], Bk["b2"], Bk["bd"]
+                g_t, dz2, g1 = self.act(B, ho, wo, cw), self.act(B, ho, wo, cw), self.act(B, ho, wo, cw)
+                bw.append(Launch("join_bwd:" + Bk["pfx"], lib.rd_join_bwd,
+                                 (d_out_v, Bk["out_v"], _v(Bk["z2"]), _v(Bk["zd"]) if bd else NULLV, _v(g_t), npix, cw, 0.0,
+                                  _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), act)))
+                emit_bn_bwd(b2, 0, _p(b2.bstats[0]), _p(b2.bstats[1]), n)
+                bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
+                                 (_v(g_t), _v(Bk["z2"]), _v(dz2), _p(b2.cA), _p(b2.cB), _p(b2.cC), npix, cw, act)))
+                dzd = None
+                if bd:
+                    dzd = self.act(B, ho, wo, cw)
+                    emit_bn_bwd(bd, 0, _p(b2.bstats[0]), _p(b2.bstats[2]), n)
+                    bw.append(Launch("bn_bwd_apply:ds", lib.rd_bn_bwd_apply,
+                                     (_v(g_t), _v(Bk["zd"]), _v(dzd), _p(bd.cA), _p(bd.cB), _p(bd.cC), npix, cw, act)))
+                emit_wgrad(bw, Bk["c2"], _v(dz2), _v(Bk["z1"]), ld=(b1.scale, b1.shift, 0.0))
+                emit_conv(bw, Bk["c2"], "d", _v(dz2), _v(g1), epi=1, zsrc=_v(Bk["z1"]), ep=(b1.scale, b1.shift, 0.0),
+                          stats=b1.bstats[:2])
+                emit_bn_bwd(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)
+                bw.append(Launch("bn_bwd_apply:bn1", lib.rd_bn_bwd_apply,
+                                 (_v(g1), _v(Bk["z1"]), _v(g1), _p(b1.cA), _p(b1.cB), _p(b1.cC), npix, cw, act)))
+                x_in_v = _v(Bk["x_in"])
+                emit_wgrad(bw, Bk["c1"], _v(g1), x_in_v)
+                dx = self.act(B, hi, wi, Bk["ci"])
+                if bd:
+                    emit_conv(bw, Bk["c1"], "d", _v(g1), _v(dx))
+                    emit_wgrad(bw, Bk["ds"], _v(dzd), x_in_v)
+                    emit_conv(bw, Bk["ds"], "d", _v(dzd), _v(dx), addend=_v(dx))
+                else:
+                    emit_conv(bw, Bk["c1"], "d", _v(g1), _v(dx), addend=_v(g_t))
+                d_out_v = _v(dx)
+            dpool.append(d_out_v)
+
+        gz_stem = self.act(B, H2, W2, 80)
+        bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
+                         (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
+                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), act)))
+        emit_bn_bwd(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem)
+        emit_bn_bwd(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)
+        bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
+                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act)))
+        emit_wgrad(bw, stem, _v(gz_stem), _v(xs))
+        self.dxs = None
+        if self.in_channels > 4:
+            self.dxs = self.act(B, H2, W2, 4 * Cs)
+            emit_conv(bw, stem, "d", _v(gz_stem), _v(self.dxs))
+
+        # ============================== arenas that depend on the totals ==============================
+        self.wpk = torch.zeros(self._wpk_total, dtype=torch.bfloat16, device=self.device)
+        self.dw = torch.zeros(max(self._dw_total, 1), dtype=torch.float32, device=self.device)
+        self.pack_idx = torch.from_numpy(np.concatenate(self._wpk_tables)).to(self.device)
+        unpack = np.full(self.nparams, -1, dtype=np.int32)
+        unpack[np.concatenate(self._scatter_p)] = np.concatenate(self._scatter_d).astype(np.int32)
+        self.unpack_idx = torch.from_numpy(unpack).to(self.device)
+        for p, kind, off in self._pending:
+            if kind == "wpk":
+                p.wpk = _p(self.wpk, off)
+            else:
+                p.dw = _p(self.dw, off)
+        self._pending = []
+        self._wpk_tables = []
+        pack = Launch("pack_weights", lib.rd_pack_weights, (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel()))
+        self.fwd.insert(0, pack)
+        self.fwd_eval.insert(0, pack)
+        bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams)))
+        self.stats_used = self.stats[:self._stats_used]
+        self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd)
+        self.dec, self.blocks_all = dec, blocks_all
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, prog: List[Launch]):
+        st = torch.cuda.current_stream().cuda_stream
+        lib = self.lib
+        for L in prog:
+            rc = L.fn(*L.args, st)
+            if rc != 0:
+                raise _lib.RdError(f"{L.name} failed ({rc}): {lib.rd_last_error().decode()}")
+
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        B, Cc, H, W = x.shape
+        assert Cc == self.in_channels, (Cc, self.in_channels)
+        if not self.params_adopted():
+            self.adopt(x.device)
+        self.configure(B, H, W)
+        self.x_in.copy_(x)
+        if training:
+            self.stats_used.zero_()
+        self._run(self.fwd if training else self.fwd_eval)
+        return self.pred
+
+    def backward(self, dpred: torch.Tensor, accumulate: bool) -> None:
+        """Fills the gradient arena from d(loss)/d(pred).  ``accumulate`` keeps what is already there."""
+        self.dpred.copy_(dpred.reshape(self.dpred.shape))
+        if not accumulate:
+            self.gflat.zero_()
+        self.dw.zero_()
+        self._run(self.bwd)

@@ -40,7 +40,7 @@ CASES = [
 
 
 def _tols(act):
-    return (2e-2, 2e-2) if act == _lib.RD_BF16 else (2e-4, 2e-4)
+    return (2e-2, 2e-2) if act == _lib.RD_BF16 else (3e-4, 3e-4)
 
 
 def _close(got, ref, act, what):
@@ -49,7 +49,7 @@ def _close(got, ref, act, what):
     scale = ref.abs().max().item() + 1e-6
     err = (got - ref).abs().max().item()
     rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
-    assert rel < (8e-3 if act == _lib.RD_BF16 else 2e-5), (what, rel, err, scale)
+    assert rel < (8e-3 if act == _lib.RD_BF16 else 1e-4), (what, rel, err, scale)   # f32 mode = 3-term bf16 split, ~2^-16
     assert err <= atol * scale + rtol * scale, (what, rel, err, scale)
 
 
