@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the radar_depth hot path on B200 (BASELINE.json metric):
+images/s for one forward + MaskedL1 + backward (+ gradient all-reduce + SGD) training step of
+resnet18_latefusion --decoder upproj, per-GPU batch 16, 352x1216, synthetic RGB + sparse radar.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch 16] [--precision bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  `value`: device-timed throughput with inputs resident in HBM.  `e2e`: the same step
+through the public API (model(inputs) -> MaskedL1Loss -> backward -> optimizer.step) with the H2D copy of the batch
+from pinned host memory and the D2H read of the loss inside the timed region.  `roofline`: tcgen05 convolution
+kernels (fprop/dgrad/wgrad programs), algorithmic conv FLOPs / summed CUDA-event launch durations, against the
+measured dense bf16 peak.  `cpu_baseline`: the CPU oracle (port of the reference's PyTorch path) on the host cores,
+bounded sample.  `--impl reference` times that CPU path alone (the reference owns no GPU kernels of its own).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 352, 1216
+# algorithmic conv FLOPs per image (2*MAC, Unpool's structural zeros excluded, no dgrad for the stems)
+FLOP_FWD_BWD_PER_IMAGE = 120.167e9
+METRIC = "images/sec fwd+bwd resnet18_latefusion b=16 352x1216"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_sustained=d.get("bf16_tflops_sustained", 1374.9), bf16_burst=d.get("bf16_tflops", 1608.4),
+                    hbm=d.get("hbm_gbs", 6553.6), source="measured")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_host_batch(b, seed, p_lidar=0.05):
+    """SURVEY.md 8(d) synthetic batch (same recipe as oracle.torch_oracle.synth_batch), built on the host."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    rgb = torch.rand(b, 3, H, W, generator=g)
+    mk = torch.rand(b, 1, H, W, generator=g) < 100.0 / (H * W)
+    radar = torch.zeros(b, 1, H, W)
+    radar[mk] = torch.rand(int(mk.sum()), generator=g) * 79 + 1
+    inputs = torch.cat((rgb, radar), dim=1)
+    tm = torch.rand(b, 1, H, W, generator=g) < p_lidar
+    target = torch.zeros(b, 1, H, W)
+    target[tm] = torch.rand(int(tm.sum()), generator=g) * 79 + 1
+    return inputs, target
+
+
+def cpu_reference_throughput(steps: int, warmup: int, batch: int = 2):
+    """Times the CPU oracle (the reference's PyTorch path restated in oracle/) on the host cores: bounded sample."""
+    import torch
+    from oracle import torch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synth_state_dict(O.latefusion_entries(4))
+    inputs, target = O.synth_batch(batch, H, W)
+    for _ in range(max(warmup, 1)):
+        O.train_step(sd, inputs, target, "latefusion")
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(sd, inputs, target, "latefusion")
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return dict(value=batch / med, unit="images/s", cores=cores, kind="port",
+                sample=f"{steps} timed fwd+loss+bwd iterations of b={batch} 352x1216 fp32 (oracle/torch_oracle.train_step, "
+                       f"torch {torch.__version__} CPU kernels, {cores} threads), median {med:.3f} s/iter"), med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 6)
+    base, med = cpu_reference_throughput(steps, min(args.warmup, 2))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "resnet18_latefusion upproj fwd+MaskedL1+bwd, 352x1216, CPU sample b=2 per step",
+                       "global_batch": 2, "note": "the reference has no GPU kernels of its own; this arm is its PyTorch CPU path "
+                                                  "(oracle port) on the box's host cores"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from radar_depth_b200.model.models import ResNet_latefusion
+    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+    from radar_depth_b200.optim import FusedSGD
+    from radar_depth_b200 import ddp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W_ = max(args.warmup, 3)
+    K = args.steps
+    b = args.batch
+
+    torch.manual_seed(0)
+    model = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False).cuda()
+    model.precision = args.precision
+    model.train()
+    ddp.broadcast_parameters(model)
+    crit = MaskedL1Loss()
+    opt = FusedSGD(model, lr=0.01, momentum=0.9, weight_decay=1e-4)
+
+    h_in, h_tg = synth_host_batch(b, 1234 + rank, p_lidar=0.05)
+    h_in, h_tg = h_in.pin_memory(), h_tg.pin_memory()
+    d_in, d_tg = h_in.cuda(non_blocking=True), h_tg.cuda(non_blocking=True)
+    h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    collectives = [0]
+
+    def step(x, t):
+        pred = model(x)
+        loss = crit(pred, t)
+        opt.zero_grad()
+        loss.backward()
+        collectives[0] = ddp.allreduce_gradients(model)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    # ---- warm-up (first call eager, second captures the CUDA graphs)
+    for _ in range(W_):
+        loss = step(d_in, d_tg)
+    torch.cuda.synchronize()
+    loss0 = float(loss)
+
+    # ---- device-resident timing
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: step(d_in, d_tg), K)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / K
+    value = world * b / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host batch -> device every step, loss read back every step
+    def e2e_step():
+        x = h_in.cuda(non_blocking=True)
+        t = h_tg.cuda(non_blocking=True)
+        l = step(x, t)
+        h_loss.copy_(l, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = world * b / (ms_e2e / K * 1e-3)
+    h2d = h_in.numel() * 4 + h_tg.numel() * 4
+    d2h = 4
+
+    eng = model._engine
+    launches = eng.launches_per_step() + 3 + 1 + 1        # + l1 fwd (2 kernels) + l1 bwd + sgd + pack is inside fwd
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3 split)", "data": "synthetic",
+            "config": {"workload": "resnet18_latefusion --decoder upproj, fwd + MaskedL1 + bwd + grad all-reduce + SGD, "
+                                   f"per-GPU b={b}, 352x1216 RGB + sparse radar (BASELINE.json configs[1])",
+                       "global_batch": world * b, "parallelism": f"dp{world}", "cuda_graphs": bool(eng.use_graphs),
+                       "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
+                       "collectives_per_step": collectives[0], "loss_first": loss0, "loss_last": float(loss)},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches * K, "clocks": clocks}
+
+    # ---- roofline of the tcgen05 convolution programs: per-launch CUDA-event timing on the launch stream
+    if rank == 0 and not args.no_kernel_timing:
+        line["roofline"] = kernel_roofline(model, d_in, d_tg, crit, b)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_reference_throughput(4, 1)
+        line["cpu_baseline"] = base
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, d_in, d_tg, crit, b):
+    """Times every launch of one training step with CUDA events (eager, same stream) and aggregates the tcgen05
+    convolution programs: achieved = algorithmic conv FLOPs of the step / summed duration of those launches."""
+    import torch
+    eng = model._engine
+    peaks = _peaks()
+    saved = eng.use_graphs
+    eng.use_graphs = False
+    try:
+        per = {}
+        for rep in range(3):
+            pred = model(d_in)           # warm (eager)
+            loss = crit(pred, d_tg)
+            loss.backward()
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream().cuda_stream
+        reps = 3
+        for prog_name, prog in (("fwd", eng.fwd), ("bwd", eng.bwd)):
+            for L in prog:
+                evs = []
+                for _ in range(reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = L.fn(*L.args, st)
+                    e1.record()
+                    assert rc == 0, L.name
+                    evs.append((e0, e1))
+                torch.cuda.synchronize()
+                t = statistics.median(a.elapsed_time(c) for a, c in evs)
+                kind = L.name.split(":")[0]
+                per.setdefault(kind, [0.0, 0])
+                per[kind][0] += t
+                per[kind][1] += 1
+        conv_ms = sum(v[0] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
+        conv_n = sum(v[1] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
+        total_ms = sum(v[0] for v in per.values())
+        flops = FLOP_FWD_BWD_PER_IMAGE * b
+        achieved = flops / (conv_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                "kernel": "conv_fprop_kernel + conv_wgrad_kernel (tcgen05 implicit-GEMM programs)",
+                "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "conv_ms_per_step": conv_ms,
+                "all_kernels_ms_per_step": total_ms, "conv_share_of_step": conv_ms / total_ms,
+                "by_kind_ms": {k: round(v[0], 4) for k, v in sorted(per.items())},
+                "algorithmic_flop_per_step": flops}
+    finally:
+        eng.use_graphs = saved
+
+
+if __name__ == "__main__":
+    main()

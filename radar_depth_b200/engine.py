@@ -21,6 +21,7 @@ What is fused where (vs. the reference's one-library-call-per-module execution):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -52,7 +53,7 @@ class BNGroup:
         self.members = members                                   # (bn name, first channel, channels)
         self.C = sum(m[2] for m in members)
         d = eng.device
-        self.vec = torch.zeros(7, self.C, dtype=torch.float32, device=d)    # scale shift mean invstd A B C
+        self.vec = eng.hold(torch.zeros(7, self.C, dtype=torch.float32, device=d))    # scale shift mean invstd A B C
         self.scale, self.shift, self.mean, self.invstd, self.cA, self.cB, self.cC = self.vec.unbind(0)
         self.fstats = eng.alloc_stats(2 * self.C).view(2, self.C)
         self.bstats = eng.alloc_stats(3 * self.C).view(3, self.C)
@@ -79,7 +80,10 @@ class LatefusionEngine:
         self.offs: Dict[str, Tuple[int, tuple]] = {}
         self.cfg = None
         self._stats_chunks: List[torch.Tensor] = []
-        self._keep = []                    # keeps ctypes structs / tensors referenced by launches alive
+        self._keep = []                    # keeps ctypes structs referenced by launches alive
+        self._buffers = []                 # keeps every device buffer referenced by raw pointer alive
+        self.use_graphs = os.environ.get("RADAR_DEPTH_B200_GRAPHS", "1") != "0"
+        self._graphs = {}
 
     # ------------------------------------------------------------------ parameter arena
     def params_adopted(self) -> bool:
@@ -111,7 +115,7 @@ class LatefusionEngine:
                 p.data = flat[off:off + p.numel()].view(shape)
                 p.grad = None
         for b in list(self.module.buffers()):
-            if not b.is_cuda or b.device != self.device:
+            if b.device != self.device:
                 raise RuntimeError("move the module to the CUDA device before the first forward (model.cuda())")
         self.flat, self.gflat, self.offs, self.nparams = flat, gflat, offs, total
         self.cfg = None
@@ -139,7 +143,12 @@ class LatefusionEngine:
         return self.stats[off:off + n]
 
     def act(self, B, H, W, Cc) -> torch.Tensor:
-        return torch.zeros(B, H, W, Cc, dtype=self.tdtype, device=self.device)
+        return self.hold(torch.zeros(B, H, W, Cc, dtype=self.tdtype, device=self.device))
+
+    def hold(self, t):
+        """Every device buffer referenced by raw pointer from a launch must stay alive as long as the program."""
+        self._buffers.append(t)
+        return t
 
     # ------------------------------------------------------------------ configuration for one input shape
     def configure(self, B: int, H: int, W: int) -> None:
@@ -148,6 +157,8 @@ class LatefusionEngine:
             return
         o = {k: v[0] for k, v in self.offs.items()}
         self._keep = []
+        self._buffers = []
+        self._graphs = {}
         self.stats = torch.zeros(1 << 16, dtype=torch.float64, device=self.device)
         self._stats_used = 0
         self.convs = []                    # (name, GConv, fplan, dplan, wplan)
@@ -270,7 +281,7 @@ class LatefusionEngine:
         emit_conv_fwd(stem, _v(xs), _v(z_stem), None, g_stem.fstats, g_stem)
         emit_bn_fwd(g_stem, n_stem)
         p_rgb, p_d = self.act(B, H4, W4, 64), self.act(B, H4, W4, 16)
-        amax = torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device)
+        amax = self.hold(torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device))
         both(Launch("maxpool", lib.rd_maxpool_fwd,
                     (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0, 0.2, _v(p_rgb), _v(p_d),
                      _p(amax), H4, W4, act)))
@@ -372,7 +383,7 @@ class LatefusionEngine:
 
         # ---- head
         OH, OW = self.output_size
-        c3map = torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device)
+        c3map = self.hold(torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device))
         self.pred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
         w3 = _p(self.flat, o["conv3.weight"])
         both(Launch("head_conv", lib.rd_head_conv_fwd, (_v(d_in_t), w3, B, Hd, Wd, _p(c3map), act)))
@@ -381,7 +392,7 @@ class LatefusionEngine:
         # ============================== backward program ==============================
         bw = self.bwd
         self.dpred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
-        dc3 = torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device)
+        dc3 = self.hold(torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device))
         bw.append(Launch("bilinear_bwd", lib.rd_bilinear_bwd, (_p(self.dpred), B, Hd, Wd, _p(dc3), OH, OW)))
         d_out = self.act(B, Hd, Wd, dec[-1]["co"])
         bw.append(Launch("head_conv_bwd", lib.rd_head_conv_bwd,
@@ -461,6 +472,7 @@ class LatefusionEngine:
                 x_in_v = _v(Bk["x_in"])
                 emit_wgrad(bw, Bk["c1"], _v(g1), x_in_v)
                 dx = self.act(B, hi, wi, Bk["ci"])
+                Bk["dx_t"], Bk["g_t"], Bk["dz2_t"], Bk["g1_t"] = dx, g_t, dz2, g1
                 if bd:
                     emit_conv(bw, Bk["c1"], "d", _v(g1), _v(dx))
                     emit_wgrad(bw, Bk["ds"], _v(dzd), x_in_v)
@@ -505,6 +517,8 @@ class LatefusionEngine:
         self.stats_used = self.stats[:self._stats_used]
         self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd)
         self.dec, self.blocks_all = dec, blocks_all
+        self.dbg = dict(z_stem=z_stem, gz_stem=gz_stem, p_rgb=p_rgb, p_d=p_d, amax=amax, xs=xs, concat=concat, d_concat=d_concat,
+                        zf=zf, zc2=zc2, g_stem=g_stem)
 
     # ------------------------------------------------------------------ execution
     def _run(self, prog: List[Launch]):
@@ -522,15 +536,57 @@ class LatefusionEngine:
             self.adopt(x.device)
         self.configure(B, H, W)
         self.x_in.copy_(x)
+        self._replay("fwd" if training else "fwd_eval", lambda: self._fwd_body(training))
+        return self.pred
+
+    def _fwd_body(self, training: bool):
         if training:
             self.stats_used.zero_()
         self._run(self.fwd if training else self.fwd_eval)
-        return self.pred
+
+    def _bwd_body(self):
+        self.dw.zero_()
+        self._run(self.bwd)
 
     def backward(self, dpred: torch.Tensor, accumulate: bool) -> None:
         """Fills the gradient arena from d(loss)/d(pred).  ``accumulate`` keeps what is already there."""
         self.dpred.copy_(dpred.reshape(self.dpred.shape))
         if not accumulate:
             self.gflat.zero_()
-        self.dw.zero_()
-        self._run(self.bwd)
+        self._replay("bwd", self._bwd_body)
+
+    # ------------------------------------------------------------------ CUDA graphs
+    # The launch programs are static per input shape, so after one eager (warm-up) execution each program is
+    # captured into a CUDA graph and replayed: ~360 kernel launches per step cost one cudaGraphLaunch each way.
+    def _replay(self, which: str, body) -> None:
+        if not self.use_graphs:
+            body()
+            return
+        state = self._graphs.get(which)
+        if state is None:                      # first use: run eagerly (also sets kernel attributes, warms caches)
+            body()
+            self._graphs[which] = "warm"
+            return
+        if state == "warm":
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[which] = g
+            state = g
+        state.replay()
+
+    def launches_per_step(self) -> int:
+        return len(self.fwd) + len(self.bwd)
+
+    def input_grad(self) -> torch.Tensor:
+        """d(loss)/d(x) in NCHW fp32.  Only the stage-2 network of ResNet_multistage needs it (its 5th input channel
+        is the stage-1 prediction, multistage_model.py:75); the 4-channel network never propagates into its input."""
+        if self.dxs is None:
+            raise RuntimeError("input gradients are only produced for in_channels > 4")
+        B, H, W = self.cfg["B"], self.cfg["H"], self.cfg["W"]
+        Cs = self.dxs.shape[-1] // 4
+        H2, W2 = self.dxs.shape[1], self.dxs.shape[2]
+        d = self.dxs.float().view(B, H2, W2, 2, 2, Cs)[..., : self.in_channels]      # [B,H2,W2,py,px,c]
+        d = d.permute(0, 5, 1, 3, 2, 4).reshape(B, self.in_channels, 2 * H2, 2 * W2)
+        return d[:, :, :H, :W].contiguous()

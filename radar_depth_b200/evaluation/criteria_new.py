@@ -1,0 +1,45 @@
+"""Drop-in for the hot-path losses of the reference's evaluation/criteria_new.py on sm_100a kernels.
+
+MaskedL1Loss (criteria_new.py:44-54) is computed WITHOUT the reference's boolean gather (``diff[valid_mask]``
+forces a device->host sync for the dynamic shape): one reduction kernel accumulates sum|target-pred| and the valid
+count in fp64 on the device, a one-thread kernel divides; the backward kernel writes -sign(target-pred)/count.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..ops import ptr, stream_ptr
+
+
+class _MaskedL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred_c = pred.detach().float().contiguous()
+        tgt_c = target.detach().float().contiguous()
+        acc = torch.empty(2, dtype=torch.float64, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        _lib.call("rd_l1_fwd", ptr(pred_c), ptr(tgt_c), pred_c.numel(), ptr(acc), ptr(loss), stream_ptr())
+        ctx.save_for_backward(pred_c, tgt_c, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred_c, tgt_c, acc = ctx.saved_tensors
+        gpred = torch.empty_like(pred_c)
+        g = gout.detach().float().contiguous()
+        _lib.call("rd_l1_bwd", ptr(pred_c), ptr(tgt_c), pred_c.numel(), ptr(acc), ptr(g), ptr(gpred), 0, stream_ptr())
+        return gpred, None
+
+
+class MaskedL1Loss(nn.Module):
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, pred, target):
+        assert pred.dim() == target.dim(), "inconsistent dimensions"      # criteria_new.py:49
+        if not pred.is_cuda:
+            raise _lib.RdError("radar_depth_b200 losses run on a CUDA (sm_100a) device only; there is no CPU fallback")
+        self.loss = _MaskedL1Fn.apply(pred, target)
+        return self.loss

@@ -1,0 +1,264 @@
+"""GPU parity of the HBM-bound kernels (through the C ABI) against plain torch fp32/fp64 references of the same ops."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from radar_depth_b200 import _lib, ops
+from radar_depth_b200._lib import View, call
+from radar_depth_b200.ops import ptr, stream_ptr, view
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # the torch references below must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+NULLV = View(None, 0, 0)
+ACTS = [("bf16", _lib.RD_BF16, torch.bfloat16), ("f32", _lib.RD_F32, torch.float32)]
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def tol(act):
+    return dict(rtol=2e-2, atol=2e-2) if act == _lib.RD_BF16 else dict(rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("name,act,td", ACTS)
+@pytest.mark.parametrize("C,H,W", [(4, 12, 16), (5, 13, 17)])
+def test_input_pack(name, act, td, C, H, W):
+    x = torch.randn(2, C, H, W, device="cuda")
+    Cs = 4 if C <= 4 else 8
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    out = torch.full((2, H2, W2, 4 * Cs), float("nan"), device="cuda", dtype=td)
+    call("rd_input_pack", ptr(x), ptr(out), 2, C, H, W, Cs, act, stream_ptr())
+    ref = torch.zeros(2, H2, W2, 4 * Cs, device="cuda")
+    for py in range(2):
+        for px in range(2):
+            sub = x[:, :, py::2, px::2]
+            ref[:, :sub.shape[2], :sub.shape[3], (py * 2 + px) * Cs:(py * 2 + px) * Cs + C] = sub.permute(0, 2, 3, 1)
+    torch.testing.assert_close(out.float(), ref.to(td).float(), rtol=0, atol=0)
+
+
+def test_bn_finalize_train_and_eval_match_torch_batchnorm():
+    C, n = 48, 2 * 7 * 9
+    x = torch.randn(2, C, 7, 9, device="cuda", dtype=torch.float64) * 2 + 1
+    bn = torch.nn.BatchNorm2d(C).cuda().double()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    rm, rv = bn.running_mean.clone().float(), bn.running_var.clone().float()
+    nbt = torch.tensor(3, device="cuda", dtype=torch.int64)
+    y_ref = bn(x)
+    s = torch.stack([x.sum(dim=(0, 2, 3)), (x * x).sum(dim=(0, 2, 3))]).contiguous()
+    gamma, beta = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
+    vec = torch.zeros(4, C, device="cuda")
+    call("rd_bn_finalize", ptr(s[0]), ptr(s[1]), float(n), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), C, 1, 0.1, 1e-5,
+         ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), stream_ptr())
+    y = x.float() * vec[0][None, :, None, None] + vec[1][None, :, None, None]
+    torch.testing.assert_close(y, y_ref.float(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rm, bn.running_mean.float(), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(rv, bn.running_var.float(), rtol=1e-6, atol=1e-6)
+    assert int(nbt) == 4
+    bn.eval()
+    y_ref = bn(x)
+    call("rd_bn_finalize", None, None, float(n), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), None, C, 0, 0.1, 1e-5,
+         ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), stream_ptr())
+    y = x.float() * vec[0][None, :, None, None] + vec[1][None, :, None, None]
+    torch.testing.assert_close(y, y_ref.float(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,act,td", ACTS)
+@pytest.mark.parametrize("with_ds", [False, True])
+def test_residual_join_forward_backward_vs_autograd(name, act, td, with_ds):
+    """bn_add_act + join_bwd + bn_bwd_finalize + bn_bwd_apply == autograd of relu(bn(z) + identity)."""
+    torch.manual_seed(0)
+    B, C, H, W = 2, 32, 6, 10
+    n = B * H * W
+    z = torch.randn(B, H, W, C, device="cuda").to(td)
+    idt = torch.randn(B, H, W, C, device="cuda").to(td)
+    dout = torch.randn(B, H, W, C, device="cuda").to(td)
+    bn_a, bn_b = torch.nn.BatchNorm2d(C).cuda(), torch.nn.BatchNorm2d(C).cuda()
+    for bn in (bn_a, bn_b):
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.normal_(0, 0.3)
+    zr = nchw(z.float()).requires_grad_(True)
+    ir = nchw(idt.float()).requires_grad_(True)
+    out_ref = F.relu(bn_a(zr) + (bn_b(ir) if with_ds else ir))
+    out_ref.backward(nchw(dout.float()))
+
+    def finalize(t, bn):
+        tf = t.double()
+        s = torch.stack([tf.sum(dim=(0, 1, 2)), (tf * tf).sum(dim=(0, 1, 2))]).contiguous()
+        vec = torch.zeros(7, C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        call("rd_bn_finalize", ptr(s[0]), ptr(s[1]), float(n), ptr(bn.weight.data), ptr(bn.bias.data), ptr(rm), ptr(rv), None, C, 1,
+             0.1, 1e-5, ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), stream_ptr())
+        return vec
+
+    va = finalize(z, bn_a)
+    vb = finalize(idt, bn_b) if with_ds else None
+    out = torch.empty_like(z)
+    call("rd_bn_add_act", view(z), ptr(va[0]), ptr(va[1]), view(idt), ptr(vb[0]) if with_ds else None, ptr(vb[1]) if with_ds else None,
+         view(out), n, C, 0.0, act, stream_ptr())
+    torch.testing.assert_close(out.float(), nhwc(out_ref.detach()), **tol(act))
+    g = torch.empty_like(z)
+    st = torch.zeros(3, C, device="cuda", dtype=torch.float64)
+    call("rd_join_bwd", view(dout), view(out), view(z), view(idt) if with_ds else NULLV, view(g), n, C, 0.0, ptr(st[0]), ptr(st[1]),
+         ptr(st[2]), act, stream_ptr())
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    call("rd_bn_bwd_finalize", ptr(st[0]), ptr(st[1]), float(n), ptr(bn_a.weight.data), ptr(va[2]), ptr(va[3]), C, 1, ptr(dg), ptr(db),
+         ptr(va[4]), ptr(va[5]), ptr(va[6]), stream_ptr())
+    dz = torch.empty_like(z)
+    call("rd_bn_bwd_apply", view(g), view(z), view(dz), ptr(va[4]), ptr(va[5]), ptr(va[6]), n, C, act, stream_ptr())
+    t = dict(rtol=3e-2, atol=3e-2) if act == _lib.RD_BF16 else dict(rtol=1e-4, atol=1e-5)
+    # elements whose pre-activation is within rounding of 0 may flip the mask in bf16: compare in L2
+    rel = (dz.float() - nhwc(zr.grad)).norm() / nhwc(zr.grad).norm()
+    assert rel < (3e-2 if act == _lib.RD_BF16 else 1e-4), rel
+    torch.testing.assert_close(dg, bn_a.weight.grad, **t)
+    torch.testing.assert_close(db, bn_a.bias.grad, **t)
+    if with_ds:
+        dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        call("rd_bn_bwd_finalize", ptr(st[0]), ptr(st[2]), float(n), ptr(bn_b.weight.data), ptr(vb[2]), ptr(vb[3]), C, 1, ptr(dg2),
+             ptr(db2), ptr(vb[4]), ptr(vb[5]), ptr(vb[6]), stream_ptr())
+        did = torch.empty_like(z)
+        call("rd_bn_bwd_apply", view(g), view(idt), view(did), ptr(vb[4]), ptr(vb[5]), ptr(vb[6]), n, C, act, stream_ptr())
+        rel = (did.float() - nhwc(ir.grad)).norm() / nhwc(ir.grad).norm()
+        assert rel < (3e-2 if act == _lib.RD_BF16 else 1e-4), rel
+        torch.testing.assert_close(dg2, bn_b.weight.grad, **t)
+    else:
+        rel = (g.float() - nhwc(ir.grad)).norm() / nhwc(ir.grad).norm()
+        assert rel < (3e-2 if act == _lib.RD_BF16 else 1e-5), rel
+
+
+@pytest.mark.parametrize("name,act,td", ACTS)
+@pytest.mark.parametrize("H,W,ties", [(12, 16, False), (11, 15, False), (12, 16, True)])
+def test_maxpool_forward_backward_vs_autograd(name, act, td, H, W, ties):
+    """Both stems at once: channels [0,64) ReLU, [64,80) LeakyReLU(0.2); arg-max tie rule = first max in window order."""
+    torch.manual_seed(1)
+    B, C, split = 2, 80, 64
+    z = torch.randn(B, H, W, C, device="cuda")
+    if ties:   # mostly-constant map like the depth stem on a ~empty radar image
+        z = torch.zeros(B, H, W, C, device="cuda")
+        z[:, 3, 4] = 1.0
+        z[:, 7, 9] = -2.0
+    z = z.to(td)
+    sc = (torch.rand(C, device="cuda") + 0.5) * torch.where(torch.rand(C, device="cuda") < 0.2, -1.0, 1.0)
+    sh = torch.randn(C, device="cuda") * 0.3
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    oa = torch.empty(B, Ho, Wo, split, device="cuda", dtype=td)
+    ob = torch.empty(B, Ho, Wo, C - split, device="cuda", dtype=td)
+    amax = torch.zeros(B, Ho, Wo, C, device="cuda", dtype=torch.uint8)
+    call("rd_maxpool_fwd", view(z), ptr(sc), ptr(sh), B, H, W, C, split, 0.0, 0.2, view(oa), view(ob), ptr(amax), Ho, Wo, act, stream_ptr())
+    zr = nchw(z.float()).requires_grad_(True)
+    y = zr * sc[None, :, None, None] + sh[None, :, None, None]
+    y = torch.cat([F.relu(y[:, :split]), F.leaky_relu(y[:, split:], 0.2)], 1)
+    if act == _lib.RD_BF16:
+        y = y + (y.detach().bfloat16().float() - y.detach())      # straight-through rounding, like a stored activation
+    pooled = F.max_pool2d(y.cpu(), 3, 2, 1).cuda() if False else F.max_pool2d(y, 3, 2, 1)
+    got = torch.cat([oa, ob], dim=-1).float()
+    torch.testing.assert_close(got, nhwc(pooled.detach()), **tol(act))
+    dpa = torch.randn(B, Ho, Wo, split, device="cuda").to(td)
+    dpb = torch.randn(B, Ho, Wo, C - split, device="cuda").to(td)
+    # CPU autograd defines the tie rule the oracle follows
+    zc = nchw(z.float()).cpu().requires_grad_(True)
+    yc = zc * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None]
+    yc = torch.cat([F.relu(yc[:, :split]), F.leaky_relu(yc[:, split:], 0.2)], 1)
+    if act == _lib.RD_BF16:
+        yc = yc + (yc.detach().bfloat16().float() - yc.detach())
+    F.max_pool2d(yc, 3, 2, 1).backward(nchw(torch.cat([dpa, dpb], -1).float()).cpu())
+    g = torch.empty(B, H, W, C, device="cuda", dtype=td)
+    st = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    call("rd_maxpool_bwd", view(dpa), view(dpb), ptr(amax), view(z), ptr(sc), ptr(sh), B, H, W, C, split, 0.0, 0.2, Ho, Wo, view(g),
+         ptr(st[0]), ptr(st[1]), act, stream_ptr())
+    gref = nhwc(zc.grad).cuda() / sc          # gradient w.r.t. the BN output's pre-activation y... undo the affine
+    torch.testing.assert_close(g.float(), gref, **(dict(rtol=2e-2, atol=2e-2) if act == _lib.RD_BF16 else dict(rtol=1e-5, atol=1e-5)))
+    # the statistics are accumulated from the fp32 values before the store rounds them (bf16: ~2^-9 per element)
+    st_tol = dict(rtol=1e-3, atol=1e-3) if act == _lib.RD_F32 else dict(rtol=2e-2, atol=8e-2)
+    torch.testing.assert_close(st[0].float(), g.float().sum(dim=(0, 1, 2)), **st_tol)
+    torch.testing.assert_close(st[1].float(), (g.float() * z.float()).sum(dim=(0, 1, 2)), **st_tol)
+
+
+@pytest.mark.parametrize("name,act,td", ACTS)
+def test_head_conv_and_bilinear_vs_autograd(name, act, td):
+    torch.manual_seed(2)
+    B, H, W, OH, OW = 2, 11, 19, 23, 37
+    x = torch.randn(B, H, W, 16, device="cuda").to(td)
+    w = (torch.randn(1, 16, 3, 3, device="cuda") * 0.2).contiguous()
+    xr = nchw(x.float()).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    c3_ref = F.conv2d(xr, wr, None, 1, 1)
+    pred_ref = F.interpolate(c3_ref, size=(OH, OW), mode="bilinear", align_corners=True)
+    dpred = torch.randn(B, 1, OH, OW, device="cuda")
+    pred_ref.backward(dpred)
+    c3 = torch.empty(B, H, W, device="cuda")
+    pred = torch.empty(B, 1, OH, OW, device="cuda")
+    call("rd_head_conv_fwd", view(x), ptr(w), B, H, W, ptr(c3), act, stream_ptr())
+    call("rd_bilinear_fwd", ptr(c3), B, H, W, ptr(pred), OH, OW, stream_ptr())
+    torch.testing.assert_close(pred, pred_ref.detach(), rtol=1e-4, atol=1e-4)
+    dc3 = torch.empty(B, H, W, device="cuda")
+    call("rd_bilinear_bwd", ptr(dpred), B, H, W, ptr(dc3), OH, OW, stream_ptr())
+    dx = torch.empty_like(x)
+    dw = torch.zeros(144, device="cuda")
+    call("rd_head_conv_bwd", ptr(dc3), view(x), ptr(w), B, H, W, view(dx), ptr(dw), act, stream_ptr())
+    torch.testing.assert_close(dx.float(), nhwc(xr.grad), **(dict(rtol=2e-2, atol=2e-2) if act == _lib.RD_BF16 else dict(rtol=1e-4, atol=1e-5)))
+    torch.testing.assert_close(dw.view(1, 16, 3, 3), wr.grad, rtol=1e-3, atol=1e-3)
+
+
+def test_masked_l1_forward_backward_vs_reference_formula():
+    torch.manual_seed(3)
+    pred = (torch.rand(2, 1, 24, 40, device="cuda") * 30).requires_grad_(True)
+    tgt = torch.rand(2, 1, 24, 40, device="cuda") * 50
+    tgt[torch.rand_like(tgt) < 0.7] = 0
+    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+    crit = MaskedL1Loss()
+    loss = crit(pred, tgt)
+    (loss * 3.0).backward()
+    p2 = pred.detach().clone().requires_grad_(True)
+    ref = (tgt - p2)[tgt > 0].abs().mean()            # criteria_new.py:50-53
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 and crit.loss is loss
+    torch.testing.assert_close(pred.grad, p2.grad, rtol=1e-5, atol=1e-9)
+    with pytest.raises(AssertionError):
+        crit(pred[0], tgt)
+
+
+def test_sid_filter_matches_reference_formula():
+    torch.manual_seed(4)
+    d = torch.rand(2, 1, 20, 30, device="cuda") * 80
+    r = torch.zeros_like(d)
+    mk = torch.rand_like(d) < 0.3
+    r[mk] = torch.rand(int(mk.sum()), device="cuda") * 80 + 1
+    rf, mask = torch.empty_like(d), torch.empty_like(d)
+    call("rd_sid_filter", ptr(r), ptr(d), d.numel(), ptr(rf), ptr(mask), stream_ptr())
+    thr = torch.exp(d * math.log(18.0 / 5.0) / 100.0 + math.log(5.0))      # multistage_model.py:96-100
+    mref = ((d - r).abs() <= thr).float()
+    assert (mask != mref).float().mean() < 1e-3      # only exact-threshold ties may differ
+    torch.testing.assert_close(rf, r * mask)
+
+
+def test_pack_unpack_and_sgd():
+    torch.manual_seed(5)
+    src = torch.randn(1000, device="cuda")
+    idx = torch.randint(-1, 1000, (4096,), device="cuda", dtype=torch.int32)
+    lo = idx.clone()
+    lo[idx >= 0] |= (1 << 30)
+    out = ops.pack_weights(src, torch.cat([idx, lo]))
+    hi_ref = torch.where(idx >= 0, src[idx.clamp(min=0).long()], torch.zeros((), device="cuda")).bfloat16()
+    assert torch.equal(out[:4096], hi_ref)
+    lo_ref = torch.where(idx >= 0, src[idx.clamp(min=0).long()] - hi_ref.float(), torch.zeros((), device="cuda")).bfloat16()
+    assert torch.equal(out[4096:], lo_ref)
+    p, g, m = torch.randn(777, device="cuda"), torch.randn(777, device="cuda"), torch.zeros(777, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    for step in range(3):
+        pr.grad = g.clone()
+        opt.step()
+        call("rd_sgd", ptr(p), ptr(g), ptr(m), 777, 0.01, 0.9, 1e-4, 1 if step == 0 else 0, stream_ptr())
+    torch.testing.assert_close(p, pr.detach(), rtol=1e-6, atol=1e-7)

@@ -1,0 +1,197 @@
+"""Whole-model parity on the GPU: ResNet_latefusion on the sm_100a kernels vs the CPU oracle (itself pinned to the
+reference by tests/golden) on the same seeded inputs and weights, forward + MaskedL1 + backward + BN buffers.
+
+Tolerances.  north_star: outputs within 1e-3 relative of the reference fp32 forward, losses within 1e-4 -- checked
+in the fp32 parity mode (fp32 activations, 3-term bf16 split on the tensor cores).  bf16 throughput mode is
+compared at the level the reference's OWN bf16-autocast run differs from its fp32 run (5.7e-2 rel-L2 in train mode,
+SURVEY.md 7.2-1).
+
+Gradients.  d(loss)/d(param) of this network is NOT a smooth function of the forward values: every ReLU mask and the
+sign() of the L1 loss flip for elements whose forward value is within the forward error of zero, so a forward
+relative error e produces a gradient rel-L2 error ~ sqrt(e) (measured: the fp32 oracle vs the fp64 oracle differs
+by 4e-3 in gradients for a 1e-6 forward difference; the fp32 parity mode, forward error 2e-4, differs by 1-3e-2,
+growing smoothly from 1e-6 at conv3 to 3e-2 at the stems, cosine > 0.999).  Small images make it worse (layer4 has
+12 samples per BatchNorm channel at 64x96).  So gradients are checked three ways: (1) per-tensor rel-L2 / cosine
+against the oracle with those measured bounds, tightest at full size; (2) exactly, kernel by kernel, in
+tests/test_kernels_gpu.py and tests/test_elementwise_gpu.py; (3) by a directional-derivative test of the engine's
+backward against its own forward, which does not depend on the oracle at all."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as O
+from radar_depth_b200.model.models import ResNet_latefusion
+from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _check_grads(m, ref, rel_tol, cos_tol):
+    scale = float(ref["grads"]["conv3.weight"].norm())
+    worst_rel, worst_cos = ("", 0.0), ("", 1.0)
+    for k, p in m.named_parameters():
+        g_ref = ref["grads"][k]
+        assert p.grad is not None, k
+        g = p.grad.double().cpu()
+        # (bn_fusion.bias has an exactly-zero gradient: it feeds conv2 -> bn2, which removes any constant)
+        r = float((g - g_ref).norm() / (g_ref.norm() + 1e-4 * scale))
+        if r > worst_rel[1]:
+            worst_rel = (k, r)
+        if float(g_ref.norm()) > 1e-6 * scale:
+            c = float((g * g_ref).sum() / (g.norm() * g_ref.norm()))
+            if c < worst_cos[1]:
+                worst_cos = (k, c)
+    assert worst_rel[1] < rel_tol, worst_rel
+    assert worst_cos[1] > cos_tol, worst_cos
+
+
+def _build(cin, hw, precision, training=True):
+    m = ResNet_latefusion(18, "upproj", hw, cin, pretrained=False)
+    sd = O.synth_state_dict(O.latefusion_entries(cin))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    m.precision = precision
+    m.train(training)
+    return m, sd
+
+
+def _inputs(b, h, w, cin):
+    inputs, target = O.synth_batch(b, h, w)
+    if cin == 5:
+        gen = torch.Generator().manual_seed(99)
+        inputs = torch.cat((inputs, torch.rand(b, 1, h, w, generator=gen) * 40), dim=1)
+    return inputs, target
+
+
+@pytest.mark.parametrize("cin,h,w", [(4, 64, 96), (4, 90, 160), (5, 64, 96)])
+def test_train_step_parity_fp32_mode(cin, h, w):
+    m, sd = _build(cin, (h, w), "fp32")
+    inputs, target = _inputs(2, h, w, cin)
+    ref = O.train_step(sd, inputs, target, "latefusion", dtype=torch.float64)
+    crit = MaskedL1Loss()
+    pred = m(inputs.cuda())
+    loss = crit(pred, target.cuda())
+    loss.backward()
+    assert _rel(pred, ref["pred"]) < 1e-3
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-4 * max(1.0, abs(float(ref["loss"])))
+    _check_grads(m, ref, rel_tol=0.25, cos_tol=0.98)          # tiny maps: see the module docstring
+    for k, v in ref["new_buffers"].items():
+        got = m.state_dict()[k]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(v), k
+        else:
+            np.testing.assert_allclose(got.cpu().numpy(), v.float().numpy(), rtol=2e-4, atol=1e-5, err_msg=k)
+
+
+def test_matches_reference_golden_fixture_fp32_mode():
+    g = np.load(os.path.join(GOLDEN, "latefusion_train_b2_64x96.npz"))
+    m, _ = _build(4, (64, 96), "fp32")
+    inputs, target = _inputs(2, 64, 96, 4)
+    pred = m(inputs.cuda())
+    loss = MaskedL1Loss()(pred, target.cuda())
+    assert _rel(pred, torch.from_numpy(g["pred"])) < 1e-3
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
+
+
+def test_eval_forward_parity_fp32_mode():
+    g = np.load(os.path.join(GOLDEN, "latefusion_eval_b1_64x96.npz"))
+    m, _ = _build(4, (64, 96), "fp32", training=False)
+    inputs, target = _inputs(1, 64, 96, 4)
+    with torch.no_grad():
+        pred = m(inputs.cuda())
+    assert _rel(pred, torch.from_numpy(g["pred"])) < 1e-3
+    assert int(m.bn1.num_batches_tracked) == 3                 # untouched in eval mode
+
+
+def test_train_step_bf16_mode_within_autocast_level():
+    m, sd = _build(4, (64, 96), "bf16")
+    inputs, target = _inputs(2, 64, 96, 4)
+    ref = O.train_step(sd, inputs, target, "latefusion", dtype=torch.float64)
+    pred = m(inputs.cuda())
+    loss = MaskedL1Loss()(pred, target.cuda())
+    loss.backward()
+    assert _rel(pred, ref["pred"]) < 6e-2
+    assert abs(float(loss) - float(ref["loss"])) <= 2e-2 * abs(float(ref["loss"]))
+    for k in ("conv3.weight", "decoder.layer4.upper_branch.conv2.weight", "conv2.weight"):
+        assert _rel(dict(m.named_parameters())[k].grad, ref["grads"][k]) < 0.25, k
+
+
+def test_sgd_steps_follow_oracle_fp32_mode():
+    """Three SGD steps (main.py:285-290, 443-445) through torch.optim.SGD on the arena-backed parameters."""
+    m, sd = _build(4, (64, 96), "fp32")
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    crit = MaskedL1Loss()
+    inputs, target = _inputs(2, 64, 96, 4)
+    cur, mom = dict(sd), None
+    for step in range(3):
+        ref = O.train_step(cur, inputs, target, "latefusion", dtype=torch.float64)
+        pred = m(inputs.cuda())
+        loss = crit(pred, target.cuda())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"])), step
+        cur, mom = O.sgd_step({k: v.double() if v.dtype.is_floating_point else v for k, v in cur.items()},
+                              ref["grads"], mom)
+        cur.update({k: v for k, v in ref["new_buffers"].items()})
+
+
+def test_full_size_train_step_parity_fp32_mode():
+    """352x1216 (BASELINE.json configs[0] shape, b=2): oracle in fp64 on the host + the reference's golden fixture."""
+    g = np.load(os.path.join(GOLDEN, "latefusion_train_b2_352x1216.npz"))
+    m, sd = _build(4, (352, 1216), "fp32")
+    inputs, target = _inputs(2, 352, 1216, 4)
+    ref = O.train_step(sd, inputs, target, "latefusion", dtype=torch.float64)
+    pred = m(inputs.cuda())
+    loss = MaskedL1Loss()(pred, target.cuda())
+    loss.backward()
+    assert _rel(pred, ref["pred"]) < 1e-3
+    assert _rel(pred[..., ::8, ::8], torch.from_numpy(g["pred"])) < 1e-3            # the real reference's output
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    _check_grads(m, ref, rel_tol=6e-2, cos_tol=0.998)
+    names = [str(n) for n in g["grad_names"]]
+    got = dict(m.named_parameters())
+    for i, k in enumerate(names):                                                    # reference's own gradient norms
+        rn = float(g["grad_norms"][i])
+        assert abs(float(got[k].grad.double().norm()) - rn) <= 6e-2 * rn + 1e-6, k
+
+
+def test_backward_is_the_derivative_of_forward_fp32_mode():
+    """Directional derivatives: (L(w + eps d) - L(w - eps d)) / 2 eps == <grad, d> using only the engine itself."""
+    m, sd = _build(4, (96, 160), "fp32")
+    inputs, target = _inputs(2, 96, 160, 4)
+    x, t = inputs.cuda(), target.cuda()
+    crit = MaskedL1Loss()
+    loss = crit(m(x), t)
+    loss.backward()
+    params = dict(m.named_parameters())
+    grads = {k: p.grad.detach().clone() for k, p in params.items()}
+    groups = {"all": list(params), "stems": ["conv1.weight", "conv1_depth.weight", "bn1.weight", "bn1_depth.bias"],
+              "rgb_encoder": [k for k in params if k.startswith("layer") and "_depth" not in k],
+              "depth_encoder": [k for k in params if "_depth" in k and k.startswith("layer")],
+              "fusion": ["conv_fusion.weight", "bn_fusion.weight", "conv2.weight", "bn2.bias"],
+              "decoder": [k for k in params if k.startswith("decoder")], "head": ["conv3.weight"]}
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for gname, keys in groups.items():
+        dirs = {k: torch.randn(params[k].shape, device="cuda", generator=gen) * params[k].detach().abs().mean().clamp_min(1e-3)
+                for k in keys}
+        analytic = sum(float((grads[k].double() * dirs[k].double()).sum()) for k in keys)
+        eps = 2e-4
+        vals = []
+        with torch.no_grad():
+            for sgn in (+1, -1):
+                for k in keys:
+                    params[k].add_(dirs[k], alpha=sgn * eps)
+                vals.append(float(crit(m(x), t)))
+                for k in keys:
+                    params[k].add_(dirs[k], alpha=-sgn * eps)
+        numeric = (vals[0] - vals[1]) / (2 * eps)
+        assert abs(numeric - analytic) <= 3e-2 * abs(analytic) + 1e-3, (gname, numeric, analytic)
