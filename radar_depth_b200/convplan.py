@@ -219,7 +219,10 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
             mma = MB * ntaps * max(N, 32) / 2.0 * (3 if parts == 2 else 1)
             load = planes * plane_slots * 2 * 0.35 * parts
             epi = MB * P * (N / 16.0) * 40.0
-            per_tile = max(mma, load) * ncblk + epi + 600.0
+            if 2 * P * MB * N <= 512:          # two accumulator sets: the epilogue overlaps the next tile's MMAs
+                per_tile = max(max(mma, load) * ncblk, epi) + 300.0
+            else:
+                per_tile = max(mma, load) * ncblk + epi + 600.0
             return_tiles = ty * tx
             cost = return_tiles * per_tile
             if best is None or cost < best[0]:

@@ -25,6 +25,7 @@ namespace rd {
 constexpr int kFpropThreads = 320;
 constexpr int kSmemHeader = 16384;      // barriers, tmem slot, stats, BN vectors
 constexpr int kOffTmemSlot = 256;
+constexpr int kOffTapTable = 512;       // int[3][32]: a_shift, accumulator column, first-of-phase flag
 constexpr int kOffStats = 1024;         // float[512]
 constexpr int kOffEpScale = 3072;       // float[256]
 constexpr int kOffEpShift = 4096;       // float[256]
@@ -83,8 +84,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     uint64_t* in_empty = bars + kMaxStages;
     uint64_t* w_full = bars + 2 * kMaxStages;
     uint64_t* w_empty = bars + 3 * kMaxStages;
-    uint64_t* tmem_full = bars + 4 * kMaxStages;
-    uint64_t* tmem_empty = bars + 4 * kMaxStages + 1;
+    uint64_t* tmem_full = bars + 4 * kMaxStages;        // [2]
+    uint64_t* tmem_empty = bars + 4 * kMaxStages + 2;   // [2]
+    int* tap_a = reinterpret_cast<int*>(smem + kOffTapTable);
+    int* tap_d = tap_a + 32;
+    int* tap_f = tap_a + 64;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmemSlot);
     float* stats_s = reinterpret_cast<float*>(smem + kOffStats);
     float* ep_sc = reinterpret_cast<float*>(smem + kOffEpScale);
@@ -105,10 +109,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     if (tid == 0) {
         for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], 4); mbar_init(&in_empty[i], 1); }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_mbar_init();
     }
+    if (tid < p.ntaps) {
+        tap_a[tid] = p.taps[tid].a_shift;
+        tap_d[tid] = p.taps[tid].phase * p.MB * p.N;
+        tap_f[tid] = p.taps[tid].first;
+    }
+    // two accumulator sets when they fit: the epilogue of tile i overlaps the MMAs of tile i+1
+    const int acc_cols = p.P * p.MB * p.N;
+    const bool dbuf = 2 * acc_cols <= 512;
     for (int i = tid; i < 512; i += kFpropThreads) stats_s[i] = 0.f;
     if (p.ld_scale) {
         for (int i = tid; i < p.Cin; i += kFpropThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.plane_slots = p.plane_slots; ts.plane_rows = p.plane_rows; ts.Wl = p.Wl; ts.oy0 = p.sy_min; ts.ox0 = p.sx_min;
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
+        ts.prepare();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -177,33 +189,35 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const uint32_t a_lbo = PS * 16u;
             const uint32_t b_lbo = (uint32_t)p.N * 16u;
             const uint32_t tap_bytes = (uint32_t)PARTS * p.N * 32u;
+            const uint32_t a_units = PS;                         // chunk stride in 16-byte units
+            const uint32_t tap_units = tap_bytes >> 4;
             uint32_t tile_iter = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
-                mbar_wait(tmem_empty, (tile_iter & 1) ^ 1, 0x300);
+                const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
+                const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
+                mbar_wait(&tmem_empty[ab], (use & 1u) ^ 1u, 0x300);
                 tc_fence_after();
+                const uint32_t d_tile = tmem_base + ab * (uint32_t)acc_cols;
                 for (int c = 0; c < ncblk; ++c) {
                     mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_ring + (size_t)si.stage * p.istage_bytes);
+                    const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), a_lbo, 128);
+                    int t = 0;
                     for (int g = 0; g < p.ngroups; ++g) {
                         mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
                         tc_fence_after();
-                        const uint32_t w_base = smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes);
-                        for (int tl = 0; tl < p.grp_n[g]; ++tl) {
-                            const rd_tap tp = p.taps[p.grp_first[g] + tl];
-                            const uint32_t fresh = (c == 0 && tp.first) ? 1u : 0u;
-                            for (int mb = 0; mb < p.MB; ++mb) {
-                                const uint32_t d = tmem_base + (uint32_t)((tp.phase * p.MB + mb) * p.N);
-                                const uint32_t a_hi = a_base + ((uint32_t)(tp.a_shift + mb * 128) << 4);
-                                const uint32_t b_hi = w_base + (uint32_t)tl * tap_bytes;
-                                const uint64_t da = make_smem_desc(a_hi, a_lbo, 128);
-                                const uint64_t db = make_smem_desc(b_hi, b_lbo, 128);
-                                umma_bf16(d, da, db, idesc, fresh ? 0u : 1u);
+                        uint64_t db = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), b_lbo, 128);
+                        const int gn = p.grp_n[g];
+                        for (int tl = 0; tl < gn; ++tl, ++t, db += tap_units) {
+                            uint64_t da = da0 + (uint32_t)tap_a[t];
+                            uint32_t d = d_tile + (uint32_t)tap_d[t];
+                            const uint32_t acc = (c == 0 && tap_f[t]) ? 0u : 1u;
+#pragma unroll 1
+                            for (int mb = 0; mb < p.MB; ++mb, da += 128, d += (uint32_t)p.N) {
+                                umma_bf16(d, da, db, idesc, acc);
                                 if (SPLIT == 3) {
-                                    const uint64_t da_lo = make_smem_desc(a_hi + 2u * a_lbo, a_lbo, 128);
-                                    const uint64_t db_lo = make_smem_desc(b_hi + (uint32_t)p.N * 32u, b_lbo, 128);
-                                    umma_bf16(d, da, db_lo, idesc, 1u);
-                                    umma_bf16(d, da_lo, db, idesc, 1u);
+                                    umma_bf16(d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
+                                    umma_bf16(d, da + 2u * a_units, db, idesc, 1u);
                                 }
                             }
                         }
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     umma_commit(&in_empty[si.stage]);
                     si.advance();
                 }
-                umma_commit(tmem_full);
+                umma_commit(&tmem_full[ab]);
             }
         }
         __syncwarp();
@@ -223,14 +237,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
         const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
         const bool want_stats = p.stats != nullptr;
+        const FastDiv fd_wl((uint32_t)p.Wl);
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
-            mbar_wait(tmem_full, tile_iter & 1, 0x400);
+            const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
+            const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
+            mbar_wait(&tmem_full[ab], use & 1u, 0x400);
             tc_fence_after();
+            const uint32_t t_tile = tmem_base + ab * (uint32_t)acc_cols + ((uint32_t)(warp * 32) << 16);
             for (int cc = 0; cc < (p.N >> 4); ++cc) {
                 float s1[16], s2[16];
 #pragma unroll
@@ -238,12 +256,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 for (int ph = 0; ph < p.P; ++ph) {
                     for (int mb = 0; mb < p.MB; ++mb) {
                         const int m = mb * 128 + warp * 32 + lane;
-                        const int ly = m / p.Wl, lx = m - ly * p.Wl;
+                        const int ly = (int)fd_wl.div((uint32_t)m), lx = m - ly * p.Wl;
                         const int oy = y0 + ly, ox = x0 + lx;
                         const int fy = oy * p.OS + p.phase_y[ph], fx = ox * p.OS + p.phase_x[ph];
                         const bool valid = ly < p.Ht && lx < p.Wt && oy < p.Hb && ox < p.Wb && fy < p.dstH && fx < p.dstW;
                         float v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((ph * p.MB + mb) * p.N + cc * 16), v);
+                        tmem_ld16(t_tile + (uint32_t)((ph * p.MB + mb) * p.N + cc * 16), v);
                         if (valid) {
                             const size_t pix = ((size_t)img * p.dstH + fy) * p.dstW + fx;
                             const int ch = nb * p.N + cc * 16;
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
+            if (lane == 0) mbar_arrive(&tmem_empty[ab]);
         }
         if (want_stats) {
             asm volatile("bar.sync 1, 128;\n" ::: "memory");

@@ -20,6 +20,7 @@ namespace rd {
 constexpr int kWgradThreads = 288;
 constexpr int kWgSmemHeader = 10240;     // barriers + tmem slot + BN scale/shift (2 x 1024 floats)
 constexpr int kWgOffTmemSlot = 256;
+constexpr int kWgOffTaps = 512;          // int[2][32]: gradient-plane offset, source shift (16-byte units)
 constexpr int kWgOffLdScale = 1024;
 constexpr int kWgOffLdShift = 5120;
 
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     float* ld_sc = reinterpret_cast<float*>(smem + kWgOffLdScale);
     float* ld_sh = reinterpret_cast<float*>(smem + kWgOffLdShift);
     uint8_t* ring = smem + kWgSmemHeader;
+    int* tap_g = reinterpret_cast<int*>(smem + kWgOffTaps);
+    int* tap_x = tap_g + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cob = blockIdx.y;
@@ -57,6 +60,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
+    }
+    if (tid < T_n) {
+        tap_g[tid] = p.taps[t0 + tid].g_off;
+        tap_x[tid] = p.taps[t0 + tid].x_shift;
     }
     if (p.ld_scale) {
         for (int i = tid; i < p.Cin; i += kWgradThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tx_.plane_slots = p.x_plane_slots; tx_.plane_rows = p.x_plane_rows; tx_.Wl = p.Wl; tx_.oy0 = p.sy_min; tx_.ox0 = p.sx_min;
         tx_.vrows = p.x_plane_rows; tx_.vcols = p.Wl;
         tx_.sc = p.ld_scale ? ld_sc : nullptr; tx_.sh = ld_sh; tx_.slope = p.ld_slope;
+        tg_.prepare(); tx_.prepare();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -105,22 +113,19 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
                 tc_fence_after();
                 const uint32_t g_base = smem_u32(ring + (size_t)st.stage * p.stage_bytes);
-                const uint32_t x_base = g_base + (uint32_t)p.g_bytes;
+                const uint64_t da0 = make_smem_desc(g_base, 128, g_sbo);
+                const uint64_t db0 = make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
                 for (int kg = 0; kg < KG; ++kg) {
                     const uint32_t acc = (first_tile && kg == 0) ? 0u : 1u;
-                    for (int tl = 0; tl < T_n; ++tl) {
-                        const rd_wtap tp = p.taps[t0 + tl];
-                        const uint32_t a = g_base + ((uint32_t)(tp.g_off + kg * 16) << 4);
-                        const uint32_t b = x_base + ((uint32_t)(tp.x_shift + kg * 16) << 4);
-                        const uint32_t d = tmem_base + (uint32_t)(tl * p.Nc);
-                        const uint64_t da = make_smem_desc(a, 128, g_sbo);
-                        const uint64_t db = make_smem_desc(b, 128, x_sbo);
+                    uint32_t d = tmem_base;
+#pragma unroll 1
+                    for (int tl = 0; tl < T_n; ++tl, d += (uint32_t)p.Nc) {
+                        const uint64_t da = da0 + (uint32_t)(tap_g[tl] + kg * 16);
+                        const uint64_t db = db0 + (uint32_t)(tap_x[tl] + kg * 16);
                         umma_bf16(d, da, db, idesc, acc);
                         if (SPLIT == 3) {
-                            const uint64_t da_lo = make_smem_desc(a + (uint32_t)g_chunks * g_sbo, 128, g_sbo);
-                            const uint64_t db_lo = make_smem_desc(b + (uint32_t)x_chunks * x_sbo, 128, x_sbo);
-                            umma_bf16(d, da, db_lo, idesc, 1u);
-                            umma_bf16(d, da_lo, db, idesc, 1u);
+                            umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
+                            umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
                         }
                     }
                 }

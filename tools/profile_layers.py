@@ -1,0 +1,59 @@
+"""Per-launch CUDA-event timing of one training step (eager), with algorithmic TFLOP/s per convolution program."""
+import statistics
+import sys
+import torch
+from radar_depth_b200.model.models import ResNet_latefusion
+from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+sys.path.insert(0, ".")
+from bench import synth_host_batch, H, W
+
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+torch.manual_seed(0)
+m = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False).cuda().train()
+m.precision = prec
+x, t = synth_host_batch(b, 1234)
+x, t = x.cuda(), t.cuda()
+crit = MaskedL1Loss()
+m._get_engine().use_graphs = False
+for _ in range(3):
+    crit(m(x), t).backward()
+torch.cuda.synchronize()
+eng = m._engine
+flops = {}
+for rec in eng.convs:
+    g = rec["g"]
+    p = rec["fplan"].params
+    base = b * p.Hb * p.Wb
+    # exact MACs: every tap touches every base pixel once (border zeros included, as cuDNN counts them)
+    f = 2.0 * base * len(g.taps) * g.Cx * g.N
+    if rec["name"] == "stem":
+        f = 2.0 * b * p.Hb * p.Wb * (49 * 3 * 64 + 49 * (g.Cx // 4 - 3 if g.Cx == 16 else 2) * 16)
+    flops[rec["name"]] = f
+st = torch.cuda.current_stream().cuda_stream
+rows = []
+for prog in (eng.fwd, eng.bwd):
+    for L in prog:
+        evs = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); rc = L.fn(*L.args, st); e1.record()
+            assert rc == 0
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = statistics.median(a.elapsed_time(c) for a, c in evs)
+        rows.append((L.name, ms))
+tot = sum(r[1] for r in rows)
+print(f"total {tot:.3f} ms over {len(rows)} launches, b={b} {prec}")
+for name, ms in sorted(rows, key=lambda r: -r[1])[:70]:
+    kind, _, lname = name.partition(":")
+    lname = lname.replace("(eval)", "")
+    tf = ""
+    if kind in ("conv_f", "conv_d", "wgrad") and lname in flops:
+        tf = f"{flops[lname] / (ms * 1e-3) / 1e12:8.1f} TFLOP/s"
+    print(f"{ms:8.4f} ms  {100 * ms / tot:5.1f}%  {name:60s} {tf}")
+agg = {}
+for name, ms in rows:
+    k = name.split(":")[0]
+    agg[k] = agg.get(k, 0) + ms
+print({k: round(v, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])})
