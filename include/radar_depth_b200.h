@@ -191,6 +191,13 @@ int rd_l1_fwd(const float* pred, const float* target, long long n, double* acc, 
 int rd_l1_bwd(const float* pred, const float* target, long long n, const double* acc, const float* gout,
               float* gpred, int accumulate, void* stream);
 
+/* SmoothnessLoss (criteria_new.py:8-28); image = the C-channel tensor main.py:422 passes (all 4 network inputs).
+ * scratch = 2*B+2 doubles (per-image sums, the two loss terms, per-image sum of G*d); fwd zeroes it, bwd reuses it. */
+int rd_smoothness_fwd(const float* pred, const float* image, int B, int C, int H, int W, double* scratch, float* loss,
+                      void* stream);
+int rd_smoothness_bwd(const float* pred, const float* image, int B, int C, int H, int W, double* scratch,
+                      const float* gout, float* gpred, int accumulate, void* stream);
+
 /* Filter_layer (multistage_model.py:87-119). */
 int rd_sid_filter(const float* radar, const float* depth, long long n, float* radar_f, float* mask, void* stream);
 

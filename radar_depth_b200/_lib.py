@@ -93,6 +93,8 @@ _PROTOS = {
     "rd_bilinear_bwd": ([_P, _I, _I, _I, _P, _I, _I, _P], _I),
     "rd_l1_fwd": ([_P, _P, _LL, _P, _P, _P], _I),
     "rd_l1_bwd": ([_P, _P, _LL, _P, _P, _P, _I, _P], _I),
+    "rd_smoothness_fwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
+    "rd_smoothness_bwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P], _I),
     "rd_sid_filter": ([_P, _P, _LL, _P, _P, _P], _I),
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),

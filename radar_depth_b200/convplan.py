@@ -364,7 +364,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
             nc -= 16
     Nc = nc
     ncib = g.Cx // Nc
-    tg_cap = max(1, 512 // Nc)
+    tg_cap = max(1, min(16, 512 // Nc))
     ntg = -(-ntaps // tg_cap)
     tg_size = -(-ntaps // ntg)
     # tile search: KS slots per plane, minimise staged bytes per useful pixel subject to >= 2 stages

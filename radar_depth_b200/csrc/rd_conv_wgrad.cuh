@@ -18,6 +18,7 @@
 namespace rd {
 
 constexpr int kWgradThreads = 288;
+constexpr int kMaxTapsPerCta = 16;       // taps (TMEM accumulators) handled by one CTA
 constexpr int kWgSmemHeader = 10240;     // barriers + tmem slot + BN scale/shift (2 x 1024 floats)
 constexpr int kWgOffTmemSlot = 256;
 constexpr int kWgOffTaps = 512;          // int[2][32]: gradient-plane offset, source shift (16-byte units)
@@ -109,6 +110,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = (uint32_t)XPS * 16u;
             const int KG = p.KS >> 4;
             bool first_tile = true;
+            uint32_t tg_r[kMaxTapsPerCta], tx_r[kMaxTapsPerCta];
+#pragma unroll
+            for (int tl = 0; tl < kMaxTapsPerCta; ++tl) {
+                tg_r[tl] = tl < T_n ? (uint32_t)tap_g[tl] : 0u;
+                tx_r[tl] = tl < T_n ? (uint32_t)tap_x[tl] : 0u;
+            }
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
                 tc_fence_after();
@@ -117,15 +124,20 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 const uint64_t db0 = make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
                 for (int kg = 0; kg < KG; ++kg) {
                     const uint32_t acc = (first_tile && kg == 0) ? 0u : 1u;
-                    uint32_t d = tmem_base;
-#pragma unroll 1
-                    for (int tl = 0; tl < T_n; ++tl, d += (uint32_t)p.Nc) {
-                        const uint64_t da = da0 + (uint32_t)(tap_g[tl] + kg * 16);
-                        const uint64_t db = db0 + (uint32_t)(tap_x[tl] + kg * 16);
-                        umma_bf16(d, da, db, idesc, acc);
-                        if (SPLIT == 3) {
-                            umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
-                            umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
+                    const uint64_t dak = da0 + (uint32_t)(kg * 16);
+                    const uint64_t dbk = db0 + (uint32_t)(kg * 16);
+                    // tap offsets live in registers (fully unrolled, predicated): ~5 instructions per UMMA issued
+#pragma unroll
+                    for (int tl = 0; tl < kMaxTapsPerCta; ++tl) {
+                        if (tl < T_n) {
+                            const uint32_t d = tmem_base + (uint32_t)(tl * p.Nc);
+                            const uint64_t da = dak + tg_r[tl];
+                            const uint64_t db = dbk + tx_r[tl];
+                            umma_bf16(d, da, db, idesc, acc);
+                            if (SPLIT == 3) {
+                                umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
+                                umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
+                            }
                         }
                     }
                 }

@@ -583,4 +583,76 @@ __global__ void sid_filter_kernel(const float* __restrict__ radar, const float* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SmoothnessLoss (criteria_new.py:8-28): d^ = d / (mean_HW(d) + 1e-7);
+//   loss = mean(|dx d^| * exp(-mean_c |dx I|)) + mean(|dy d^| * exp(-mean_c |dy I|)).
+// The reference calls it with the full 4-channel network input as "image" (main.py:422), so C is a parameter.
+__global__ void image_sum_kernel(const float* __restrict__ d, int B, size_t hw, double* sums /*[B]*/) {
+    const int b = blockIdx.y;
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += d[b * hw + i];
+    s = warp_sum(s);
+    __shared__ float ss[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) ss[w] = s;
+    __syncthreads();
+    if (w == 0) {
+        s = l < (int)(blockDim.x >> 5) ? ss[l] : 0.f;
+        s = warp_sum(s);
+        if (l == 0) atomicAdd(&sums[b], (double)s);
+    }
+}
+
+__device__ __forceinline__ float edge_weight(const float* __restrict__ img, int C, size_t hw, size_t p, size_t q) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a += fabsf(img[c * hw + p] - img[c * hw + q]);
+    return __expf(-a / (float)C);
+}
+__device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+// mode 0: acc[0] += sum_x terms, acc[1] += sum_y terms (forward).
+// mode 1: gd[b] += sum_p G[p] * d[p]  where G = d loss / d d^ (first backward pass).
+// mode 2: grad[p] (+)= gout * (G[p] * r_b - r_b^2 * gd[b] / (H*W))   (second backward pass).
+__global__ void smoothness_kernel(const float* __restrict__ d, const float* __restrict__ img, int B, int C, int H, int W,
+                                  const double* __restrict__ sums, int mode, double* acc, double* gd,
+                                  const float* __restrict__ gout, float* __restrict__ grad, int accumulate) {
+    const size_t hw = (size_t)H * W;
+    const size_t total = (size_t)B * hw;
+    const float inv_nx = 1.f / (float)((size_t)B * H * (W - 1));
+    const float inv_ny = 1.f / (float)((size_t)B * (H - 1) * W);
+    float a0 = 0.f, a1 = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / hw);
+        const size_t p = i - (size_t)b * hw;
+        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+        const float r = 1.f / ((float)(sums[b] / (double)hw) + 1e-7f);
+        const float* db = d + (size_t)b * hw;
+        const float* ib = img + (size_t)b * C * hw;
+        const float dc = db[p] * r;
+        if (mode == 0) {
+            if (x + 1 < W) a0 += fabsf(dc - db[p + 1] * r) * edge_weight(ib, C, hw, p, p + 1);
+            if (y + 1 < H) a1 += fabsf(dc - db[p + W] * r) * edge_weight(ib, C, hw, p, p + W);
+        } else {
+            float G = 0.f;
+            if (x + 1 < W) G += edge_weight(ib, C, hw, p, p + 1) * sgn(dc - db[p + 1] * r) * inv_nx;
+            if (x > 0) G -= edge_weight(ib, C, hw, p - 1, p) * sgn(db[p - 1] * r - dc) * inv_nx;
+            if (y + 1 < H) G += edge_weight(ib, C, hw, p, p + W) * sgn(dc - db[p + W] * r) * inv_ny;
+            if (y > 0) G -= edge_weight(ib, C, hw, p - W, p) * sgn(db[p - W] * r - dc) * inv_ny;
+            if (mode == 1) {
+                atomicAdd(&gd[b], (double)(G * db[p]));      // few hundred thousand pixels per image; fp64 REDG
+            } else {
+                const float g = (*gout) * (G * r - r * r * (float)(gd[b] / (double)hw));
+                grad[i] = accumulate ? grad[i] + g : g;
+            }
+        }
+    }
+    if (mode == 0) {
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], (double)a0 * inv_nx); atomicAdd(&acc[1], (double)a1 * inv_ny); }
+    }
+}
+__global__ void smoothness_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] + acc[1]); }
+
 }  // namespace rd

@@ -68,3 +68,32 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTS) == declared
     assert lib.rd_version() >= 1
     assert lib.rd_sizeof(0) == ctypes.sizeof(_lib.ConvParams) and lib.rd_sizeof(1) == ctypes.sizeof(_lib.WgradParams)
+
+
+def test_multistage_state_dict_and_error_conventions(tmp_path, monkeypatch):
+    from radar_depth_b200.model import multistage_model as mm
+    with pytest.raises(RuntimeError):
+        mm.ResNet_multistage(20, "upproj", (64, 96), pretrained=False)          # multistage_model.py:24-25
+    monkeypatch.setattr(mm.cfg, "PROJECT_ROOT", str(tmp_path))
+    with pytest.raises(ValueError):
+        mm.ResNet_multistage(18, "upproj", (64, 96), pretrained=True)           # multistage_model.py:37-39
+    m = mm.ResNet_multistage(18, "upproj", (64, 96), pretrained=False)
+    m.register_parameter("w_stage1", torch.nn.Parameter(torch.tensor(1.0)))     # main.py:166-172
+    m.register_parameter("w_stage2", torch.nn.Parameter(torch.tensor(1.0)))
+    ent = O.multistage_entries()
+    assert list(m.state_dict().keys()) == list(ent.keys()) and len(ent) == 652
+    for k, (shape, _) in ent.items():
+        assert tuple(m.state_dict()[k].shape) == tuple(shape), k
+    # "init from latefusion weights" (BASELINE.json configs[3]): stage1 == checkpoint, stage2 differs only in conv1_depth
+    sd = O.synth_state_dict(O.latefusion_entries(4))
+    (tmp_path / "pretrained").mkdir()
+    torch.save({"model_state_dict": sd}, str(tmp_path / "pretrained" / "resnet18_latefusion.pth.tar"))
+    m2 = mm.ResNet_multistage(18, "upproj", (64, 96), pretrained=True)
+    for k, v in sd.items():
+        assert torch.equal(m2.stage1.state_dict()[k], v), k
+        if k != "conv1_depth.weight":
+            assert torch.equal(m2.stage2.state_dict()[k], v), k
+    assert m2.stage2.conv1_depth.weight.shape == (16, 2, 7, 7)
+    d = dict(sd)
+    out = m2.filter_state_dict(d, m2.stage2.state_dict())
+    assert out is d and "conv1_depth.weight" not in d                            # mutates its argument (multistage_model.py:58-59)
