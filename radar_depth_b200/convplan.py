@@ -31,6 +31,7 @@ SMEM_BUDGET = 232448
 FPROP_HEADER = 16384
 WGRAD_HEADER = 10240
 NUM_SMS = 148
+L2_BYTES_PER_CYCLE = 24.0      # sustained L2 -> SM bytes per cycle per SM with all SMs pulling (planning constant)
 
 
 @dataclass
@@ -196,7 +197,7 @@ class FpropPlan:
     info: dict = field(default_factory=dict)
 
 
-def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes):
+def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16):
     best = None
     MBmax = max(1, 512 // (P * N))
     planes = S * S
@@ -215,16 +216,20 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
             if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > SMEM_BUDGET:
                 continue
             ty, tx = -(-Hb // Ht), -(-Wb // Wt)
-            # cycle model per tile: tensor pipe vs loader, plus the (serialised) epilogue
+            # cycle model per 16-channel stage: tensor pipe vs loader warps vs L2->SMEM traffic (source tile + the
+            # weight block, which every CTA streams again for every tile), plus the epilogue per tile
             mma = MB * ntaps * max(N, 32) / 2.0 * (3 if parts == 2 else 1)
-            load = planes * plane_slots * 2 * 0.35 * parts
+            load = planes * plane_rows * Wl * 2 * 0.08 * parts
+            l2 = (planes * plane_rows * Wl * 32 * (2 if parts == 2 else 1) + ntaps * N * 32 * parts) / L2_BYTES_PER_CYCLE
             epi = MB * P * (N / 16.0) * 40.0
+            stage = max(mma, load, l2)
             if 2 * P * MB * N <= 512:          # two accumulator sets: the epilogue overlaps the next tile's MMAs
-                per_tile = max(max(mma, load) * ncblk, epi) + 300.0
+                per_tile = max(stage * ncblk, epi) + 300.0
             else:
-                per_tile = max(mma, load) * ncblk + epi + 600.0
-            return_tiles = ty * tx
-            cost = return_tiles * per_tile
+                per_tile = stage * ncblk + epi + 600.0
+            ctas = max(1, NUM_SMS // nblk)
+            rounds = -(-(ty * tx * B_) // ctas)
+            cost = rounds * per_tile
             if best is None or cost < best[0]:
                 best = (cost, dict(MB=MB, Wl=Wl, Wt=Wt, Ht=Ht, plane_rows=plane_rows, plane_slots=plane_slots,
                                    istage=istage, tiles_y=ty, tiles_x=tx))
@@ -264,7 +269,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     base, rem = divmod(ntaps, ngroups)
     grp_n = [base + (1 if i < rem else 0) for i in range(ngroups)]
     wstage = _round_up(max(grp_n) * tap_bytes, 128)
-    geo = tile_override or _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage)
+    geo = tile_override or _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B)
     if tile_override:
         geo = dict(geo)
         geo.setdefault("Wl", geo["Wt"] + halo_x)
@@ -359,9 +364,13 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     Mc = min(_round_up(g.N, 8), 128)
     ncob = -(-g.N // Mc)
     if nc is None:
-        nc = min(g.Cx, 64)
-        while g.Cx % nc:
-            nc -= 16
+        # prefer ONE tap group per CTA (the gradient and source tiles are then staged once per pixel tile instead
+        # of once per tap group): the widest Nc (multiple of 16 dividing Cx) with ntaps*Nc <= 512 TMEM columns
+        tpc = min(ntaps, 16)
+        nc = 16
+        for cand in range(16, min(g.Cx, 256) + 1, 16):
+            if g.Cx % cand == 0 and tpc * cand <= 512:
+                nc = cand
     Nc = nc
     ncib = g.Cx // Nc
     tg_cap = max(1, min(16, 512 // Nc))

@@ -11,9 +11,9 @@
 // zero-stuffed Unpool output (models.py:13-27,191,198) and stride-2 data gradients run as 4 output phases,
 // each with its own tap list, on the UN-stuffed source.
 //
-// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7 source-tile loaders
-// (fused BatchNorm affine + ReLU/LeakyReLU + bf16 cast, optional hi/lo split for parity mode), warp 8 lane 0
-// UMMA issuer, warp 9 lane 0 weight bulk-copy issuer.  Two mbarrier rings (source tile stages, weight
+// Warp roles (448 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11 source-tile loaders
+// (fused BatchNorm affine + ReLU/LeakyReLU + bf16 cast, optional hi/lo split for parity mode), warp 12 lane 0
+// UMMA issuer, warp 13 lane 0 weight bulk-copy issuer.  Two mbarrier rings (source tile stages, weight
 // stages) plus a TMEM full/empty pair; the kernel is persistent over tiles.
 #pragma once
 #include "rd_common.cuh"
@@ -22,7 +22,8 @@
 
 namespace rd {
 
-constexpr int kFpropThreads = 320;
+constexpr int kFpropLoaderWarps = 8;
+constexpr int kFpropThreads = (4 + kFpropLoaderWarps + 2) * 32;   // epilogue x4, loaders, UMMA issuer, weight copier
 constexpr int kSmemHeader = 16384;      // barriers, tmem slot, stats, BN vectors
 constexpr int kOffTmemSlot = 256;
 constexpr int kOffTapTable = 512;       // int[3][32]: a_shift, accumulator column, first-of-phase flag
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     uint8_t* w_ring = a_ring + (size_t)p.IS * p.istage_bytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarpMma = 4 + kFpropLoaderWarps, kWarpW = kWarpMma + 1;
     const int nb = blockIdx.y;                       // N block
     constexpr int PARTS = (SPLIT == 3) ? 2 : 1;
     const int ncblk = p.Cin >> 4;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
 
     // ---- one-time setup
     if (tid == 0) {
-        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], 4); mbar_init(&in_empty[i], 1); }
+        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], kFpropLoaderWarps); mbar_init(&in_empty[i], 1); }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_mbar_init();
@@ -127,16 +129,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     if (p.epi == 1) {
         for (int i = tid; i < p.N; i += kFpropThreads) { ep_sc[i] = p.ep_scale[nb * p.N + i]; ep_sh[i] = p.ep_shift[nb * p.N + i]; }
     }
-    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    zero_smem(a_ring, (size_t)p.IS * p.istage_bytes, tid, kFpropThreads);   // tile tails / junk rows stay zero forever
+    fence_proxy_async_smem();
+    if (warp == kWarpW) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < kWarpMma) {
         // ================= source tile loaders =================
         PipeState st(p.IS);
-        const int ltid = tid - 128;
         TileSrc ts;
         ts.ptr = p.src.ptr; ts.pitch = p.src.pitch; ts.coff = p.src.coff; ts.H = p.srcH; ts.W = p.srcW; ts.S = p.S;
         ts.plane_slots = p.plane_slots; ts.plane_rows = p.plane_rows; ts.Wl = p.Wl; ts.oy0 = p.sy_min; ts.ox0 = p.sx_min;
@@ -150,14 +153,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
             for (int c = 0; c < ncblk; ++c) {
                 mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
-                stage_tile<T, SPLIT>(ts, a_ring + (size_t)st.stage * p.istage_bytes, img, y0, x0, c * 16, 2, ltid, 128);
+                stage_tile<T, SPLIT>(ts, a_ring + (size_t)st.stage * p.istage_bytes, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&in_full[st.stage]);
                 st.advance();
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kWarpW) {
         // ================= weight bulk-copy issuer =================
         if (lane == 0) {
             PipeState st(p.WS);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             }
         }
         __syncwarp();
-    } else if (warp == 8) {
+    } else if (warp == kWarpMma) {
         // ================= UMMA issuer =================
         if (lane == 0) {
             PipeState si(p.IS), sw(p.WS);
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc<512>(tmem_base);
+    if (warp == kWarpW) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace rd

@@ -8,8 +8,8 @@
 // accumulator [128 x Nc]; a CTA walks its share of the pixel tiles with the accumulators resident and
 // finally adds them into dw with vector fp32 reductions (REDG.128).
 //
-// Warp roles (288 threads): warps 0-3 epilogue, warps 4-7 loaders (gy raw; x with fused BN+activation),
-// warp 8 lane 0 UMMA issuer (also owns TMEM alloc/dealloc).
+// Warp roles (416 threads): warps 0-3 epilogue, warps 4-11 loaders (gy raw; x with fused BN+activation),
+// warp 12 lane 0 UMMA issuer (also owns TMEM alloc/dealloc).
 #pragma once
 #include "rd_common.cuh"
 #include "rd_tile.cuh"
@@ -17,7 +17,8 @@
 
 namespace rd {
 
-constexpr int kWgradThreads = 288;
+constexpr int kWgLoaderWarps = 8;
+constexpr int kWgradThreads = (4 + kWgLoaderWarps + 1) * 32;   // epilogue x4, loaders, UMMA issuer
 constexpr int kMaxTapsPerCta = 16;       // taps (TMEM accumulators) handled by one CTA
 constexpr int kWgSmemHeader = 10240;     // barriers + tmem slot + BN scale/shift (2 x 1024 floats)
 constexpr int kWgOffTmemSlot = 256;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     int* tap_x = tap_g + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarpMma = 4 + kWgLoaderWarps;
     const int cob = blockIdx.y;
     const int cib = blockIdx.z / p.ntg;
     const int tg = blockIdx.z - cib * p.ntg;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const int XPS = p.Sx * p.Sx * p.x_plane_slots;
 
     if (tid == 0) {
-        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], 4); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], kWgLoaderWarps); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
@@ -69,16 +71,17 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     if (p.ld_scale) {
         for (int i = tid; i < p.Cin; i += kWgradThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
     }
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    zero_smem(ring, (size_t)p.NS * p.stage_bytes, tid, kWgradThreads);   // tile tails stay zero forever
+    fence_proxy_async_smem();
+    if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < kWarpMma) {
         // ================= loaders =================
         PipeState st(p.NS);
-        const int ltid = tid - 128;
         TileSrc tg_, tx_;
         tg_.ptr = p.gy.ptr; tg_.pitch = p.gy.pitch; tg_.coff = p.gy.coff; tg_.H = p.gH; tg_.W = p.gW; tg_.S = p.Sg;
         tg_.plane_slots = p.KS; tg_.plane_rows = p.Ht; tg_.Wl = p.Wl; tg_.oy0 = 0; tg_.ox0 = 0;
@@ -95,14 +98,14 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
             mbar_wait(&empty[st.stage], st.phase ^ 1, 0x500 + st.stage);
             uint8_t* sbase = ring + (size_t)st.stage * p.stage_bytes;
-            stage_tile<T, SPLIT>(tg_, sbase, img, y0, x0, co0, g_chunks, ltid, 128);
-            stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, img, y0, x0, ci0, x_chunks, ltid, 128);
+            stage_tile<T, SPLIT>(tg_, sbase, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
+            stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[st.stage]);
             st.advance();
         }
-    } else if (warp == 8) {
+    } else if (warp == kWarpMma) {
         // ================= UMMA issuer =================
         if (lane == 0) {
             PipeState st(p.NS);
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem_base);
+    if (warp == kWarpMma) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace rd

@@ -43,6 +43,7 @@ template <> struct Raw8<bf16> {
     uint4 u;
     __device__ __forceinline__ void load(const bf16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
     __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ uint4 bits() const { return u; }
     __device__ __forceinline__ void unpack(float* v) const {
         v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
         v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
@@ -55,76 +56,99 @@ template <> struct Raw8<float> {
         b = __ldg(reinterpret_cast<const float4*>(p + 4));
     }
     __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+    __device__ __forceinline__ uint4 bits() const { return make_uint4(0, 0, 0, 0); }   // (never used: fp32 always converts)
     __device__ __forceinline__ void unpack(float* v) const {
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
 };
 
-// Stages `nchunks` 8-channel chunks (first channel c0) of the tile.  Work items (slot, chunk) are processed in
-// batches of kBatch per thread: all global loads of a batch are issued before the first is consumed, so each
-// loader thread keeps kBatch x 16 B (32 B in fp32 mode) in flight instead of one dependent load at a time.
+// Stages `nchunks` 8-channel chunks (first channel c0) of the tile.  One loader WARP owns one tile row at a time:
+// everything that depends on the row (source row pointer, vertical bounds, destination slot base) is warp-uniform
+// and computed once; lanes walk the row's (column, chunk) items, chunk fastest, so a warp reads contiguous
+// nchunks*16 B per pixel.  Loads are issued in batches of kBatch per lane before any is consumed (memory-level
+// parallelism).  A raw bf16 source with no fused transform is moved as 16-byte words without unpacking.
+// Slots past plane_rows*Wl are never written here: the caller zero-fills the ring once at kernel start.
 template <typename T, int SPLIT>
 __device__ __forceinline__ void stage_tile(const TileSrc& t, uint8_t* dst, int img, int y0, int x0, int c0,
-                                           int nchunks, int tid, int nthreads) {
+                                           int nchunks, int warp_idx, int nwarps, int lane) {
     constexpr int kBatch = (sizeof(T) == 2) ? 8 : 4;
     const int planes = t.S * t.S;
     const int PS = planes * t.plane_slots;
-    const int items = PS * nchunks;
-    const T* src = reinterpret_cast<const T*>(t.ptr);
-    const size_t img_base = (size_t)img * t.H * t.W;
-    const FastDiv fd_ch((uint32_t)nchunks);
     const int sh_s = t.S >> 1;                         // S is 1 or 2
-    for (int it0 = tid; it0 < items; it0 += nthreads * kBatch) {
-        Raw8<T> raw[kBatch];
-        int sj[kBatch];            // (slot << 8) | chunk, or -1 when out of range
+    const T* src = reinterpret_cast<const T*>(t.ptr);
+    const int row_items = t.Wl * nchunks;
+    const FastDiv fd_ch((uint32_t)nchunks);
+    const bool raw_copy = (SPLIT == 1) && (sizeof(T) == 2) && (t.sc == nullptr);
+    const int nrows = planes * t.plane_rows;
+    int q = 0, r = warp_idx;                           // (plane, row) of this warp's current row
+    while (r >= t.plane_rows) { r -= t.plane_rows; ++q; }
+    for (int rr = warp_idx; rr < nrows; rr += nwarps) {
+        const int py = q >> sh_s, px = q - (py << sh_s);
+        const int iy = (y0 + t.oy0 + r) * t.S + py;
+        const bool rowok = (r < t.vrows) && iy >= 0 && iy < t.H;
+        const T* rowp = src + ((size_t)img * t.H + (rowok ? iy : 0)) * t.W * t.pitch + t.coff + c0;
+        const int xbase = (x0 + t.ox0) * t.S + px;
+        const int slot0 = q * t.plane_slots + r * t.Wl;
+        for (int it0 = lane; it0 < row_items; it0 += 32 * kBatch) {
+            Raw8<T> raw[kBatch];
+            int cj[kBatch];                            // (cx << 8) | j | 0x80 if zero, -1 past the row
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int it = it0 + u * nthreads;
-            sj[u] = -1;
-            raw[u].zero();
-            if (it < items) {
-                const int s = (int)fd_ch.div((uint32_t)it), j = it - s * nchunks;
-                const int q = (int)t.fd_slots.div((uint32_t)s);
-                const int rs = s - q * t.plane_slots;
-                const int r = (int)t.fd_wl.div((uint32_t)rs);
-                const int cx = rs - r * t.Wl;
-                const int py = q >> sh_s, px = q - (py << sh_s);
-                const int iy = (y0 + t.oy0 + r) * t.S + py;
-                const int ix = (x0 + t.ox0 + cx) * t.S + px;
-                const bool ok = (r < t.plane_rows) && (r < t.vrows) && (cx < t.vcols) && iy >= 0 && iy < t.H && ix >= 0 && ix < t.W;
-                sj[u] = (s << 8) | j | (ok ? 0 : 0x80);
-                if (ok) raw[u].load(src + (img_base + (size_t)iy * t.W + ix) * t.pitch + t.coff + c0 + j * 8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            if (sj[u] < 0) continue;
-            const int s = sj[u] >> 8, j = sj[u] & 0x7F;
-            const bool ok = !(sj[u] & 0x80);
-            float v[8];
-            raw[u].unpack(v);
-            if (ok && t.sc != nullptr) {
-                const int c = c0 + j * 8;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float y = fmaf(v[k], t.sc[c + k], t.sh[c + k]);
-                    v[k] = y > 0.f ? y : y * t.slope;
+            for (int u = 0; u < kBatch; ++u) {
+                const int it = it0 + u * 32;
+                cj[u] = -1;
+                raw[u].zero();
+                if (it < row_items) {
+                    const int cx = (int)fd_ch.div((uint32_t)it), j = it - cx * nchunks;
+                    const int ix = xbase + cx * t.S;
+                    const bool ok = rowok && (cx < t.vcols) && ix >= 0 && ix < t.W;
+                    cj[u] = (cx << 8) | j | (ok ? 0 : 0x80);
+                    if (ok) raw[u].load(rowp + (size_t)ix * t.pitch + j * 8);
                 }
             }
-            uint4 hi;
-            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(dst + ((size_t)(j * PS + s) << 4)) = hi;
-            if (SPLIT == 3) {
-                uint4 lo;
-                lo.x = pack_bf16x2(v[0] - bf16lo(hi.x), v[1] - bf16hi(hi.x));
-                lo.y = pack_bf16x2(v[2] - bf16lo(hi.y), v[3] - bf16hi(hi.y));
-                lo.z = pack_bf16x2(v[4] - bf16lo(hi.z), v[5] - bf16hi(hi.z));
-                lo.w = pack_bf16x2(v[6] - bf16lo(hi.w), v[7] - bf16hi(hi.w));
-                *reinterpret_cast<uint4*>(dst + ((size_t)((nchunks + j) * PS + s) << 4)) = lo;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (cj[u] < 0) continue;
+                const int cx = cj[u] >> 8, j = cj[u] & 0x7F;
+                const int s = slot0 + cx;
+                uint8_t* d = dst + ((size_t)(j * PS + s) << 4);
+                if (raw_copy) {
+                    *reinterpret_cast<uint4*>(d) = raw[u].bits();
+                    continue;
+                }
+                float v[8];
+                raw[u].unpack(v);
+                if (!(cj[u] & 0x80) && t.sc != nullptr) {
+                    const int c = c0 + j * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float y = fmaf(v[k], t.sc[c + k], t.sh[c + k]);
+                        v[k] = y > 0.f ? y : y * t.slope;
+                    }
+                }
+                uint4 hi;
+                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(d) = hi;
+                if (SPLIT == 3) {
+                    uint4 lo;
+                    lo.x = pack_bf16x2(v[0] - bf16lo(hi.x), v[1] - bf16hi(hi.x));
+                    lo.y = pack_bf16x2(v[2] - bf16lo(hi.y), v[3] - bf16hi(hi.y));
+                    lo.z = pack_bf16x2(v[4] - bf16lo(hi.z), v[5] - bf16hi(hi.z));
+                    lo.w = pack_bf16x2(v[6] - bf16lo(hi.w), v[7] - bf16hi(hi.w));
+                    *reinterpret_cast<uint4*>(d + ((size_t)(nchunks * PS) << 4)) = lo;
+                }
             }
         }
+        r += nwarps;
+        while (r >= t.plane_rows) { r -= t.plane_rows; ++q; }
     }
+}
+
+// Zero-fills a shared-memory region (16-byte granular) cooperatively; used once per CTA for the operand rings.
+__device__ __forceinline__ void zero_smem(uint8_t* base, size_t bytes, int tid, int nthreads) {
+    uint4* p = reinterpret_cast<uint4*>(base);
+    const size_t n = bytes >> 4;
+    for (size_t i = tid; i < n; i += nthreads) p[i] = make_uint4(0, 0, 0, 0);
 }
 
 struct PipeState {
