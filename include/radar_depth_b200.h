@@ -79,6 +79,7 @@ typedef struct rd_conv_params {
     int32_t Hb, Wb;          /* base output size (before phase interleave) */
     int32_t Ht, Wt, Wl;      /* tile rows, valid cols, local row width in slots */
     int32_t plane_rows, plane_slots;
+    int32_t chunk_stride;    /* slots between consecutive 8-channel chunk planes (>= S*S*plane_slots; padded against bank conflicts) */
     int32_t sy_min, sx_min;  /* plane-coordinate offset of slot 0 relative to the tile origin */
     int32_t MB;              /* 128-row accumulator blocks per tile */
     int32_t tiles_y, tiles_x;
@@ -133,6 +134,7 @@ typedef struct rd_wgrad_params {
     int32_t B;
     int32_t Hb, Wb, Ht, Wt, Wl;
     int32_t KS;                 /* gradient slots per plane (multiple of 16, >= Ht*Wl) */
+    int32_t g_chunk_stride, x_chunk_stride; /* slots between chunk planes of the two staged tiles */
     int32_t x_plane_rows, x_plane_slots, sy_min, sx_min;
     int32_t tiles_y, tiles_x;
     int32_t ntaps, tg_size, ntg;  /* taps per CTA and number of tap groups */
@@ -143,6 +145,9 @@ typedef struct rd_wgrad_params {
     int32_t NS, stage_bytes, g_bytes;
     int32_t act_dtype;
     int32_t max_ctas;            /* pixel-split CTAs (grid.x) */
+    long long* dbg;              /* optional [4][gridDim.x*y*z] cycle counters (loader wait/fill, issuer wait/issue); NULL = off */
+    int32_t dbg_flags;           /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging */
+    int32_t pad_;
 } rd_wgrad_params;
 
 int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);

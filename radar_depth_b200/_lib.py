@@ -32,7 +32,8 @@ class ConvParams(C.Structure):
         ("src", View), ("srcH", C.c_int32), ("srcW", C.c_int32), ("Cin", C.c_int32), ("S", C.c_int32),
         ("ld_scale", C.c_void_p), ("ld_shift", C.c_void_p), ("ld_slope", C.c_float), ("B", C.c_int32),
         ("Hb", C.c_int32), ("Wb", C.c_int32), ("Ht", C.c_int32), ("Wt", C.c_int32), ("Wl", C.c_int32),
-        ("plane_rows", C.c_int32), ("plane_slots", C.c_int32), ("sy_min", C.c_int32), ("sx_min", C.c_int32),
+        ("plane_rows", C.c_int32), ("plane_slots", C.c_int32), ("chunk_stride", C.c_int32),
+        ("sy_min", C.c_int32), ("sx_min", C.c_int32),
         ("MB", C.c_int32), ("tiles_y", C.c_int32), ("tiles_x", C.c_int32),
         ("P", C.c_int32), ("OS", C.c_int32), ("ntaps", C.c_int32), ("ngroups", C.c_int32),
         ("phase_y", C.c_int32 * RD_MAX_PHASES), ("phase_x", C.c_int32 * RD_MAX_PHASES),
@@ -58,13 +59,13 @@ class WgradParams(C.Structure):
         ("x", View), ("xH", C.c_int32), ("xW", C.c_int32), ("Cin", C.c_int32), ("Sx", C.c_int32),
         ("ld_scale", C.c_void_p), ("ld_shift", C.c_void_p), ("ld_slope", C.c_float), ("B", C.c_int32),
         ("Hb", C.c_int32), ("Wb", C.c_int32), ("Ht", C.c_int32), ("Wt", C.c_int32), ("Wl", C.c_int32),
-        ("KS", C.c_int32), ("x_plane_rows", C.c_int32), ("x_plane_slots", C.c_int32),
+        ("KS", C.c_int32), ("g_chunk_stride", C.c_int32), ("x_chunk_stride", C.c_int32), ("x_plane_rows", C.c_int32), ("x_plane_slots", C.c_int32),
         ("sy_min", C.c_int32), ("sx_min", C.c_int32), ("tiles_y", C.c_int32), ("tiles_x", C.c_int32),
         ("ntaps", C.c_int32), ("tg_size", C.c_int32), ("ntg", C.c_int32),
         ("taps", WTap * RD_MAX_TAPS),
         ("Mc", C.c_int32), ("ncob", C.c_int32), ("Nc", C.c_int32), ("ncib", C.c_int32),
         ("dw", C.c_void_p), ("NS", C.c_int32), ("stage_bytes", C.c_int32), ("g_bytes", C.c_int32),
-        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32),
+        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -187,6 +187,23 @@ def _round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+def _chunk_stride(ps: int, nchunks: int) -> int:
+    """Smallest stride (in 16-byte slots) >= ps between chunk planes such that the 8 lanes of a quarter-warp, which
+    store (column, chunk) items with the chunk index fastest, hit 8 distinct 16-byte bank groups."""
+    if nchunks >= 8:
+        want = lambda v: v % 2 == 1                    # odd: chunks 0..7 land 16 B apart (mod 128)
+    elif nchunks == 4:
+        want = lambda v: v % 8 in (2, 6)
+    elif nchunks == 2:
+        want = lambda v: v % 8 == 4
+    else:
+        want = lambda v: True
+    v = ps
+    while not want(v):
+        v += 1
+    return v
+
+
 @dataclass
 class FpropPlan:
     g: GConv
@@ -212,7 +229,7 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
                 continue                                   # a smaller MB covers this tile
             plane_rows = Ht + halo_y
             plane_slots = _round_up(M + halo_y * Wl + halo_x, 8)
-            istage = _round_up(parts * 2 * planes * plane_slots * 16, 128)
+            istage = _round_up(parts * 2 * _chunk_stride(planes * plane_slots, 2) * 16, 128)
             if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > SMEM_BUDGET:
                 continue
             ty, tx = -(-Hb // Ht), -(-Wb // Wt)
@@ -277,7 +294,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
         M = geo["MB"] * 128
         geo["plane_rows"] = geo["Ht"] + halo_y
         geo["plane_slots"] = _round_up(M + halo_y * geo["Wl"] + halo_x, 8)
-        geo["istage"] = _round_up(parts * 2 * g.S * g.S * geo["plane_slots"] * 16, 128)
+        geo["istage"] = _round_up(parts * 2 * _chunk_stride(g.S * g.S * geo["plane_slots"], 2) * 16, 128)
         geo["tiles_y"], geo["tiles_x"] = -(-Hb // geo["Ht"]), -(-Wb // geo["Wt"])
     istage = geo["istage"]
     # ring depths within the shared-memory budget
@@ -302,6 +319,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     p.Hb, p.Wb = Hb, Wb
     p.Ht, p.Wt, p.Wl = geo["Ht"], geo["Wt"], geo["Wl"]
     p.plane_rows, p.plane_slots = geo["plane_rows"], geo["plane_slots"]
+    p.chunk_stride = _chunk_stride(g.S * g.S * geo["plane_slots"], 2)
     p.sy_min, p.sx_min = sy_min, sx_min
     p.MB = geo["MB"]
     p.tiles_y, p.tiles_x = geo["tiles_y"], geo["tiles_x"]
@@ -388,8 +406,8 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
                 continue
             xrows = Ht + halo_y
             xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
-            GPS = g.OS * g.OS * KS
-            XPS = g.S * g.S * xslots
+            GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
+            XPS = _chunk_stride(g.S * g.S * xslots, Nc // 8)
             g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
             stage = _round_up(g_bytes + parts * (Nc // 8) * XPS * 16, 128)
             # the M=128 operand always spans 16 chunk planes; rows past Mc are junk but must stay inside smem
@@ -402,7 +420,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
             cost = ty * tx * (max(mma, load * 0.35 * parts) + 300.0)
             if best is None or cost < best[0]:
                 best = (cost, dict(KS=KS, Wl=Wl, Wt=Wt, Ht=Ht, xrows=xrows, xslots=xslots, g_bytes=g_bytes,
-                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad))
+                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad, GPS=GPS, XPS=XPS))
     if best is None:
         raise ValueError("no feasible wgrad tile")
     geo = best[1]
@@ -416,6 +434,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     p.B = B
     p.Hb, p.Wb, p.Ht, p.Wt, p.Wl = Hb, Wb, geo["Ht"], geo["Wt"], geo["Wl"]
     p.KS = geo["KS"]
+    p.g_chunk_stride, p.x_chunk_stride = geo["GPS"], geo["XPS"]
     p.x_plane_rows, p.x_plane_slots = geo["xrows"], geo["xslots"]
     p.sy_min, p.sx_min = sy_min, sx_min
     p.tiles_y, p.tiles_x = geo["tiles_y"], geo["tiles_x"]

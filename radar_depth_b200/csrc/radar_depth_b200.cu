@@ -85,7 +85,8 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     RD_REQUIRE(p->Wl >= p->Wt && p->Ht * p->Wl <= p->MB * 128, "tile does not fit its accumulator blocks");
     const int parts = (p->act_dtype == RD_F32) ? 2 : 1;
     const int PS = p->S * p->S * p->plane_slots;
-    RD_REQUIRE(p->istage_bytes >= parts * 2 * PS * 16 && p->istage_bytes % 128 == 0, "istage_bytes too small / misaligned");
+    RD_REQUIRE(p->chunk_stride >= PS, "chunk_stride smaller than the plane set");
+    RD_REQUIRE(p->istage_bytes >= parts * 2 * p->chunk_stride * 16 && p->istage_bytes % 128 == 0, "istage_bytes too small / misaligned");
     int max_shift = 0, max_grp = 0;
     for (int t = 0; t < p->ntaps; ++t) {
         RD_REQUIRE(p->taps[t].a_shift >= 0 && p->taps[t].phase >= 0 && p->taps[t].phase < p->P, "bad tap");

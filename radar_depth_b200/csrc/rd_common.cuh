@@ -64,6 +64,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS) 16-byte copies with zero fill
+// src_bytes = 16 copies, src_bytes = 0 writes 16 zero bytes (the source address must still be valid).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------- bulk async copy global -> shared
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -133,6 +143,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Warp-uniform leader election (elect.sync).  The whole warp runs the issue loops with identical (uniform) values
+// and only the tcgen05 instructions are predicated on the elected lane: descriptors then live in uniform registers.
+// (Issuing from inside an `if (lane == 0)` branch makes every operand divergent and costs a R2UR "waterfall" of
+// ~15 instructions per tcgen05.mma.)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}\n"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
 }
 
 // ---------------------------------------------------------------- small helpers

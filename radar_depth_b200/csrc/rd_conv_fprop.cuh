@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
         ts.prepare();
+        // Raw tiles go through cp.async, one stage ahead (see rd_conv_wgrad.cuh); transformed tiles are staged
+        // synchronously through registers.
+        const bool src_async = tile_is_raw<T, SPLIT>(ts);
+        int prev_stage = -1;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -153,12 +157,31 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
             for (int c = 0; c < ncblk; ++c) {
                 mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
-                stage_tile<T, SPLIT>(ts, a_ring + (size_t)st.stage * p.istage_bytes, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&in_full[st.stage]);
+                uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
+                if (src_async) {
+                    stage_tile_async<T>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
+                    cp_async_commit();
+                    if (prev_stage >= 0) {
+                        cp_async_wait<1>();
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&in_full[prev_stage]);
+                    }
+                    prev_stage = st.stage;
+                } else {
+                    stage_tile<T, SPLIT>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&in_full[st.stage]);
+                }
                 st.advance();
             }
+        }
+        if (prev_stage >= 0) {
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&in_full[prev_stage]);
         }
     } else if (warp == kWarpW) {
         // ================= weight bulk-copy issuer =================
@@ -184,11 +207,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         }
         __syncwarp();
     } else if (warp == kWarpMma) {
-        // ================= UMMA issuer =================
-        if (lane == 0) {
+        // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
+        {
+            const bool leader = elect_one_sync();
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             PipeState si(p.IS), sw(p.WS);
             const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
-            const uint32_t PS = (uint32_t)(p.S * p.S * p.plane_slots);
+            const uint32_t PS = (uint32_t)p.chunk_stride;        // chunk stride in slots
             const uint32_t a_lbo = PS * 16u;
             const uint32_t b_lbo = (uint32_t)p.N * 16u;
             const uint32_t tap_bytes = (uint32_t)PARTS * p.N * 32u;
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
                 mbar_wait(&tmem_empty[ab], (use & 1u) ^ 1u, 0x300);
                 tc_fence_after();
-                const uint32_t d_tile = tmem_base + ab * (uint32_t)acc_cols;
+                const uint32_t d_tile = tmem_u + ab * (uint32_t)acc_cols;
                 for (int c = 0; c < ncblk; ++c) {
                     mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
                     tc_fence_after();
@@ -212,25 +237,30 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                         uint64_t db = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), b_lbo, 128);
                         const int gn = p.grp_n[g];
                         for (int tl = 0; tl < gn; ++tl, ++t, db += tap_units) {
-                            uint64_t da = da0 + (uint32_t)tap_a[t];
-                            uint32_t d = d_tile + (uint32_t)tap_d[t];
-                            const uint32_t acc = (c == 0 && tap_f[t]) ? 0u : 1u;
-#pragma unroll 1
+                            // tap data straight from the (uniform) kernel parameter bank: no LDS -> R2UR per UMMA
+                            uint64_t da = da0 + (uint32_t)p.taps[t].a_shift;
+                            uint32_t d = d_tile + (uint32_t)(p.taps[t].phase * p.MB * p.N);
+                            const uint32_t acc = (c == 0 && p.taps[t].first) ? 0u : 1u;
+#pragma unroll 4
                             for (int mb = 0; mb < p.MB; ++mb, da += 128, d += (uint32_t)p.N) {
-                                umma_bf16(d, da, db, idesc, acc);
-                                if (SPLIT == 3) {
-                                    umma_bf16(d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
-                                    umma_bf16(d, da + 2u * a_units, db, idesc, 1u);
+                                if (leader) {
+                                    umma_bf16(d, da, db, idesc, acc);
+                                    if (SPLIT == 3) {
+                                        umma_bf16(d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
+                                        umma_bf16(d, da + 2u * a_units, db, idesc, 1u);
+                                    }
                                 }
                             }
                         }
-                        umma_commit(&w_empty[sw.stage]);
+                        __syncwarp();
+                        if (leader) umma_commit(&w_empty[sw.stage]);
                         sw.advance();
                     }
-                    umma_commit(&in_empty[si.stage]);
+                    if (leader) umma_commit(&in_empty[si.stage]);
                     si.advance();
                 }
-                umma_commit(&tmem_full[ab]);
+                if (leader) umma_commit(&tmem_full[ab]);
+                __syncwarp();
             }
         }
         __syncwarp();

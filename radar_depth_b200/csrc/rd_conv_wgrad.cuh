@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const int tiles_per_img = p.tiles_y * p.tiles_x;
     const int ntiles = tiles_per_img * p.B;
     const int g_chunks = p.Mc >> 3, x_chunks = p.Nc >> 3;
-    const int GPS = p.Sg * p.Sg * p.KS;
-    const int XPS = p.Sx * p.Sx * p.x_plane_slots;
+    const int GPS = p.g_chunk_stride;              // chunk strides in slots (>= planes * plane slots)
+    const int XPS = p.x_chunk_stride;
 
     if (tid == 0) {
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], kWgLoaderWarps); mbar_init(&empty[i], 1); }
@@ -91,36 +91,62 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tx_.vrows = p.x_plane_rows; tx_.vcols = p.Wl;
         tx_.sc = p.ld_scale ? ld_sc : nullptr; tx_.sh = ld_sh; tx_.slope = p.ld_slope;
         tg_.prepare(); tx_.prepare();
+        // Raw tiles go through cp.async, one tile ahead: the copies of tile t are in flight while tile t-1 is
+        // completed (wait_group 1), published to the async proxy and handed to the UMMA issuer.
+        const bool g_async = tile_is_raw<T, SPLIT>(tg_), x_async = tile_is_raw<T, SPLIT>(tx_);
+        int prev_stage = -1;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
+            const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty[st.stage], st.phase ^ 1, 0x500 + st.stage);
+            const long long tw1 = p.dbg ? clock64() : 0;
             uint8_t* sbase = ring + (size_t)st.stage * p.stage_bytes;
-            stage_tile<T, SPLIT>(tg_, sbase, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
-            stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+            if (!(p.dbg_flags & 2)) {
+            if (g_async) stage_tile_async<T>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
+            if (x_async) stage_tile_async<T>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+            cp_async_commit();
+            if (!g_async) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
+            if (!x_async) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+            }
+            if (prev_stage >= 0) {
+                cp_async_wait<1>();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[prev_stage]);
+            }
+            prev_stage = st.stage;
+            st.advance();
+            if (p.dbg && warp == 4 && lane == 0) {
+                const long long tw2 = clock64();
+                const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+                const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+                p.dbg[0 * ncta + cta] += tw1 - tw0;
+                p.dbg[1 * ncta + cta] += tw2 - tw1;
+            }
+        }
+        if (prev_stage >= 0) {
+            cp_async_wait<0>();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[st.stage]);
-            st.advance();
+            if (lane == 0) mbar_arrive(&full[prev_stage]);
         }
     } else if (warp == kWarpMma) {
-        // ================= UMMA issuer =================
-        if (lane == 0) {
+        // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
+        {
+            const bool leader = elect_one_sync();
             PipeState st(p.NS);
             const uint32_t idesc = make_idesc_bf16(128, p.Nc, 1, 1);
             const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = (uint32_t)XPS * 16u;
             const int KG = p.KS >> 4;
             bool first_tile = true;
-            uint32_t tg_r[kMaxTapsPerCta], tx_r[kMaxTapsPerCta];
-#pragma unroll
-            for (int tl = 0; tl < kMaxTapsPerCta; ++tl) {
-                tg_r[tl] = tl < T_n ? (uint32_t)tap_g[tl] : 0u;
-                tx_r[tl] = tl < T_n ? (uint32_t)tap_x[tl] : 0u;
-            }
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long tm0 = p.dbg ? clock64() : 0;
                 mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
+                const long long tm1 = p.dbg ? clock64() : 0;
                 tc_fence_after();
                 const uint32_t g_base = smem_u32(ring + (size_t)st.stage * p.stage_bytes);
                 const uint64_t da0 = make_smem_desc(g_base, 128, g_sbo);
@@ -129,13 +155,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     const uint32_t acc = (first_tile && kg == 0) ? 0u : 1u;
                     const uint64_t dak = da0 + (uint32_t)(kg * 16);
                     const uint64_t dbk = db0 + (uint32_t)(kg * 16);
-                    // tap offsets live in registers (fully unrolled, predicated): ~5 instructions per UMMA issued
-#pragma unroll
-                    for (int tl = 0; tl < kMaxTapsPerCta; ++tl) {
-                        if (tl < T_n) {
-                            const uint32_t d = tmem_base + (uint32_t)(tl * p.Nc);
-                            const uint64_t da = dak + tg_r[tl];
-                            const uint64_t db = dbk + tx_r[tl];
+#pragma unroll 4
+                    for (int tl = 0; tl < T_n; ++tl) {
+                        if (leader && !(p.dbg_flags & 1)) {
+                            // tap offsets come straight from the (uniform) kernel parameter bank: no LDS -> R2UR
+                            const uint32_t d = tmem_u + (uint32_t)(tl * p.Nc);
+                            const uint64_t da = dak + (uint32_t)p.taps[t0 + tl].g_off;
+                            const uint64_t db = dbk + (uint32_t)p.taps[t0 + tl].x_shift;
                             umma_bf16(d, da, db, idesc, acc);
                             if (SPLIT == 3) {
                                 umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
@@ -144,11 +170,19 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                         }
                     }
                 }
-                umma_commit(&empty[st.stage]);
+                __syncwarp();
+                if (leader) umma_commit(&empty[st.stage]);
                 st.advance();
                 first_tile = false;
+                if (p.dbg && lane == 0) {
+                    const long long tm2 = clock64();
+                    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+                    const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+                    p.dbg[2 * ncta + cta] += tm1 - tm0;
+                    p.dbg[3 * ncta + cta] += tm2 - tm1;
+                }
             }
-            umma_commit(tmem_full);
+            if (leader) umma_commit(tmem_full);
         }
         __syncwarp();
     } else {

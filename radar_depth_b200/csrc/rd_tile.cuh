@@ -62,85 +62,120 @@ template <> struct Raw8<float> {
     }
 };
 
-// Stages `nchunks` 8-channel chunks (first channel c0) of the tile.  One loader WARP owns one tile row at a time:
-// everything that depends on the row (source row pointer, vertical bounds, destination slot base) is warp-uniform
-// and computed once; lanes walk the row's (column, chunk) items, chunk fastest, so a warp reads contiguous
-// nchunks*16 B per pixel.  Loads are issued in batches of kBatch per lane before any is consumed (memory-level
-// parallelism).  A raw bf16 source with no fused transform is moved as 16-byte words without unpacking.
+// Stages `nchunks` 8-channel chunks (first channel c0) of the tile.  Loader warp w owns tile rows w, w+nwarps, ...;
+// its (row, column, chunk) items are flattened (chunk fastest, so a warp reads contiguous nchunks*16 B per pixel)
+// and processed in batches of kBatch per lane with every global load of a batch issued before any is consumed,
+// so one DRAM/L2 latency is paid per batch, not per row.  A raw bf16 source with no fused transform is moved as
+// 16-byte words without unpacking.  `cs` = chunk stride in slots (>= planes*plane_slots, padded by the host so
+// that the 16-byte stores of one quarter-warp fall into distinct shared-memory banks).
 // Slots past plane_rows*Wl are never written here: the caller zero-fills the ring once at kernel start.
 template <typename T, int SPLIT>
-__device__ __forceinline__ void stage_tile(const TileSrc& t, uint8_t* dst, int img, int y0, int x0, int c0,
+__device__ __forceinline__ void stage_tile(const TileSrc& t, uint8_t* dst, int cs, int img, int y0, int x0, int c0,
                                            int nchunks, int warp_idx, int nwarps, int lane) {
     constexpr int kBatch = (sizeof(T) == 2) ? 8 : 4;
     const int planes = t.S * t.S;
-    const int PS = planes * t.plane_slots;
     const int sh_s = t.S >> 1;                         // S is 1 or 2
     const T* src = reinterpret_cast<const T*>(t.ptr);
     const int row_items = t.Wl * nchunks;
-    const FastDiv fd_ch((uint32_t)nchunks);
+    const FastDiv fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
     const bool raw_copy = (SPLIT == 1) && (sizeof(T) == 2) && (t.sc == nullptr);
     const int nrows = planes * t.plane_rows;
-    int q = 0, r = warp_idx;                           // (plane, row) of this warp's current row
-    while (r >= t.plane_rows) { r -= t.plane_rows; ++q; }
-    for (int rr = warp_idx; rr < nrows; rr += nwarps) {
-        const int py = q >> sh_s, px = q - (py << sh_s);
-        const int iy = (y0 + t.oy0 + r) * t.S + py;
-        const bool rowok = (r < t.vrows) && iy >= 0 && iy < t.H;
-        const T* rowp = src + ((size_t)img * t.H + (rowok ? iy : 0)) * t.W * t.pitch + t.coff + c0;
-        const int xbase = (x0 + t.ox0) * t.S + px;
-        const int slot0 = q * t.plane_slots + r * t.Wl;
-        for (int it0 = lane; it0 < row_items; it0 += 32 * kBatch) {
-            Raw8<T> raw[kBatch];
-            int cj[kBatch];                            // (cx << 8) | j | 0x80 if zero, -1 past the row
+    const int my_rows = nrows > warp_idx ? (nrows - warp_idx + nwarps - 1) / nwarps : 0;
+    const int my_items = my_rows * row_items;
+    const size_t img_off = (size_t)img * t.H;
+    for (int f0 = lane; f0 < my_items; f0 += 32 * kBatch) {
+        Raw8<T> raw[kBatch];
+        int sj[kBatch];                                // (slot << 8) | j | 0x80 if zero, -1 past the end
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int it = it0 + u * 32;
-                cj[u] = -1;
-                raw[u].zero();
-                if (it < row_items) {
-                    const int cx = (int)fd_ch.div((uint32_t)it), j = it - cx * nchunks;
-                    const int ix = xbase + cx * t.S;
-                    const bool ok = rowok && (cx < t.vcols) && ix >= 0 && ix < t.W;
-                    cj[u] = (cx << 8) | j | (ok ? 0 : 0x80);
-                    if (ok) raw[u].load(rowp + (size_t)ix * t.pitch + j * 8);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if (cj[u] < 0) continue;
-                const int cx = cj[u] >> 8, j = cj[u] & 0x7F;
-                const int s = slot0 + cx;
-                uint8_t* d = dst + ((size_t)(j * PS + s) << 4);
-                if (raw_copy) {
-                    *reinterpret_cast<uint4*>(d) = raw[u].bits();
-                    continue;
-                }
-                float v[8];
-                raw[u].unpack(v);
-                if (!(cj[u] & 0x80) && t.sc != nullptr) {
-                    const int c = c0 + j * 8;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float y = fmaf(v[k], t.sc[c + k], t.sh[c + k]);
-                        v[k] = y > 0.f ? y : y * t.slope;
-                    }
-                }
-                uint4 hi;
-                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(d) = hi;
-                if (SPLIT == 3) {
-                    uint4 lo;
-                    lo.x = pack_bf16x2(v[0] - bf16lo(hi.x), v[1] - bf16hi(hi.x));
-                    lo.y = pack_bf16x2(v[2] - bf16lo(hi.y), v[3] - bf16hi(hi.y));
-                    lo.z = pack_bf16x2(v[4] - bf16lo(hi.z), v[5] - bf16hi(hi.z));
-                    lo.w = pack_bf16x2(v[6] - bf16lo(hi.w), v[7] - bf16hi(hi.w));
-                    *reinterpret_cast<uint4*>(d + ((size_t)(nchunks * PS) << 4)) = lo;
-                }
+        for (int u = 0; u < kBatch; ++u) {
+            const int f = f0 + u * 32;
+            sj[u] = -1;
+            raw[u].zero();
+            if (f < my_items) {
+                const int k = (int)fd_row.div((uint32_t)f);
+                const int it = f - k * row_items;
+                const int rr = warp_idx + k * nwarps;
+                const int q = (int)fd_pr.div((uint32_t)rr), r = rr - q * t.plane_rows;
+                const int py = q >> sh_s, px = q - (py << sh_s);
+                const int cx = (int)fd_ch.div((uint32_t)it), j = it - cx * nchunks;
+                const int iy = (y0 + t.oy0 + r) * t.S + py;
+                const int ix = (x0 + t.ox0 + cx) * t.S + px;
+                const bool ok = (r < t.vrows) && (cx < t.vcols) && iy >= 0 && iy < t.H && ix >= 0 && ix < t.W;
+                sj[u] = ((q * t.plane_slots + r * t.Wl + cx) << 8) | j | (ok ? 0 : 0x80);
+                if (ok) raw[u].load(src + ((img_off + iy) * t.W + ix) * t.pitch + t.coff + c0 + j * 8);
             }
         }
-        r += nwarps;
-        while (r >= t.plane_rows) { r -= t.plane_rows; ++q; }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (sj[u] < 0) continue;
+            const int s = sj[u] >> 8, j = sj[u] & 0x7F;
+            uint8_t* d = dst + ((size_t)(j * cs + s) << 4);
+            if (raw_copy) {
+                *reinterpret_cast<uint4*>(d) = raw[u].bits();
+                continue;
+            }
+            float v[8];
+            raw[u].unpack(v);
+            if (!(sj[u] & 0x80) && t.sc != nullptr) {
+                const int c = c0 + j * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float y = fmaf(v[k], t.sc[c + k], t.sh[c + k]);
+                    v[k] = y > 0.f ? y : y * t.slope;
+                }
+            }
+            uint4 hi;
+            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(d) = hi;
+            if (SPLIT == 3) {
+                uint4 lo;
+                lo.x = pack_bf16x2(v[0] - bf16lo(hi.x), v[1] - bf16hi(hi.x));
+                lo.y = pack_bf16x2(v[2] - bf16lo(hi.y), v[3] - bf16hi(hi.y));
+                lo.z = pack_bf16x2(v[4] - bf16lo(hi.z), v[5] - bf16hi(hi.z));
+                lo.w = pack_bf16x2(v[6] - bf16lo(hi.w), v[7] - bf16hi(hi.w));
+                *reinterpret_cast<uint4*>(d + ((size_t)(nchunks * cs) << 4)) = lo;
+            }
+        }
+    }
+}
+
+// True when the tile can be staged with fire-and-forget cp.async copies: bf16 storage, no hi/lo split, no fused
+// BatchNorm/activation on load.
+template <typename T, int SPLIT>
+__device__ __forceinline__ bool tile_is_raw(const TileSrc& t) {
+    return (SPLIT == 1) && (sizeof(T) == 2) && (t.sc == nullptr);
+}
+
+// Asynchronous variant of stage_tile for raw tiles: every (row, column, chunk) item becomes one 16-byte cp.async
+// (zero-filling out-of-range items), nothing is held in registers and the caller overlaps the copies with other
+// work; completion is observed with cp.async.wait_group by the issuing thread.
+template <typename T>
+__device__ __forceinline__ void stage_tile_async(const TileSrc& t, uint8_t* dst, int cs, int img, int y0, int x0, int c0,
+                                                 int nchunks, int warp_idx, int nwarps, int lane) {
+    const int planes = t.S * t.S;
+    const int sh_s = t.S >> 1;
+    const T* src = reinterpret_cast<const T*>(t.ptr);
+    const int row_items = t.Wl * nchunks;
+    const FastDiv fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
+    const int nrows = planes * t.plane_rows;
+    const int my_rows = nrows > warp_idx ? (nrows - warp_idx + nwarps - 1) / nwarps : 0;
+    const int my_items = my_rows * row_items;
+    const size_t img_off = (size_t)img * t.H;
+#pragma unroll 4
+    for (int f = lane; f < my_items; f += 32) {
+        const int k = (int)fd_row.div((uint32_t)f);
+        const int it = f - k * row_items;
+        const int rr = warp_idx + k * nwarps;
+        const int q = (int)fd_pr.div((uint32_t)rr), r = rr - q * t.plane_rows;
+        const int py = q >> sh_s, px = q - (py << sh_s);
+        const int cx = (int)fd_ch.div((uint32_t)it), j = it - cx * nchunks;
+        const int iy = (y0 + t.oy0 + r) * t.S + py;
+        const int ix = (x0 + t.ox0 + cx) * t.S + px;
+        const bool ok = (r < t.vrows) && (cx < t.vcols) && iy >= 0 && iy < t.H && ix >= 0 && ix < t.W;
+        const int s = q * t.plane_slots + r * t.Wl + cx;
+        const T* g = ok ? src + ((img_off + iy) * t.W + ix) * t.pitch + t.coff + c0 + j * 8 : src;
+        cp_async16(dst + ((size_t)(j * cs + s) << 4), g, ok ? 16u : 0u);
     }
 }
 

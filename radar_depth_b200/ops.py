@@ -72,8 +72,10 @@ def conv_fprop(plan, src: View, wpk, dst: View, ld=None, epi: int = 0, addend: O
     _lib.call("rd_conv_fprop", C.byref(p), stream_ptr())
 
 
-def conv_wgrad(plan, gy: View, x: View, dw, ld=None, max_ctas: Optional[int] = None):
+def conv_wgrad(plan, gy: View, x: View, dw, ld=None, max_ctas: Optional[int] = None, dbg=None, dbg_flags: int = 0):
     p = type(plan.params).from_buffer_copy(plan.params)
+    p.dbg = ptr(dbg) if dbg is not None else None
+    p.dbg_flags = dbg_flags
     p.gy = gy
     p.x = x
     p.dw = dw if isinstance(dw, int) else ptr(dw)
