@@ -5,17 +5,23 @@ import sys
 import torch
 from radar_depth_b200 import _lib, convplan as cp, ops
 
-shapes = {"l1": (64, 64, 3, 1, 1, (88, 304), (88, 304)), "l2": (128, 128, 3, 1, 1, (44, 152), (44, 152)),
+shapes = {"up4": None, "l1": (64, 64, 3, 1, 1, (88, 304), (88, 304)), "l2": (128, 128, 3, 1, 1, (44, 152), (44, 152)),
           "l4": (512, 512, 3, 1, 1, (11, 38), (11, 38)), "d16": (16, 16, 3, 1, 1, (176, 608), (176, 608))}
 name = sys.argv[1] if len(sys.argv) > 1 else "l1"
-Cout, Cin, k, s, pad, shw, dhw = shapes[name]
 B = 16
-g = cp.gconv_standard(0, Cout, Cin, k, s, pad)
-x = torch.randn(B, shw[0], shw[1], Cin, device="cuda").bfloat16()
-dy = torch.randn(B, dhw[0], dhw[1], Cout, device="cuda").bfloat16()
-flops = 2.0 * B * dhw[0] * dhw[1] * k * k * Cin * Cout
-for nc, ks, maxc in itertools.product((64, 32), (256,), (0, 148)):
-    if nc > Cin:
+if name.startswith("up"):
+    cin = {"up1": 256, "up2": 128, "up3": 64, "up4": 32}[name]
+    hw = {"up1": (11, 38), "up2": (22, 76), "up3": (44, 152), "up4": (88, 304)}[name]
+    g = cp.gconv_upproj(0, 10 ** 7, cin, cin // 2)
+    Cout, Cin, k, shw, dhw = cin, cin, 5, hw, (2 * hw[0], 2 * hw[1])
+else:
+    Cout, Cin, k, s, pad, shw, dhw = shapes[name]
+    g = cp.gconv_standard(0, Cout, Cin, k, s, pad)
+x = torch.randn(B, shw[0], shw[1], g.Cx, device="cuda").bfloat16()
+dy = torch.randn(B, dhw[0], dhw[1], g.N, device="cuda").bfloat16()
+flops = 2.0 * B * (dhw[0] // g.OS) * (dhw[1] // g.OS) * len(g.taps) * g.Cx * g.N
+for nc, ks, maxc in itertools.product((128, 64, 32, 16), (64, 128, 192, 256, 384), (0,)):
+    if nc > g.Cx or g.Cx % nc:
         continue
     try:
         plan = cp.plan_wgrad(g, B, shw, dhw, _lib.RD_BF16, ks_target=ks, nc=nc)
@@ -40,15 +46,6 @@ for nc, ks, maxc in itertools.product((64, 32), (256,), (0, 148)):
     torch.cuda.synchronize()
     d = dbg.double().mean(dim=1).cpu().numpy() / 1e3
     tiles_per_cta = plan.info["ntiles"] / mc
-    for fl, nm in ((1, "no-MMA"), (2, "no-load"), (3, "neither")):
-        for _ in range(2):
-            ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, max_ctas=mc, dbg_flags=fl)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, max_ctas=mc, dbg_flags=fl); e1.record()
-        torch.cuda.synchronize()
-        print(f"      {nm}: {e0.elapsed_time(e1) * 1e3:7.1f} us", end="")
-    print()
     print(f"      kcycles/CTA: loader wait {d[0]:7.1f} fill {d[1]:7.1f} | issuer wait {d[2]:7.1f} issue {d[3]:7.1f} | tiles/CTA {tiles_per_cta:.1f}")
     i = plan.info
     print(f"{name} nc={nc:3d} ks_t={ks:3d} -> KS={i['geo']['KS']:3d} Wl={i['geo']['Wl']:3d} Ht={i['geo']['Ht']:2d} tg={i['tg_size']:2d}x{i['ntg']} NS={i['NS']} "
