@@ -71,6 +71,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// Arrive on `bar` once every cp.async previously issued by this thread has landed (no wait, no pending-count increment:
+// the barrier's expected count must include one arrival per issuing thread).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 

@@ -108,8 +108,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     const int ntiles = tiles_per_img * p.B;
 
     // ---- one-time setup
+    // raw bf16 source tiles are staged with cp.async (one arrival per loader thread), others through registers
+    const bool src_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr);
     if (tid == 0) {
-        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], kFpropLoaderWarps); mbar_init(&in_empty[i], 1); }
+        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps); mbar_init(&in_empty[i], 1); }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_mbar_init();
@@ -146,10 +148,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
         ts.prepare();
-        // Raw tiles go through cp.async, one stage ahead (see rd_conv_wgrad.cuh); transformed tiles are staged
-        // synchronously through registers.
-        const bool src_async = tile_is_raw<T, SPLIT>(ts);
-        int prev_stage = -1;
+        // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
+        // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -160,28 +160,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
                 if (src_async) {
                     stage_tile_async<T>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
-                    cp_async_commit();
-                    if (prev_stage >= 0) {
-                        cp_async_wait<1>();
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&in_full[prev_stage]);
-                    }
-                    prev_stage = st.stage;
+                    cp_async_mbar_arrive_noinc(&in_full[st.stage]);
                 } else {
                     stage_tile<T, SPLIT>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
-                    fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&in_full[st.stage]);
                 }
                 st.advance();
             }
-        }
-        if (prev_stage >= 0) {
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&in_full[prev_stage]);
         }
     } else if (warp == kWarpW) {
         // ================= weight bulk-copy issuer =================
@@ -228,6 +214,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 const uint32_t d_tile = tmem_u + ab * (uint32_t)acc_cols;
                 for (int c = 0; c < ncblk; ++c) {
                     mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
+                    fence_proxy_async_smem();      // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
                     tc_fence_after();
                     const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), a_lbo, 128);
                     int t = 0;

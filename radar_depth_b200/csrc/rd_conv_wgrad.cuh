@@ -17,7 +17,7 @@
 
 namespace rd {
 
-constexpr int kWgLoaderWarps = 8;
+constexpr int kWgLoaderWarps = 12;
 constexpr int kWgradThreads = (4 + kWgLoaderWarps + 1) * 32;   // epilogue x4, loaders, UMMA issuer
 constexpr int kMaxTapsPerCta = 16;       // taps (TMEM accumulators) handled by one CTA
 constexpr int kWgSmemHeader = 10240;     // barriers + tmem slot + BN scale/shift (2 x 1024 floats)
@@ -59,8 +59,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const int GPS = p.g_chunk_stride;              // chunk strides in slots (>= planes * plane slots)
     const int XPS = p.x_chunk_stride;
 
+    // raw bf16 tiles are staged with cp.async (one arrival per loader thread), transformed tiles through registers
+    // (one arrival per loader warp)
+    const bool g_async = (SPLIT == 1) && (sizeof(T) == 2);
+    const bool x_async = g_async && (p.ld_scale == nullptr);
+    const uint32_t full_count = (uint32_t)(((g_async || x_async) ? 32 * kWgLoaderWarps : 0) + ((!g_async || !x_async) ? kWgLoaderWarps : 0));
     if (tid == 0) {
-        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], kWgLoaderWarps); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], full_count); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
@@ -91,10 +96,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tx_.vrows = p.x_plane_rows; tx_.vcols = p.Wl;
         tx_.sc = p.ld_scale ? ld_sc : nullptr; tx_.sh = ld_sh; tx_.slope = p.ld_slope;
         tg_.prepare(); tx_.prepare();
-        // Raw tiles go through cp.async, one tile ahead: the copies of tile t are in flight while tile t-1 is
-        // completed (wait_group 1), published to the async proxy and handed to the UMMA issuer.
-        const bool g_async = tile_is_raw<T, SPLIT>(tg_), x_async = tile_is_raw<T, SPLIT>(tx_);
-        int prev_stage = -1;
+        // Raw tiles go through fire-and-forget cp.async: every loader thread arrives on full[stage] through
+        // cp.async.mbarrier.arrive.noinc when ITS copies have landed, so the loaders run ahead as far as the ring
+        // allows and never wait for memory.  Tiles with a fused transform are staged through registers and
+        // signalled with one ordinary arrival per warp.  The generic->async proxy fence is executed by the consumer
+        // (UMMA warp) after it has observed full[stage]: a producer-side fence would have to drain the copies.
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -105,19 +111,18 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             const long long tw1 = p.dbg ? clock64() : 0;
             uint8_t* sbase = ring + (size_t)st.stage * p.stage_bytes;
             if (!(p.dbg_flags & 2)) {
-            if (g_async) stage_tile_async<T>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
-            if (x_async) stage_tile_async<T>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
-            cp_async_commit();
-            if (!g_async) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
-            if (!x_async) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+                if (g_async) stage_tile_async<T>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
+                if (x_async) stage_tile_async<T>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
             }
-            if (prev_stage >= 0) {
-                cp_async_wait<1>();
-                fence_proxy_async_smem();
+            if (g_async || x_async) cp_async_mbar_arrive_noinc(&full[st.stage]);
+            if (!g_async || !x_async) {
+                if (!(p.dbg_flags & 2)) {
+                    if (!g_async) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
+                    if (!x_async) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[prev_stage]);
+                if (lane == 0) mbar_arrive(&full[st.stage]);
             }
-            prev_stage = st.stage;
             st.advance();
             if (p.dbg && warp == 4 && lane == 0) {
                 const long long tw2 = clock64();
@@ -126,12 +131,6 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 p.dbg[0 * ncta + cta] += tw1 - tw0;
                 p.dbg[1 * ncta + cta] += tw2 - tw1;
             }
-        }
-        if (prev_stage >= 0) {
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[prev_stage]);
         }
     } else if (warp == kWarpMma) {
         // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
@@ -147,22 +146,30 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 const long long tm0 = p.dbg ? clock64() : 0;
                 mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
                 const long long tm1 = p.dbg ? clock64() : 0;
+                fence_proxy_async_smem();          // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
                 tc_fence_after();
                 const uint32_t g_base = smem_u32(ring + (size_t)st.stage * p.stage_bytes);
                 const uint64_t da0 = make_smem_desc(g_base, 128, g_sbo);
                 const uint64_t db0 = make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
-                for (int kg = 0; kg < KG; ++kg) {
-                    const uint32_t acc = (first_tile && kg == 0) ? 0u : 1u;
-                    const uint64_t dak = da0 + (uint32_t)(kg * 16);
-                    const uint64_t dbk = db0 + (uint32_t)(kg * 16);
+                // tap-outer / k-group-inner: inside the inner loop the descriptors only advance by 16 slots, so one
+                // UMMA costs two uniform adds; the tap offsets come from the (uniform) parameter bank once per tap
+                for (int tl = 0; tl < T_n; ++tl) {
+                    const uint32_t d = tmem_u + (uint32_t)(tl * p.Nc);
+                    uint64_t da = da0 + (uint32_t)p.taps[t0 + tl].g_off;
+                    uint64_t db = db0 + (uint32_t)p.taps[t0 + tl].x_shift;
+                    if (leader && !(p.dbg_flags & 1)) {
+                        umma_bf16(d, da, db, idesc, first_tile ? 0u : 1u);
+                        if (SPLIT == 3) {
+                            umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
+                            umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
+                        }
+                    }
 #pragma unroll 4
-                    for (int tl = 0; tl < T_n; ++tl) {
+                    for (int kg = 1; kg < KG; ++kg) {
+                        da += 16;
+                        db += 16;
                         if (leader && !(p.dbg_flags & 1)) {
-                            // tap offsets come straight from the (uniform) kernel parameter bank: no LDS -> R2UR
-                            const uint32_t d = tmem_u + (uint32_t)(tl * p.Nc);
-                            const uint64_t da = dak + (uint32_t)p.taps[t0 + tl].g_off;
-                            const uint64_t db = dbk + (uint32_t)p.taps[t0 + tl].x_shift;
-                            umma_bf16(d, da, db, idesc, acc);
+                            umma_bf16(d, da, db, idesc, 1u);
                             if (SPLIT == 3) {
                                 umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
                                 umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);

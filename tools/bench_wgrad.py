@@ -20,7 +20,7 @@ else:
 x = torch.randn(B, shw[0], shw[1], g.Cx, device="cuda").bfloat16()
 dy = torch.randn(B, dhw[0], dhw[1], g.N, device="cuda").bfloat16()
 flops = 2.0 * B * (dhw[0] // g.OS) * (dhw[1] // g.OS) * len(g.taps) * g.Cx * g.N
-for nc, ks, maxc in itertools.product((128, 64, 32, 16), (64, 128, 192, 256, 384), (0,)):
+for nc, ks, maxc in itertools.product((32,), (256,), (0,)):
     if nc > g.Cx or g.Cx % nc:
         continue
     try:
@@ -46,6 +46,18 @@ for nc, ks, maxc in itertools.product((128, 64, 32, 16), (64, 128, 192, 256, 384
     torch.cuda.synchronize()
     d = dbg.double().mean(dim=1).cpu().numpy() / 1e3
     tiles_per_cta = plan.info["ntiles"] / mc
+    for fl, nm in ((1, "no-MMA"), (2, "no-load"), (3, "neither")):
+        for _ in range(2):
+            ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, max_ctas=mc, dbg_flags=fl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, max_ctas=mc, dbg_flags=fl); e1.record()
+        torch.cuda.synchronize()
+        dbg2 = torch.zeros(4, ncta, dtype=torch.int64, device="cuda")
+        ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, max_ctas=mc, dbg=dbg2, dbg_flags=fl)
+        torch.cuda.synchronize()
+        d2 = dbg2.double().mean(dim=1).cpu().numpy() / 1e3
+        print(f"      {nm}: {e0.elapsed_time(e1) * 1e3:7.1f} us  [loader wait {d2[0]:6.1f} fill {d2[1]:6.1f} | issuer wait {d2[2]:6.1f} issue {d2[3]:6.1f}]")
     print(f"      kcycles/CTA: loader wait {d[0]:7.1f} fill {d[1]:7.1f} | issuer wait {d[2]:7.1f} issue {d[3]:7.1f} | tiles/CTA {tiles_per_cta:.1f}")
     i = plan.info
     print(f"{name} nc={nc:3d} ks_t={ks:3d} -> KS={i['geo']['KS']:3d} Wl={i['geo']['Wl']:3d} Ht={i['geo']['Ht']:2d} tg={i['tg_size']:2d}x{i['ntg']} NS={i['NS']} "
