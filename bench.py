@@ -298,16 +298,15 @@ def kernel_roofline(model, d_in, d_tg, crit, b):
         reps = 3
         for prog_name, prog in (("fwd", eng.fwd), ("bwd", eng.bwd)):
             for L in prog:
-                evs = []
+                # `reps` launches back to back inside one event pair (the queue hides host launch latency)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
                 for _ in range(reps):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
                     rc = L.fn(*L.args, st)
-                    e1.record()
                     assert rc == 0, L.name
-                    evs.append((e0, e1))
+                e1.record()
                 torch.cuda.synchronize()
-                t = statistics.median(a.elapsed_time(c) for a, c in evs)
+                t = e0.elapsed_time(e1) / reps
                 kind = L.name.split(":")[0]
                 per.setdefault(kind, [0.0, 0])
                 per[kind][0] += t

@@ -109,6 +109,9 @@ typedef struct rd_conv_params {
     int32_t istage_bytes, wstage_bytes;
     int32_t act_dtype;       /* RD_BF16 / RD_F32 */
     int32_t max_ctas;        /* persistent grid cap (0 = one CTA per tile) */
+    long long* dbg;          /* optional [6][gridDim.x*gridDim.y] cycle counters: loader wait/fill, issuer wait/issue, epilogue wait/work */
+    int32_t dbg_flags;       /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging, 4 = skip epilogue stores */
+    int32_t pad_;
 } rd_conv_params;
 
 int rd_conv_fprop(const rd_conv_params* p, void* stream);

@@ -45,7 +45,7 @@ class ConvParams(C.Structure):
         ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_slope", C.c_float),
         ("stats", C.c_void_p), ("stats_stride", C.c_int32),
         ("IS", C.c_int32), ("WS", C.c_int32), ("istage_bytes", C.c_int32), ("wstage_bytes", C.c_int32),
-        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32),
+        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -19,7 +19,9 @@ the descriptions (against F.conv2d on CPU) and the kernels (on the GPU).
 """
 from __future__ import annotations
 
+import json
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -28,6 +30,25 @@ import numpy as np
 from . import _lib
 
 SMEM_BUDGET = 232448
+_TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_tiles.json")
+_TUNED = None
+
+
+def tuned_table() -> dict:
+    """Tile choices measured on a B200 by tools/autotune.py (committed with the repo); the analytic cost models below
+    are the fallback for shapes that are not in the table."""
+    global _TUNED
+    if _TUNED is None:
+        try:
+            with open(_TUNED_PATH) as f:
+                _TUNED = json.load(f)
+        except Exception:
+            _TUNED = {}
+    return _TUNED
+
+
+def tune_key(kind: str, g: "GConv", B: int, src_hw, dst_hw, act_dtype: int) -> str:
+    return f"{kind}|Cx{g.Cx}|N{g.N}|S{g.S}|OS{g.OS}|T{len(g.taps)}|{src_hw[0]}x{src_hw[1]}>{dst_hw[0]}x{dst_hw[1]}|B{B}|dt{act_dtype}"
 FPROP_HEADER = 16384
 WGRAD_HEADER = 10240
 NUM_SMS = 148
@@ -215,12 +236,19 @@ class FpropPlan:
 
 
 def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16):
+    """Tile search.  The cost model was fitted to per-role cycle counters measured on B200 (tools/bench_fprop.py):
+    UMMA ~max(48, N/2) cycles each, epilogue ~40 cycles per 16 columns per 32 rows (overlapped with the next tile
+    when two accumulator sets fit in TMEM), ~2.5k cycles of pipeline hand-off per tile, and a strong preference for
+    wide tiles (long contiguous runs per row for the loaders) with at most 4 accumulator blocks."""
     best = None
     MBmax = max(1, 512 // (P * N))
+    if N >= 64:
+        MBmax = min(MBmax, 4)
     planes = S * S
+    wl_min = min(24, Wb + halo_x)
     for MB in range(1, MBmax + 1):
         M = MB * 128
-        for Wl in range(halo_x + 1, min(Wb + halo_x, M) + 1):
+        for Wl in range(max(halo_x + 1, wl_min), min(Wb + halo_x, M, 256 // S) + 1):
             Wt = Wl - halo_x
             Ht = min(M // Wl, Hb)
             if Ht < 1:
@@ -233,17 +261,14 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
             if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > SMEM_BUDGET:
                 continue
             ty, tx = -(-Hb // Ht), -(-Wb // Wt)
-            # cycle model per 16-channel stage: tensor pipe vs loader warps vs L2->SMEM traffic (source tile + the
-            # weight block, which every CTA streams again for every tile), plus the epilogue per tile
-            mma = MB * ntaps * max(N, 32) / 2.0 * (3 if parts == 2 else 1)
-            load = planes * plane_rows * Wl * 2 * 0.08 * parts
-            l2 = (planes * plane_rows * Wl * 32 * (2 if parts == 2 else 1) + ntaps * N * 32 * parts) / L2_BYTES_PER_CYCLE
-            epi = MB * P * (N / 16.0) * 40.0
-            stage = max(mma, load, l2)
+            mma = MB * ntaps * max(N, 96) / 2.0 * (3 if parts == 2 else 1)
+            load = planes * plane_rows * Wl * 2 * 0.9 * parts
+            epi = MB * P * (N / 16.0) * 160.0
+            stage = max(mma, load)
             if 2 * P * MB * N <= 512:          # two accumulator sets: the epilogue overlaps the next tile's MMAs
-                per_tile = max(stage * ncblk, epi) + 300.0
+                per_tile = max(stage * ncblk, epi) + 2500.0
             else:
-                per_tile = stage * ncblk + epi + 600.0
+                per_tile = stage * ncblk + epi + 2500.0
             ctas = max(1, NUM_SMS // nblk)
             rounds = -(-(ty * tx * B_) // ctas)
             cost = rounds * per_tile
@@ -256,7 +281,7 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
 
 
 def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, n_per_cta: Optional[int] = None,
-               tile_override: Optional[dict] = None) -> FpropPlan:
+               tile_override: Optional[dict] = None, use_tuned: bool = True) -> FpropPlan:
     assert g.Cx % 16 == 0 and g.N % 16 == 0, (g.Cx, g.N)
     parts = 2 if act_dtype == _lib.RD_F32 else 1
     taps, phases = g.sorted_taps()
@@ -286,6 +311,8 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     base, rem = divmod(ntaps, ngroups)
     grp_n = [base + (1 if i < rem else 0) for i in range(ngroups)]
     wstage = _round_up(max(grp_n) * tap_bytes, 128)
+    if tile_override is None and use_tuned:
+        tile_override = tuned_table().get(tune_key("f", g, B, src_hw, dst_hw, act_dtype))
     geo = tile_override or _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B)
     if tile_override:
         geo = dict(geo)
@@ -367,9 +394,13 @@ class WgradPlan:
 
 
 def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
-               nc: Optional[int] = None) -> WgradPlan:
+               nc: Optional[int] = None, use_tuned: bool = True) -> WgradPlan:
     """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient."""
     assert g.Cx % 16 == 0 and g.N % 8 == 0
+    if use_tuned and nc is None:
+        t = tuned_table().get(tune_key("w", g, B, x_hw, g_hw, act_dtype))
+        if t:
+            nc, ks_target = t["nc"], t["ks"]
     parts = 2 if act_dtype == _lib.RD_F32 else 1
     taps, phases = g.sorted_taps()
     ntaps = len(taps)

@@ -156,8 +156,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
             for (int c = 0; c < ncblk; ++c) {
+                const long long t0_ = p.dbg ? clock64() : 0;
                 mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
+                const long long t1_ = p.dbg ? clock64() : 0;
                 uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
+                if (p.dbg_flags & 2) {
+                    if (src_async) cp_async_mbar_arrive_noinc(&in_full[st.stage]);
+                    else { __syncwarp(); if (lane == 0) mbar_arrive(&in_full[st.stage]); }
+                } else
                 if (src_async) {
                     stage_tile_async<T>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
                     cp_async_mbar_arrive_noinc(&in_full[st.stage]);
@@ -167,6 +173,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     if (lane == 0) mbar_arrive(&in_full[st.stage]);
                 }
                 st.advance();
+                if (p.dbg && warp == 4 && lane == 0) {
+                    const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+                    p.dbg[0 * ncta + cta] += t1_ - t0_;
+                    p.dbg[1 * ncta + cta] += clock64() - t1_;
+                }
             }
         }
     } else if (warp == kWarpW) {
@@ -213,13 +224,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 tc_fence_after();
                 const uint32_t d_tile = tmem_u + ab * (uint32_t)acc_cols;
                 for (int c = 0; c < ncblk; ++c) {
+                    const long long t0_ = p.dbg ? clock64() : 0;
                     mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
+                    const long long t1_ = p.dbg ? clock64() : 0;
+                    long long tw_ = 0;
                     fence_proxy_async_smem();      // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
                     tc_fence_after();
                     const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), a_lbo, 128);
                     int t = 0;
                     for (int g = 0; g < p.ngroups; ++g) {
+                        const long long t2_ = p.dbg ? clock64() : 0;
                         mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
+                        if (p.dbg) tw_ += clock64() - t2_;
                         tc_fence_after();
                         uint64_t db = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), b_lbo, 128);
                         const int gn = p.grp_n[g];
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                             const uint32_t acc = (c == 0 && p.taps[t].first) ? 0u : 1u;
 #pragma unroll 4
                             for (int mb = 0; mb < p.MB; ++mb, da += 128, d += (uint32_t)p.N) {
-                                if (leader) {
+                                if (leader && !(p.dbg_flags & 1)) {
                                     umma_bf16(d, da, db, idesc, acc);
                                     if (SPLIT == 3) {
                                         umma_bf16(d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
@@ -245,6 +261,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     }
                     if (leader) umma_commit(&in_empty[si.stage]);
                     si.advance();
+                    if (p.dbg && lane == 0) {
+                        const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+                        p.dbg[2 * ncta + cta] += (t1_ - t0_) + tw_;
+                        p.dbg[3 * ncta + cta] += clock64() - t1_ - tw_;
+                    }
                 }
                 if (leader) umma_commit(&tmem_full[ab]);
                 __syncwarp();
@@ -266,7 +287,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const int y0 = ty * p.Ht, x0 = tx * p.Wt;
             const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
             const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
+            const long long t0_ = p.dbg ? clock64() : 0;
             mbar_wait(&tmem_full[ab], use & 1u, 0x400);
+            const long long t1_ = p.dbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t t_tile = tmem_base + ab * (uint32_t)acc_cols + ((uint32_t)(warp * 32) << 16);
             for (int cc = 0; cc < (p.N >> 4); ++cc) {
@@ -282,7 +305,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                         const bool valid = ly < p.Ht && lx < p.Wt && oy < p.Hb && ox < p.Wb && fy < p.dstH && fx < p.dstW;
                         float v[16];
                         tmem_ld16(t_tile + (uint32_t)((ph * p.MB + mb) * p.N + cc * 16), v);
-                        if (valid) {
+                        if (valid && !(p.dbg_flags & 4)) {
                             const size_t pix = ((size_t)img * p.dstH + fy) * p.dstW + fx;
                             const int ch = nb * p.N + cc * 16;
                             if (addend) {
@@ -326,6 +349,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+            if (p.dbg && warp == 0 && lane == 0) {
+                const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+                p.dbg[4 * ncta + cta] += t1_ - t0_;
+                p.dbg[5 * ncta + cta] += clock64() - t1_;
+            }
         }
         if (want_stats) {
             asm volatile("bar.sync 1, 128;\n" ::: "memory");

@@ -44,11 +44,13 @@ def pack_weights(wflat: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Ten
 
 def conv_fprop(plan, src: View, wpk, dst: View, ld=None, epi: int = 0, addend: Optional[View] = None,
                zsrc: Optional[View] = None, ep=None, stats: Optional[Tuple[torch.Tensor, int]] = None,
-               max_ctas: Optional[int] = None):
+               max_ctas: Optional[int] = None, dbg=None, dbg_flags: int = 0):
     """Launch one tcgen05 convolution program.  ``wpk``: packed weights (tensor or raw pointer);
     ``ld`` = (scale, shift, slope) fuses the producer's BN+activation on load; ``ep`` likewise for the
     activation-gradient epilogue (epi=1); ``stats`` = (fp64 tensor [2, stride], stride)."""
     p = type(plan.params).from_buffer_copy(plan.params)
+    p.dbg = ptr(dbg) if dbg is not None else None
+    p.dbg_flags = dbg_flags
     p.src = src
     p.dst = dst
     p.wpk = wpk if isinstance(wpk, int) else ptr(wpk)

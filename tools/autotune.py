@@ -1,0 +1,124 @@
+"""Measures tile choices for every convolution program of resnet18_latefusion at a given batch / size on the GPU and
+writes radar_depth_b200/tuned_tiles.json (committed: the table travels with the repo, the planner falls back to its
+cost model for shapes that are missing).  usage: python tools/autotune.py [batch] [H] [W]"""
+import json
+import os
+import sys
+import torch
+from radar_depth_b200 import _lib, convplan as cp, ops
+from radar_depth_b200.model.models import ResNet_latefusion
+from radar_depth_b200.engine import LatefusionEngine
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 352
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 1216
+act = _lib.RD_BF16
+table = cp.tuned_table().copy()
+cp._TUNED = {}                       # plan from the cost model while tuning
+
+
+def time_launch(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def fprop_candidates(g, src_hw, dst_hw):
+    taps, phases = g.sorted_taps()
+    P = len(phases)
+    N = min(g.N, 128)
+    while g.N % N:
+        N -= 16
+    dH, dW = dst_hw
+    Hb, Wb = -(-dH // g.OS), -(-dW // g.OS)
+    sx = [t.s[1] for t in taps]
+    halo_x = max(sx) - min(sx)
+    out = []
+    for MB in range(1, max(1, 512 // (P * N)) + 1):
+        M = MB * 128
+        for Wl in sorted({16, 24, 32, 40, 48, 64, 80, 96, 128, 160, 192, 256, Wb + halo_x, (Wb + 1) // 2 + halo_x, (Wb + 2) // 3 + halo_x}):
+            if Wl <= halo_x or Wl > min(M, 256 // g.S) or Wl > Wb + halo_x:
+                continue
+            Ht = min(M // Wl, Hb)
+            if Ht < 1 or (MB > 1 and Ht * Wl <= (MB - 1) * 128):
+                continue
+            out.append(dict(Ht=Ht, Wt=Wl - halo_x))
+    return out
+
+
+m = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False)
+eng = LatefusionEngine(m, 4, (H, W), act)
+eng.adopt("cpu")
+eng.configure(B, H, W)
+seen = set()
+for rec in eng.convs:
+    g = rec["g"]
+    fp = rec["fplan"].params
+    src_hw, dst_hw = (fp.srcH, fp.srcW), (fp.dstH, fp.dstW)
+    jobs = [("f", g, src_hw, dst_hw)]
+    if rec["dplan"] is not None:
+        jobs.append(("f", g.transposed(), dst_hw, src_hw))
+    for kind, gg, s_hw, d_hw in jobs:
+        key = cp.tune_key(kind, gg, B, s_hw, d_hw, act)
+        if key in seen:
+            continue
+        seen.add(key)
+        x = torch.randn(B, s_hw[0], s_hw[1], gg.Cx, device="cuda").bfloat16()
+        w = torch.randn(int(max(int(t.widx.max()) for t in gg.taps)) + 1, device="cuda") * 0.05
+        out = torch.empty(B, d_hw[0], d_hw[1], gg.N, device="cuda", dtype=torch.bfloat16)
+        stats = torch.zeros(2, gg.N, dtype=torch.float64, device="cuda")
+        best = None
+        for ov in [None] + fprop_candidates(gg, s_hw, d_hw):
+            try:
+                plan = cp.plan_fprop(gg, B, s_hw, d_hw, act, tile_override=ov, use_tuned=False)
+            except Exception:
+                continue
+            wpk = ops.pack_weights(w, torch.from_numpy(plan.pack_idx).cuda())
+            try:
+                ms = time_launch(lambda: ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), stats=(stats, gg.N)))
+            except Exception as e:  # noqa
+                continue
+            geo = plan.info["geo"]
+            if best is None or ms < best[0]:
+                best = (ms, dict(Ht=geo["Ht"], Wt=geo["Wt"]), ov is None)
+            if ov is None:
+                base = ms
+        table[key] = best[1]
+        print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
+    if rec["wplan"] is not None:
+        key = cp.tune_key("w", g, B, src_hw, dst_hw, act)
+        if key in seen:
+            continue
+        seen.add(key)
+        x = torch.randn(B, src_hw[0], src_hw[1], g.Cx, device="cuda").bfloat16()
+        dy = torch.randn(B, dst_hw[0], dst_hw[1], g.N, device="cuda").bfloat16()
+        best, base = None, None
+        for nc in (None, 16, 32, 64, 128):
+            for ks in (128, 192, 256, 384):
+                if nc is not None and (nc > g.Cx or g.Cx % nc):
+                    continue
+                try:
+                    plan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, ks_target=ks, nc=nc, use_tuned=False)
+                except Exception:
+                    continue
+                dw = torch.zeros(plan.dw_elems, device="cuda")
+                try:
+                    ms = time_launch(lambda: ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw))
+                except Exception:
+                    continue
+                if nc is None and ks == 256:
+                    base = ms
+                if best is None or ms < best[0]:
+                    best = (ms, dict(nc=plan.info["Nc"], ks=ks))
+        table[key] = best[1]
+        print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/tuned_tiles.json", "w") as f:
+    json.dump(table, f, indent=0, sort_keys=True)
+print("entries", len(table))

@@ -1,0 +1,49 @@
+"""Times the tcgen05 forward/data-gradient program on one layer shape with per-role cycle counters (GPU box)."""
+import statistics
+import sys
+import torch
+from radar_depth_b200 import _lib, convplan as cp, ops
+
+shapes = {"l1": (64, 64, 3, 1, 1, (88, 304), (88, 304)), "l2": (128, 128, 3, 1, 1, (44, 152), (44, 152)),
+          "l3": (256, 256, 3, 1, 1, (22, 76), (22, 76)), "l4": (512, 512, 3, 1, 1, (11, 38), (11, 38)),
+          "l2s2": (128, 64, 3, 2, 1, (88, 304), (44, 152)), "d16": (16, 16, 3, 1, 1, (176, 608), (176, 608))}
+name = sys.argv[1] if len(sys.argv) > 1 else "l1"
+bn = len(sys.argv) > 2 and sys.argv[2] == "bn"
+Cout, Cin, k, s, pad, shw, dhw = shapes[name]
+B = 16
+g = cp.gconv_standard(0, Cout, Cin, k, s, pad)
+x = torch.randn(B, shw[0], shw[1], Cin, device="cuda").bfloat16()
+w = torch.randn(Cout * Cin * k * k, device="cuda") * 0.05
+sc, sh = torch.rand(Cin, device="cuda") + 0.5, torch.randn(Cin, device="cuda") * 0.1
+flops = 2.0 * B * dhw[0] * dhw[1] * k * k * Cin * Cout
+overrides = [None]
+if len(sys.argv) > 3:
+    for spec in sys.argv[3:]:
+        ht, wt = (int(v) for v in spec.split("x"))
+        overrides.append(dict(Ht=ht, Wt=wt))
+for ov in overrides:
+    plan = cp.plan_fprop(g, B, shw, dhw, _lib.RD_BF16, tile_override=ov)
+    wpk = ops.pack_weights(w, torch.from_numpy(plan.pack_idx).cuda())
+    out = torch.empty(B, dhw[0], dhw[1], Cout, device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(2, Cout, dtype=torch.float64, device="cuda")
+    ld = (sc, sh, 0.0) if bn else None
+    p = plan.params
+    ncta = min(p.max_ctas, plan.ntiles) * p.nblk
+    i = plan.info
+    print(f"{name}{' +bn' if bn else ''}: geo={ {k_: i['geo'][k_] for k_ in ('MB', 'Wl', 'Wt', 'Ht', 'tiles_y', 'tiles_x')} } N={i['N']}x{i['nblk']} IS={i['IS']} WS={i['WS']} tiles={plan.ntiles} ctas={ncta}")
+    for fl, nm in ((0, "full"), (1, "no-MMA"), (2, "no-load"), (4, "no-store"), (7, "neither")):
+        for _ in range(3):
+            ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg_flags=fl)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg_flags=fl); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        dbg = torch.zeros(6, ncta, dtype=torch.int64, device="cuda")
+        ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg=dbg, dbg_flags=fl)
+        torch.cuda.synchronize()
+        d = dbg.double().mean(dim=1).cpu().numpy() / 1e3
+        ms = statistics.median(ts)
+        print(f"   {nm:8s} {ms * 1e3:7.1f} us {flops / ms / 1e9:7.1f} TF | kcyc/CTA loader wait {d[0]:6.1f} fill {d[1]:6.1f} | issuer wait {d[2]:6.1f} issue {d[3]:6.1f} | epi wait {d[4]:6.1f} work {d[5]:6.1f}")

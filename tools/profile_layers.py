@@ -34,14 +34,17 @@ st = torch.cuda.current_stream().cuda_stream
 rows = []
 for prog in (eng.fwd, eng.bwd):
     for L in prog:
-        evs = []
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); rc = L.fn(*L.args, st); e1.record()
+        # 4 launches back to back inside one event pair: the queue hides the host launch latency, which would
+        # otherwise be charged to short kernels
+        reps = 4
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            rc = L.fn(*L.args, st)
             assert rc == 0
-            evs.append((e0, e1))
+        e1.record()
         torch.cuda.synchronize()
-        ms = statistics.median(a.elapsed_time(c) for a, c in evs)
+        ms = e0.elapsed_time(e1) / reps
         rows.append((L.name, ms))
 tot = sum(r[1] for r in rows)
 print(f"total {tot:.3f} ms over {len(rows)} launches, b={b} {prec}")
