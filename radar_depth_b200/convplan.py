@@ -393,6 +393,40 @@ class WgradPlan:
     info: dict = field(default_factory=dict)
 
 
+def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks_target):
+    """KS slots per plane / tile shape minimising the modelled cycles subject to >= 2 ring stages in shared memory."""
+    tg_cap = max(1, min(16, 512 // Nc))
+    ntg = -(-ntaps // tg_cap)
+    tg_size = -(-ntaps // ntg)
+    best = None
+    for KS in (32, 64, 96, 128, 192, 256, 384, 512):
+        if KS > max(ks_target, 32):
+            continue
+        for Wl in range(halo_x + 1, min(Wb + halo_x, KS) + 1):
+            Wt = Wl - halo_x
+            Ht = min(KS // Wl, Hb)
+            if Ht < 1:
+                continue
+            xrows = Ht + halo_y
+            xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
+            GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
+            XPS = _chunk_stride(g.S * g.S * xslots, Nc // 8)
+            g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
+            stage = _round_up(g_bytes + parts * (Nc // 8) * XPS * 16, 128)
+            # the M=128 operand always spans 16 chunk planes; rows past Mc are junk but must stay inside smem
+            pad = max(0, ((parts - 1) * (Mc // 8) + 16) * GPS * 16 - stage)
+            if WGRAD_HEADER + 2 * stage + pad > SMEM_BUDGET:
+                continue
+            ty, tx = -(-Hb // Ht), -(-Wb // Wt)
+            load = (Mc // 8) * GPS + (Nc // 8) * XPS
+            mma = (KS // 16) * tg_size * max(Nc, 32) / 2.0 * (3 if parts == 2 else 1)
+            cost = ty * tx * (max(mma, load * 0.35 * parts) + 300.0)
+            if best is None or cost < best[0]:
+                best = (cost, dict(KS=KS, Wl=Wl, Wt=Wt, Ht=Ht, xrows=xrows, xslots=xslots, g_bytes=g_bytes,
+                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad, GPS=GPS, XPS=XPS))
+    return best
+
+
 def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
                nc: Optional[int] = None, use_tuned: bool = True) -> WgradPlan:
     """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient."""
@@ -420,40 +454,18 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
         for cand in range(16, min(g.Cx, 256) + 1, 16):
             if g.Cx % cand == 0 and tpc * cand <= 512:
                 nc = cand
-    Nc = nc
+    nc_candidates = [nc] + [c for c in (128, 64, 32, 16) if c < nc and g.Cx % c == 0]
+    best = None
+    for Nc in nc_candidates:
+        best = _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks_target)
+        if best is not None:
+            break
+    if best is None:
+        raise ValueError("no feasible wgrad tile")
     ncib = g.Cx // Nc
     tg_cap = max(1, min(16, 512 // Nc))
     ntg = -(-ntaps // tg_cap)
     tg_size = -(-ntaps // ntg)
-    # tile search: KS slots per plane, minimise staged bytes per useful pixel subject to >= 2 stages
-    best = None
-    for KS in (32, 64, 96, 128, 192, 256, 384, 512):
-        if KS > max(ks_target, 32):
-            continue
-        for Wl in range(halo_x + 1, min(Wb + halo_x, KS) + 1):
-            Wt = Wl - halo_x
-            Ht = min(KS // Wl, Hb)
-            if Ht < 1:
-                continue
-            xrows = Ht + halo_y
-            xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
-            GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
-            XPS = _chunk_stride(g.S * g.S * xslots, Nc // 8)
-            g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
-            stage = _round_up(g_bytes + parts * (Nc // 8) * XPS * 16, 128)
-            # the M=128 operand always spans 16 chunk planes; rows past Mc are junk but must stay inside smem
-            pad = max(0, ((parts - 1) * (Mc // 8) + 16) * GPS * 16 - stage)
-            if WGRAD_HEADER + 2 * stage + pad > SMEM_BUDGET:
-                continue
-            ty, tx = -(-Hb // Ht), -(-Wb // Wt)
-            load = (Mc // 8) * GPS + (Nc // 8) * XPS
-            mma = (KS // 16) * tg_size * max(Nc, 32) / 2.0 * (3 if parts == 2 else 1)
-            cost = ty * tx * (max(mma, load * 0.35 * parts) + 300.0)
-            if best is None or cost < best[0]:
-                best = (cost, dict(KS=KS, Wl=Wl, Wt=Wt, Ht=Ht, xrows=xrows, xslots=xslots, g_bytes=g_bytes,
-                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad, GPS=GPS, XPS=XPS))
-    if best is None:
-        raise ValueError("no feasible wgrad tile")
     geo = best[1]
     NS = 2
     while NS < 4 and WGRAD_HEADER + (NS + 1) * geo["stage"] + geo["pad"] <= SMEM_BUDGET:

@@ -179,6 +179,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Exact n / d for n * d < 2^32 with one multiply-high (d is a runtime constant of the launch).
+struct FastDiv {
+    uint32_t m, d;
+    __device__ __forceinline__ FastDiv() : m(0), d(1) {}
+    __device__ __forceinline__ explicit FastDiv(uint32_t d_) : m(d_ > 1 ? 0xFFFFFFFFu / d_ + 1u : 0u), d(d_) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
+};
+
 // Activation storage abstraction: bf16 (throughput mode) or fp32 (parity mode).
 template <typename T> struct Act;
 template <> struct Act<bf16> {

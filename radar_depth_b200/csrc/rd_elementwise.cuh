@@ -128,9 +128,10 @@ __global__ void bn_add_act_kernel(VView z, const float* __restrict__ sc, const f
                                   const float* __restrict__ id_sc, const float* __restrict__ id_sh, VView out,
                                   size_t npix, int C, float slope) {
     const int groups = C >> 3;
-    const size_t total = npix * groups;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t pix = i / groups;
+    const uint32_t total = (uint32_t)npix * (uint32_t)groups;       // launcher guarantees npix * groups < 2^31
+    const FastDiv fdg((uint32_t)groups);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = fdg.div(i);
         const int c = (int)(i - pix * groups) * 8;
         float v[8], r[8];
         Act<T>::load8(vptr<T>(z, pix, c), v);
@@ -189,9 +190,10 @@ template <typename T>
 __global__ void bn_bwd_apply_kernel(VView g, VView z, VView dz, const float* __restrict__ A, const float* __restrict__ Bz,
                                     const float* __restrict__ Cc, size_t npix, int C) {
     const int groups = C >> 3;
-    const size_t total = npix * groups;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t pix = i / groups;
+    const uint32_t total = (uint32_t)npix * (uint32_t)groups;
+    const FastDiv fdg((uint32_t)groups);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = fdg.div(i);
         const int c = (int)(i - pix * groups) * 8;
         float gv[8], zv[8];
         Act<T>::load8(vptr<T>(g, pix, c), gv);
@@ -238,13 +240,15 @@ __global__ void maxpool_fwd_kernel(VView z, const float* __restrict__ sc, const 
                                    int C, int split, float slope_a, float slope_b, VView outa, VView outb,
                                    uint8_t* __restrict__ amax, int Ho, int Wo) {
     const int groups = C >> 3;
-    const size_t total = (size_t)B * Ho * Wo * groups;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t pix = i / groups;
+    const uint32_t total = (uint32_t)B * Ho * Wo * groups;
+    const FastDiv fdg((uint32_t)groups), fdw((uint32_t)Wo), fdh((uint32_t)Ho);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = fdg.div(i);
         const int c = (int)(i - pix * groups) * 8;
-        const int ox = (int)(pix % Wo);
-        const int oy = (int)((pix / Wo) % Ho);
-        const int b = (int)(pix / ((size_t)Wo * Ho));
+        const uint32_t prow = fdw.div(pix);
+        const int ox = (int)(pix - prow * Wo);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * Ho);
         const float slope = c < split ? slope_a : slope_b;
         float best[8];
         int bi[8];
@@ -297,12 +301,14 @@ __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restri
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
-    const size_t npix = (size_t)B * H * W;
+    const uint32_t npix = (uint32_t)B * H * W;
+    const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
     if (pl < ppb) {
-        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += (size_t)gridDim.x * ppb) {
-            const int ix = (int)(pix % W);
-            const int iy = (int)((pix / W) % H);
-            const int b = (int)(pix / ((size_t)W * H));
+        for (uint32_t pix = blockIdx.x * ppb + pl; pix < npix; pix += gridDim.x * ppb) {
+            const uint32_t prow = fdw.div(pix);
+            const int ix = (int)(pix - prow * W);
+            const int b = (int)fdh.div(prow);
+            const int iy = (int)(prow - (uint32_t)b * H);
             float gsum[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) gsum[k] = 0.f;
@@ -353,11 +359,13 @@ __global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16]
     __shared__ float ws[144];
     for (int i = threadIdx.x; i < 144; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
-    const size_t total = (size_t)B * H * W;
-    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(pix % W);
-        const int oy = (int)((pix / W) % H);
-        const int b = (int)(pix / ((size_t)W * H));
+    const uint32_t total = (uint32_t)B * H * W;
+    const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+        const uint32_t prow = fdw.div(pix);
+        const int ox = (int)(pix - prow * W);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * H);
         float acc = 0.f;
         for (int dy = 0; dy < 3; ++dy) {
             const int iy = oy + dy - 1;
@@ -391,10 +399,12 @@ __global__ void head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, con
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int c = 0; c < 16; ++c) wacc[t][c] = 0.f;
-    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(pix % W);
-        const int oy = (int)((pix / W) % H);
-        const int b = (int)(pix / ((size_t)W * H));
+    const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < (uint32_t)total; pix += gridDim.x * blockDim.x) {
+        const uint32_t prow = fdw.div(pix);
+        const int ox = (int)(pix - prow * W);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * H);
         // data gradient at this pixel (gather form) and weight gradient (this pixel's x against shifted dc3)
         float xv[16], dxa[16];
         Act<T>::load8(vptr<T>(x, pix, 0), xv);

@@ -13,14 +13,6 @@
 
 namespace rd {
 
-// Exact n / d for n * d < 2^32 with one multiply-high (d is a runtime constant of the launch).
-struct FastDiv {
-    uint32_t m, d;
-    __device__ __forceinline__ FastDiv() : m(0), d(1) {}
-    __device__ __forceinline__ explicit FastDiv(uint32_t d_) : m(d_ > 1 ? 0xFFFFFFFFu / d_ + 1u : 0u), d(d_) {}
-    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
-};
-
 struct TileSrc {
     const void* ptr;
     int pitch, coff;        // NHWC view
