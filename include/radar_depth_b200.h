@@ -41,7 +41,7 @@ extern "C" {
 const char* rd_last_error(void);
 int rd_version(void);
 /* sizeof() of the parameter blocks below, for binding self-checks. */
-int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params */
+int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params, 2: rd_bn_tail */
 /* reads and clears the device-side error word (0 = none).  Synchronises the stream. */
 int rd_device_error(void* stream);
 
@@ -51,6 +51,42 @@ typedef struct rd_view {
     int32_t pitch; /* elements per pixel in the underlying buffer (multiple of 8) */
     int32_t coff;  /* first channel of the slice (multiple of 8) */
 } rd_view;
+
+/* BatchNorm finalisation fused into the tail of the kernel that produces its statistics: the LAST CTA to finish
+ * (ticket counter) turns the per-channel fp64 sums into the vectors the next kernel consumes, so that no separate
+ * one-block launch sits between two convolutions.  Same arithmetic as rd_bn_finalize / rd_bn_bwd_finalize.
+ *   kind 1 (forward, training):  sum_a = sum z, sum_b = sum z^2 -> v0 = scale, v1 = shift, v2 = save_mean,
+ *                                v3 = save_invstd; running_mean/var (unbiased) and num_batches_tracked updated.
+ *   kind 2 (backward):           sum_a = sum g, sum_b = sum g*z, v0 = save_mean (read), v1 = save_invstd (read),
+ *                                v2 = dgamma (+=), v3 = dbeta (+=), cA/cB/cC = coefficients of dz = A*g + B*z + C. */
+typedef struct rd_bn_job {
+    int32_t kind; /* 0 = none */
+    int32_t C;
+    const double* sum_a;
+    const double* sum_b;
+    double count;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    long long* nbt;
+    float* v0;
+    float* v1;
+    float* v2;
+    float* v3;
+    float* cA;
+    float* cB;
+    float* cC;
+    float momentum, eps;
+} rd_bn_job;
+
+#define RD_MAX_BN_JOBS 2
+typedef struct rd_bn_tail {
+    uint32_t* counter; /* zero before the launch; NULL = no fused finalisation */
+    int32_t njobs;
+    int32_t pad_;
+    rd_bn_job job[RD_MAX_BN_JOBS];
+} rd_bn_tail;
 
 typedef struct rd_tap {
     int32_t a_shift; /* slot offset of this tap inside the staged input tile (includes the parity-plane base) */
@@ -104,6 +140,7 @@ typedef struct rd_conv_params {
     float ep_slope;
     double* stats;           /* [2][stats_stride] or NULL */
     int32_t stats_stride;
+    rd_bn_tail tail;         /* BatchNorm finalisation(s) run by the last CTA (needs stats) */
     /* pipeline */
     int32_t IS, WS;          /* input / weight ring depths */
     int32_t istage_bytes, wstage_bytes;
@@ -175,7 +212,8 @@ int rd_bn_add_act(rd_view z, const float* sc, const float* sh, rd_view idv, cons
                   rd_view out, long long npix, int C, float slope, int act_dtype, void* stream);
 /* g = dout*act'(out) + BN-backward statistics of the joined branches. */
 int rd_join_bwd(rd_view dout, rd_view out, rd_view z, rd_view zid, rd_view g, long long npix, int C, float slope,
-                double* sum_g, double* sum_gz, double* sum_gzid, int act_dtype, void* stream);
+                double* sum_g, double* sum_gz, double* sum_gzid, const rd_bn_tail* tail /* may be NULL */, int act_dtype,
+                void* stream);
 int rd_bn_bwd_apply(rd_view g, rd_view z, rd_view dz, const float* coefA, const float* coefB, const float* coefC,
                     long long npix, int C, int act_dtype, void* stream);
 int rd_grad_stats(rd_view g, rd_view z, long long npix, int C, double* sum_g, double* sum_gz, int act_dtype, void* stream);
@@ -185,7 +223,7 @@ int rd_maxpool_fwd(rd_view z, const float* sc, const float* sh, int B, int H, in
                    float slope_b, rd_view outa, rd_view outb, uint8_t* amax, int Ho, int Wo, int act_dtype, void* stream);
 int rd_maxpool_bwd(rd_view dpa, rd_view dpb, const uint8_t* amax, rd_view z, const float* sc, const float* sh, int B,
                    int H, int W, int C, int split, float slope_a, float slope_b, int Ho, int Wo, rd_view g,
-                   double* sum_g, double* sum_gz, int act_dtype, void* stream);
+                   double* sum_g, double* sum_gz, const rd_bn_tail* tail /* may be NULL */, int act_dtype, void* stream);
 
 /* conv3 (3x3, 16->1, models.py:587,661) and nn.Upsample(bilinear, align_corners=True) (models.py:588,662). */
 int rd_head_conv_fwd(rd_view x, const float* w, int B, int H, int W, float* out, int act_dtype, void* stream);

@@ -27,6 +27,21 @@ class Tap(C.Structure):
     _fields_ = [("a_shift", C.c_int32), ("phase", C.c_int32), ("first", C.c_int32), ("pad_", C.c_int32)]
 
 
+class BnJob(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("C", C.c_int32), ("sum_a", C.c_void_p), ("sum_b", C.c_void_p), ("count", C.c_double),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("nbt", C.c_void_p), ("v0", C.c_void_p), ("v1", C.c_void_p), ("v2", C.c_void_p), ("v3", C.c_void_p),
+                ("cA", C.c_void_p), ("cB", C.c_void_p), ("cC", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float)]
+
+
+RD_MAX_BN_JOBS = 2
+
+
+class BnTail(C.Structure):
+    """rd_bn_tail: BatchNorm finalisation(s) executed by the last CTA of the statistics-producing kernel."""
+    _fields_ = [("counter", C.c_void_p), ("njobs", C.c_int32), ("pad_", C.c_int32), ("job", BnJob * RD_MAX_BN_JOBS)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [
         ("src", View), ("srcH", C.c_int32), ("srcW", C.c_int32), ("Cin", C.c_int32), ("S", C.c_int32),
@@ -43,7 +58,7 @@ class ConvParams(C.Structure):
         ("dst", View), ("dstH", C.c_int32), ("dstW", C.c_int32),
         ("epi", C.c_int32), ("addend", View), ("zsrc", View),
         ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_slope", C.c_float),
-        ("stats", C.c_void_p), ("stats_stride", C.c_int32),
+        ("stats", C.c_void_p), ("stats_stride", C.c_int32), ("tail", BnTail),
         ("IS", C.c_int32), ("WS", C.c_int32), ("istage_bytes", C.c_int32), ("wstage_bytes", C.c_int32),
         ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("pad_", C.c_int32),
     ]
@@ -83,11 +98,11 @@ _PROTOS = {
     "rd_bn_finalize": ([_P, _P, _D, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P], _I),
     "rd_bn_bwd_finalize": ([_P, _P, _D, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "rd_bn_add_act": ([View, _P, _P, View, _P, _P, View, _LL, _I, _F, _I, _P], _I),
-    "rd_join_bwd": ([View, View, View, View, View, _LL, _I, _F, _P, _P, _P, _I, _P], _I),
+    "rd_join_bwd": ([View, View, View, View, View, _LL, _I, _F, _P, _P, _P, C.POINTER(BnTail), _I, _P], _I),
     "rd_bn_bwd_apply": ([View, View, View, _P, _P, _P, _LL, _I, _I, _P], _I),
     "rd_grad_stats": ([View, View, _LL, _I, _P, _P, _I, _P], _I),
     "rd_maxpool_fwd": ([View, _P, _P, _I, _I, _I, _I, _I, _F, _F, View, View, _P, _I, _I, _I, _P], _I),
-    "rd_maxpool_bwd": ([View, View, _P, View, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, View, _P, _P, _I, _P], _I),
+    "rd_maxpool_bwd": ([View, View, _P, View, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, View, _P, _P, C.POINTER(BnTail), _I, _P], _I),
     "rd_head_conv_fwd": ([View, _P, _I, _I, _I, _P, _I, _P], _I),
     "rd_head_conv_bwd": ([_P, View, _P, _I, _I, _I, View, _P, _I, _P], _I),
     "rd_bilinear_fwd": ([_P, _I, _I, _I, _P, _I, _I, _P], _I),
@@ -119,6 +134,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
+    if lib.rd_sizeof(2) != C.sizeof(BnTail):
+        raise RdError(f"rd_bn_tail layout mismatch: {lib.rd_sizeof(2)} vs {C.sizeof(BnTail)}")
     if lib.rd_sizeof(0) != C.sizeof(ConvParams) or lib.rd_sizeof(1) != C.sizeof(WgradParams):
         raise RdError("parameter block layout mismatch between _lib.py and the built library: "
                       f"{lib.rd_sizeof(0)} vs {C.sizeof(ConvParams)}, {lib.rd_sizeof(1)} vs {C.sizeof(WgradParams)}")

@@ -54,6 +54,7 @@ int rd_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(rd_conv_params);
         case 1: return (int)sizeof(rd_wgrad_params);
+        case 2: return (int)sizeof(rd_bn_tail);
         default: return -1;
     }
 }
@@ -71,6 +72,8 @@ int rd_device_error(void* stream) {
     }
     return (int)code;
 }
+
+static const char* check_tail(const rd_bn_tail& t);
 
 int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     RD_REQUIRE(p != nullptr, "null params");
@@ -103,6 +106,8 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     RD_REQUIRE(p->wstage_bytes >= max_grp * parts * p->N * 32 && p->wstage_bytes % 128 == 0, "wstage_bytes too small / misaligned");
     RD_REQUIRE(p->epi == 0 || (p->epi == 1 && p->zsrc.ptr && p->ep_scale && p->ep_shift), "epi 1 needs zsrc / scale / shift");
     RD_REQUIRE(p->stats == nullptr || p->stats_stride >= p->nblk * p->N, "stats_stride too small");
+    RD_REQUIRE(p->tail.counter == nullptr || p->stats != nullptr, "a fused BatchNorm finalisation needs the statistics epilogue");
+    { const char* e = check_tail(p->tail); if (e) return fail(RD_EINVAL, e); }
     const long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes;
     RD_REQUIRE(smem <= kMaxSmem, "shared memory budget exceeded");
     const int ntiles = p->tiles_y * p->tiles_x * p->B;

@@ -120,6 +120,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+// Same, with the issue predicate INSIDE the asm block: the C++ side executes it unconditionally (all operands stay in
+// uniform registers, no predicated operand copies) and only the tcgen05.mma itself is guarded.
+__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+
 // Instruction descriptor for kind::f16, bf16 operands, fp32 accumulate (cute::UMMA::InstrDescriptor):
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
@@ -186,6 +199,45 @@ struct FastDiv {
     __device__ __forceinline__ explicit FastDiv(uint32_t d_) : m(d_ > 1 ? 0xFFFFFFFFu / d_ + 1u : 0u), d(d_) {}
     __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
 };
+
+// ---------------------------------------------------------------- fused BatchNorm finalisation (rd_bn_tail)
+// Executed by every thread of the LAST block of the statistics-producing kernel (after the ticket); the fp64 sums
+// were accumulated with L2 atomics by all blocks, hence the .cg loads.
+template <typename TAIL>
+__device__ __forceinline__ void bn_tail_run(const TAIL& t, int tid, int nthreads) {
+    for (int j = 0; j < t.njobs; ++j) {
+        const auto& J = t.job[j];
+        if (J.kind == 1) {
+            if (tid == 0 && J.nbt) *J.nbt += 1;
+            for (int c = tid; c < J.C; c += nthreads) {
+                const double m = __ldcg(J.sum_a + c) / J.count;
+                double var = __ldcg(J.sum_b + c) / J.count - m * m;
+                if (var < 0.0) var = 0.0;
+                const float mean = (float)m;
+                const float invstd = (float)(1.0 / sqrt(var + (double)J.eps));
+                const double unbiased = J.count > 1.0 ? var * J.count / (J.count - 1.0) : var;
+                J.running_mean[c] = (1.f - J.momentum) * J.running_mean[c] + J.momentum * mean;
+                J.running_var[c] = (1.f - J.momentum) * J.running_var[c] + J.momentum * (float)unbiased;
+                const float sc = J.gamma[c] * invstd;
+                J.v0[c] = sc;
+                J.v1[c] = J.beta[c] - mean * sc;
+                J.v2[c] = mean;
+                J.v3[c] = invstd;
+            }
+        } else if (J.kind == 2) {
+            for (int c = tid; c < J.C; c += nthreads) {
+                const double sg = __ldcg(J.sum_a + c), sgz = __ldcg(J.sum_b + c);
+                const double mu = J.v0[c], r = J.v1[c], g = J.gamma[c];
+                const double dg = r * (sgz - mu * sg);
+                J.v2[c] += (float)dg;
+                J.v3[c] += (float)sg;
+                J.cA[c] = (float)(g * r);
+                J.cB[c] = (float)(-g * r * r * dg / J.count);
+                J.cC[c] = (float)(-g * r * sg / J.count + g * r * r * mu * dg / J.count);
+            }
+        }
+    }
+}
 
 // Activation storage abstraction: bf16 (throughput mode) or fp32 (parity mode).
 template <typename T> struct Act;

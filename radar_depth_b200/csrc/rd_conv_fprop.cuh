@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWarpMma = 4 + kFpropLoaderWarps, kWarpW = kWarpMma + 1;
+    // dbg_flags & 8: the six counters become a timeline (cycles since kernel entry): prologue done, loaders done,
+    // first operand stage consumed, last UMMA committed, first accumulator ready, epilogue done
+    const bool tl_mode = p.dbg && (p.dbg_flags & 8);
+    const long long t_entry = p.dbg ? clock64() : 0;
     const int nb = blockIdx.y;                       // N block
     constexpr int PARTS = (SPLIT == 3) ? 2 : 1;
     const int ncblk = p.Cin >> 4;
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
         ts.prepare();
+        if (tl_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -175,8 +180,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 st.advance();
                 if (p.dbg && warp == 4 && lane == 0) {
                     const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                    p.dbg[0 * ncta + cta] += t1_ - t0_;
-                    p.dbg[1 * ncta + cta] += clock64() - t1_;
+                    if (tl_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry;
+                    else { p.dbg[0 * ncta + cta] += t1_ - t0_; p.dbg[1 * ncta + cta] += clock64() - t1_; }
                 }
             }
         }
@@ -216,6 +221,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const uint32_t tap_bytes = (uint32_t)PARTS * p.N * 32u;
             const uint32_t a_units = PS;                         // chunk stride in 16-byte units
             const uint32_t tap_units = tap_bytes >> 4;
+            const uint32_t do_issue = (leader && !(p.dbg_flags & 1)) ? 1u : 0u;
+            const int mbn = p.MB * p.N;
             uint32_t tile_iter = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
                 const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
@@ -231,7 +238,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     fence_proxy_async_smem();      // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
                     tc_fence_after();
                     const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), a_lbo, 128);
+                    // Tap data comes from the (uniform) kernel parameter bank; the values of tap t+1 are fetched while
+                    // the UMMAs of tap t are being issued, so the indexed constant loads are off the issue path.
                     int t = 0;
+                    uint32_t nx_a = (uint32_t)p.taps[0].a_shift, nx_d = (uint32_t)(p.taps[0].phase * mbn), nx_f = (uint32_t)p.taps[0].first;
                     for (int g = 0; g < p.ngroups; ++g) {
                         const long long t2_ = p.dbg ? clock64() : 0;
                         mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
@@ -239,19 +249,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                         tc_fence_after();
                         uint64_t db = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), b_lbo, 128);
                         const int gn = p.grp_n[g];
-                        for (int tl = 0; tl < gn; ++tl, ++t, db += tap_units) {
-                            // tap data straight from the (uniform) kernel parameter bank: no LDS -> R2UR per UMMA
-                            uint64_t da = da0 + (uint32_t)p.taps[t].a_shift;
-                            uint32_t d = d_tile + (uint32_t)(p.taps[t].phase * p.MB * p.N);
-                            const uint32_t acc = (c == 0 && p.taps[t].first) ? 0u : 1u;
+                        for (int tl = 0; tl < gn; ++tl, db += tap_units) {
+                            uint64_t da = da0 + nx_a;
+                            uint32_t d = d_tile + nx_d;
+                            const uint32_t acc = (c == 0 && nx_f) ? 0u : 1u;
+                            t = (t + 1 < p.ntaps) ? t + 1 : 0;
+                            nx_a = (uint32_t)p.taps[t].a_shift; nx_d = (uint32_t)(p.taps[t].phase * mbn); nx_f = (uint32_t)p.taps[t].first;
 #pragma unroll 4
                             for (int mb = 0; mb < p.MB; ++mb, da += 128, d += (uint32_t)p.N) {
-                                if (leader && !(p.dbg_flags & 1)) {
-                                    umma_bf16(d, da, db, idesc, acc);
-                                    if (SPLIT == 3) {
-                                        umma_bf16(d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
-                                        umma_bf16(d, da + 2u * a_units, db, idesc, 1u);
-                                    }
+                                umma_bf16_if(do_issue, d, da, db, idesc, acc);
+                                if (SPLIT == 3) {
+                                    umma_bf16_if(do_issue, d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
+                                    umma_bf16_if(do_issue, d, da + 2u * a_units, db, idesc, 1u);
                                 }
                             }
                         }
@@ -263,8 +272,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     si.advance();
                     if (p.dbg && lane == 0) {
                         const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                        p.dbg[2 * ncta + cta] += (t1_ - t0_) + tw_;
-                        p.dbg[3 * ncta + cta] += clock64() - t1_ - tw_;
+                        if (tl_mode) { if (tile_iter == 0 && c == 0) p.dbg[2 * ncta + cta] = t1_ - t_entry; p.dbg[3 * ncta + cta] = clock64() - t_entry; }
+                        else { p.dbg[2 * ncta + cta] += (t1_ - t0_) + tw_; p.dbg[3 * ncta + cta] += clock64() - t1_ - tw_; }
                     }
                 }
                 if (leader) umma_commit(&tmem_full[ab]);
@@ -351,8 +360,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             if (lane == 0) mbar_arrive(&tmem_empty[ab]);
             if (p.dbg && warp == 0 && lane == 0) {
                 const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                p.dbg[4 * ncta + cta] += t1_ - t0_;
-                p.dbg[5 * ncta + cta] += clock64() - t1_;
+                if (tl_mode) { if (tile_iter == 0) p.dbg[4 * ncta + cta] = t1_ - t_entry; p.dbg[5 * ncta + cta] = clock64() - t_entry; }
+                else { p.dbg[4 * ncta + cta] += t1_ - t0_; p.dbg[5 * ncta + cta] += clock64() - t1_; }
             }
         }
         if (want_stats) {
@@ -360,6 +369,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             for (int i = tid; i < p.N; i += 128) {
                 atomicAdd(&p.stats[nb * p.N + i], (double)stats_s[i]);
                 atomicAdd(&p.stats[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
+            }
+            if (p.tail.counter) {
+                // last CTA to get here finalises the BatchNorm(s) fed by these statistics (rd_bn_tail)
+                __threadfence();
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (tid == 0) tmem_slot[1] = (atomicAdd(p.tail.counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1u : 0u;
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (tmem_slot[1]) {
+                    __threadfence();
+                    bn_tail_run(p.tail, tid, 128);
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
             }
         }
     }

@@ -4,8 +4,24 @@
 // per thread per access; reductions go warp -> shared -> one fp64 atomic per channel per block.
 #pragma once
 #include "rd_common.cuh"
+#include "../../include/radar_depth_b200.h"
 
 namespace rd {
+
+// Ticket + fused BatchNorm finalisation for the channel-reducing kernels: call after the block's statistics atomics
+// with ALL threads of the block.
+__device__ __forceinline__ void block_bn_tail(const rd_bn_tail& t) {
+    if (t.counter == nullptr) return;
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(t.counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        bn_tail_run(t, (int)threadIdx.x, (int)blockDim.x);
+    }
+}
 
 struct VView { void* ptr; int pitch; int coff; };   // same as rd_view, device-side
 
@@ -105,17 +121,39 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
 // NA accumulators per channel; smem partials then one fp64 atomic per channel per block.
 template <int NA>
 __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, int C, float* red_s, double* const* outs) {
-    // red_s: [NA][C] floats, zeroed here
-    for (int i = threadIdx.x; i < NA * C; i += blockDim.x) red_s[i] = 0.f;
+    // red_s: [copies][NA][C] floats (zeroed here).  With fewer than 32 channel groups many threads of a warp own the
+    // same group: lanes are first combined with shuffles (power-of-two group counts) and every warp gets a private
+    // copy, so that at most a handful of shared-memory atomics ever collide on one address.
+    const int groups = C >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const bool priv = groups < 32;
+    const int copies = priv ? nwarps : 1;
+    for (int i = threadIdx.x; i < copies * NA * C; i += blockDim.x) red_s[i] = 0.f;
     __syncthreads();
+    bool writer = true;
+    if (priv && (groups & (groups - 1)) == 0 && (blockDim.x & 31) == 0) {
+        // thread t owns group t % groups = lane % groups: xor-shuffles over the lane bits above log2(groups)
+        for (int o = 16; o >= groups; o >>= 1) {
 #pragma unroll
-    for (int a = 0; a < NA; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(&red_s[a * C + cg * 8 + k], acc[a][k]);
+                for (int k = 0; k < 8; ++k) acc[a][k] += __shfl_xor_sync(0xffffffffu, acc[a][k], o);
+        }
+        writer = lane < groups;
+    }
+    float* mine = red_s + (priv ? warp * NA * C : 0);
+    if (writer) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&mine[a * C + cg * 8 + k], acc[a][k]);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < NA * C; i += blockDim.x) {
         const int a = i / C, c = i - a * C;
-        atomicAdd(outs[a] + c, (double)red_s[i]);
+        float s = 0.f;
+        for (int w = 0; w < copies; ++w) s += red_s[w * NA * C + i];
+        atomicAdd(outs[a] + c, (double)s);
     }
 }
 
@@ -150,7 +188,7 @@ __global__ void bn_add_act_kernel(VView z, const float* __restrict__ sc, const f
 // Writes g (may alias dout).  Autograd of the residual join + ReLU.
 template <typename T>
 __global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
-                                double* sum_g, double* sum_gz, double* sum_gzid) {
+                                double* sum_g, double* sum_gz, double* sum_gzid, const __grid_constant__ rd_bn_tail tail) {
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -183,6 +221,7 @@ __global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VVie
     double* outs[3] = {sum_g, sum_gz, sum_gzid};
     if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs);
     else block_channel_reduce<2>(acc, cg, C, red_s, outs);
+    block_bn_tail(tail);
 }
 
 // bn_bwd_apply: dz = A*g + Bz*z + Cc (per channel).  dz may alias g.
@@ -288,7 +327,7 @@ template <typename T>
 __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restrict__ amax, VView z,
                                    const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
                                    int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
-                                   double* sum_gz) {
+                                   double* sum_gz, const __grid_constant__ rd_bn_tail tail) {
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -349,6 +388,7 @@ __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restri
     }
     double* outs[2] = {sum_g, sum_gz};
     block_channel_reduce<2>(acc, cg, C, red_s, outs);
+    block_bn_tail(tail);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -386,55 +426,60 @@ __global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16]
 }
 
 // head_conv_bwd: dx[p][c] = sum_tap dc3[p - tap] * w[c][tap];  dw[c][tap] += sum_p dc3[p] * x[p + tap][c].
+// One thread per (pixel, 8-channel half): 72 weight-gradient accumulators per thread instead of 144 keeps the kernel
+// out of the register cliff (it is a pure bandwidth kernel: 16 B in, 16 B out per thread and iteration).
 template <typename T>
-__global__ void head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w, int B, int H, int W,
-                                     VView dx, float* dw /*[144]*/) {
+__global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w,
+                                                             int B, int H, int W, VView dx, float* dw /*[144]*/) {
     __shared__ float ws[144];
     __shared__ float dws[144];
     for (int i = threadIdx.x; i < 144; i += blockDim.x) { ws[i] = w[i]; dws[i] = 0.f; }
     __syncthreads();
-    const size_t total = (size_t)B * H * W;
-    float wacc[9][16];
+    const uint32_t total = (uint32_t)B * H * W * 2u;
+    const int half = threadIdx.x & 1;                  // blockDim and the grid stride are even: fixed per thread
+    const float* wh = ws + half * 72;                  // this half's [8][9] weights (two-address broadcast reads)
+    float wacc[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) wacc[t][c] = 0.f;
+        for (int c = 0; c < 8; ++c) wacc[t][c] = 0.f;
     const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
-    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < (uint32_t)total; pix += gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = i >> 1;
         const uint32_t prow = fdw.div(pix);
         const int ox = (int)(pix - prow * W);
         const int b = (int)fdh.div(prow);
         const int oy = (int)(prow - (uint32_t)b * H);
-        // data gradient at this pixel (gather form) and weight gradient (this pixel's x against shifted dc3)
-        float xv[16], dxa[16];
-        Act<T>::load8(vptr<T>(x, pix, 0), xv);
-        Act<T>::load8(vptr<T>(x, pix, 8), xv + 8);
+        float xv[8], dxa[8];
+        Act<T>::load8(vptr<T>(x, pix, half * 8), xv);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dxa[c] = 0.f;
+        for (int c = 0; c < 8; ++c) dxa[c] = 0.f;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
             for (int dx_ = 0; dx_ < 3; ++dx_) {
                 // output pixel q = p - (dy-1, dx-1) used input p with tap (dy,dx)
                 const int qy = oy - (dy - 1), qx = ox - (dx_ - 1);
-                if (qy < 0 || qy >= H || qx < 0 || qx >= W) continue;
-                const float d = dc3[((size_t)b * H + qy) * W + qx];
+                const bool ok = qy >= 0 && qy < H && qx >= 0 && qx < W;
+                const float d = ok ? __ldg(dc3 + ((size_t)b * H + qy) * W + qx) : 0.f;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    dxa[c] = fmaf(d, ws[c * 9 + dy * 3 + dx_], dxa[c]);
+                for (int c = 0; c < 8; ++c) {
+                    dxa[c] = fmaf(d, wh[c * 9 + dy * 3 + dx_], dxa[c]);
                     wacc[dy * 3 + dx_][c] = fmaf(d, xv[c], wacc[dy * 3 + dx_][c]);
                 }
             }
         }
-        Act<T>::store8(vptr_w<T>(dx, pix, 0), dxa);
-        Act<T>::store8(vptr_w<T>(dx, pix, 8), dxa + 8);
+        Act<T>::store8(vptr_w<T>(dx, pix, half * 8), dxa);
     }
+    // lanes of equal parity own the same channel half: xor-shuffles over lane bits 1..4
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float s = warp_sum(wacc[t][c]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&dws[c * 9 + t], s);
+        for (int c = 0; c < 8; ++c) {
+            float s = wacc[t][c];
+#pragma unroll
+            for (int o = 16; o >= 2; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) < 2) atomicAdd(&dws[(half * 8 + c) * 9 + t], s);
         }
     __syncthreads();
     for (int i = threadIdx.x; i < 144; i += blockDim.x) atomicAdd(&dw[i], dws[i]);

@@ -203,7 +203,7 @@ class LatefusionEngine:
         self._pending = []                 # launches whose weight / dw pointers are patched after arenas exist
 
         def emit_conv(prog, rec, which, src: View, dst: View, ld=None, epi=0, addend=None, zsrc=None, ep=None,
-                      stats=None, tag=""):
+                      stats=None, tag="", tail=None):
             plan = rec["fplan"] if which == "f" else rec["dplan"]
             p = type(plan.params).from_buffer_copy(plan.params)
             p.src, p.dst = src, dst
@@ -218,6 +218,9 @@ class LatefusionEngine:
                 p.ep_scale, p.ep_shift, p.ep_slope = _p(ep[0]), _p(ep[1]), float(ep[2])
             if stats is not None:
                 p.stats, p.stats_stride = _p(stats), stats.shape[1]
+            if tail is not None:
+                assert stats is not None
+                p.tail = tail
             self._pending.append((p, "wpk", rec["f_off"] if which == "f" else rec["d_off"]))
             self._keep.append(p)
             prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),)))
@@ -239,33 +242,62 @@ class LatefusionEngine:
             m = self.module.get_submodule(name)
             return m.running_mean, m.running_var, m.num_batches_tracked
 
-        def emit_bn_fwd(grp: BNGroup, count: float):
+        # BatchNorm finalisation is fused into the tail of the kernel that produces its statistics (rd_bn_tail: the
+        # last CTA turns the fp64 sums into scale/shift or into the backward coefficients).  Only the eval-mode
+        # forward, which has no statistics pass, still uses the stand-alone rd_bn_finalize launch.
+        def new_tail(jobs) -> "_lib.BnTail":
+            t = _lib.BnTail()
+            assert 1 <= len(jobs) <= _lib.RD_MAX_BN_JOBS
+            t.counter = _p(self.alloc_stats(1))            # 8-byte slot of the fp64 arena, zeroed with the statistics
+            t.njobs = len(jobs)
+            for i, j in enumerate(jobs):
+                t.job[i] = j
+            self._keep.append(t)
+            return t
+
+        def fwd_jobs(grp: BNGroup, count: float):
+            jobs = []
+            for (name, c0, Cn) in grp.members:
+                rm, rv, nbt = bn_buffers(name)
+                j = _lib.BnJob()
+                j.kind, j.C, j.count = 1, Cn, float(count)
+                j.sum_a, j.sum_b = _p(grp.fstats[0], c0), _p(grp.fstats[1], c0)
+                j.gamma, j.beta = _p(self.flat, o[name + ".weight"]), _p(self.flat, o[name + ".bias"])
+                j.running_mean, j.running_var, j.nbt = _p(rm), _p(rv), _p(nbt)
+                j.v0, j.v1, j.v2, j.v3 = _p(grp.scale, c0), _p(grp.shift, c0), _p(grp.mean, c0), _p(grp.invstd, c0)
+                j.momentum, j.eps = BN_MOMENTUM, BN_EPS
+                jobs.append(j)
+            return jobs
+
+        def emit_bn_eval(grp: BNGroup, count: float):
             for (name, c0, Cn) in grp.members:
                 rm, rv, nbt = bn_buffers(name)
                 go, bo = o[name + ".weight"], o[name + ".bias"]
-                common = (_p(self.flat, go), _p(self.flat, bo), _p(rm), _p(rv))
-                tail = (_p(grp.scale, c0), _p(grp.shift, c0), _p(grp.mean, c0), _p(grp.invstd, c0))
-                self.fwd.append(Launch("bn_fin:" + name, lib.rd_bn_finalize,
-                                       (_p(grp.fstats[0], c0), _p(grp.fstats[1], c0), float(count)) + common +
-                                       (_p(nbt), Cn, 1, BN_MOMENTUM, BN_EPS) + tail))
                 self.fwd_eval.append(Launch("bn_fin_eval:" + name, lib.rd_bn_finalize,
-                                            (None, None, float(count)) + common + (None, Cn, 0, BN_MOMENTUM, BN_EPS) + tail))
+                                            (None, None, float(count), _p(self.flat, go), _p(self.flat, bo), _p(rm), _p(rv),
+                                             None, Cn, 0, BN_MOMENTUM, BN_EPS, _p(grp.scale, c0), _p(grp.shift, c0),
+                                             _p(grp.mean, c0), _p(grp.invstd, c0))))
 
-        def emit_bn_bwd(grp: BNGroup, midx: int, sum_g_ptr: int, sum_gz_ptr: int, count: float):
+        def bwd_job(grp: BNGroup, midx: int, sum_g_ptr: int, sum_gz_ptr: int, count: float):
             name, c0, Cn = grp.members[midx]
             go, bo = o[name + ".weight"], o[name + ".bias"]
-            self.bwd.append(Launch("bn_bwd_fin:" + name, lib.rd_bn_bwd_finalize,
-                                   (sum_g_ptr, sum_gz_ptr, float(count), _p(self.flat, go), _p(grp.mean, c0),
-                                    _p(grp.invstd, c0), Cn, 1, _p(self.gflat, go), _p(self.gflat, bo),
-                                    _p(grp.cA, c0), _p(grp.cB, c0), _p(grp.cC, c0))))
+            j = _lib.BnJob()
+            j.kind, j.C, j.count = 2, Cn, float(count)
+            j.sum_a, j.sum_b = sum_g_ptr, sum_gz_ptr
+            j.gamma = _p(self.flat, go)
+            j.v0, j.v1, j.v2, j.v3 = _p(grp.mean, c0), _p(grp.invstd, c0), _p(self.gflat, go), _p(self.gflat, bo)
+            j.cA, j.cB, j.cC = _p(grp.cA, c0), _p(grp.cB, c0), _p(grp.cC, c0)
+            return j
 
         def both(launch: Launch):          # identical in train and eval forward
             self.fwd.append(launch)
             self.fwd_eval.append(launch)
 
-        def emit_conv_fwd(rec, src, dst, ld, stats, count_grp: Optional[BNGroup]):
-            emit_conv(self.fwd, rec, "f", src, dst, ld=ld, stats=stats)
+        def emit_conv_fwd(rec, src, dst, ld, grp: BNGroup, count: float):
+            """conv + (training) statistics epilogue + fused BatchNorm finalisation; eval: conv, then running-stat affine."""
+            emit_conv(self.fwd, rec, "f", src, dst, ld=ld, stats=grp.fstats, tail=new_tail(fwd_jobs(grp, count)))
             emit_conv(self.fwd_eval, rec, "f", src, dst, ld=ld, stats=None, tag="(eval)")
+            emit_bn_eval(grp, count)
 
         # ============================== buffers + forward program ==============================
         self.x_in = torch.zeros(B, self.in_channels, H, W, dtype=torch.float32, device=self.device)
@@ -278,8 +310,7 @@ class LatefusionEngine:
         z_stem = self.act(B, H2, W2, 80)
         g_stem = BNGroup(self, [("bn1", 0, 64), ("bn1_depth", 64, 16)])
         n_stem = float(B * H2 * W2)
-        emit_conv_fwd(stem, _v(xs), _v(z_stem), None, g_stem.fstats, g_stem)
-        emit_bn_fwd(g_stem, n_stem)
+        emit_conv_fwd(stem, _v(xs), _v(z_stem), None, g_stem, n_stem)
         p_rgb, p_d = self.act(B, H4, W4, 64), self.act(B, H4, W4, 16)
         amax = self.hold(torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device))
         both(Launch("maxpool", lib.rd_maxpool_fwd,
@@ -313,16 +344,13 @@ class LatefusionEngine:
                     z1, z2 = self.act(B, ho, wo, cw), self.act(B, ho, wo, cw)
                     b1 = BNGroup(self, [(pfx + ".bn1", 0, cw)])
                     b2 = BNGroup(self, [(pfx + ".bn2", 0, cw)])
-                    emit_conv_fwd(c1, _v(x_cur), _v(z1), None, b1.fstats, b1)
-                    emit_bn_fwd(b1, n)
-                    emit_conv_fwd(c2, _v(z1), _v(z2), (b1.scale, b1.shift, 0.0), b2.fstats, b2)
-                    emit_bn_fwd(b2, n)
+                    emit_conv_fwd(c1, _v(x_cur), _v(z1), None, b1, n)
+                    emit_conv_fwd(c2, _v(z1), _v(z2), (b1.scale, b1.shift, 0.0), b2, n)
                     zd, bd = None, None
                     if ds is not None:
                         zd = self.act(B, ho, wo, cw)
                         bd = BNGroup(self, [(pfx + ".downsample.1", 0, cw)])
-                        emit_conv_fwd(ds, _v(x_cur), _v(zd), None, bd.fstats, bd)
-                        emit_bn_fwd(bd, n)
+                        emit_conv_fwd(ds, _v(x_cur), _v(zd), None, bd, n)
                     last = (li == 4 and bi == 1)
                     if last:
                         out_t, out_v = concat, _v(concat, cat_off)
@@ -344,13 +372,11 @@ class LatefusionEngine:
         cf = reg("conv_fusion", cp.gconv_standard(o["conv_fusion.weight"], 512, 640, 1, 1, 0), (h32, w32), (h32, w32))
         zf = self.act(B, h32, w32, 512)
         bf = BNGroup(self, [("bn_fusion", 0, 512)])
-        emit_conv_fwd(cf, _v(concat), _v(zf), None, bf.fstats, bf)
-        emit_bn_fwd(bf, nf)
+        emit_conv_fwd(cf, _v(concat), _v(zf), None, bf, nf)
         cc2 = reg("conv2", cp.gconv_standard(o["conv2.weight"], 256, 512, 1, 1, 0), (h32, w32), (h32, w32))
         zc2 = self.act(B, h32, w32, 256)
         bc2 = BNGroup(self, [("bn2", 0, 256)])
-        emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2.fstats, bc2)
-        emit_bn_fwd(bc2, nf)
+        emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2, nf)
 
         # ---- decoder (UpProj x4)
         dec = []
@@ -367,10 +393,8 @@ class LatefusionEngine:
             gcat = BNGroup(self, [(pfx + ".upper_branch.batchnorm1", 0, co), (pfx + ".bottom_branch.batchnorm", co, co)])
             bu2 = BNGroup(self, [(pfx + ".upper_branch.batchnorm2", 0, co)])
             n = float(B * ho * wo)
-            emit_conv_fwd(up, _v(d_in_t), _v(zcat), d_in_ld, gcat.fstats, gcat)
-            emit_bn_fwd(gcat, n)
-            emit_conv_fwd(c3, _v(zcat, 0), _v(zu2), (gcat.scale, gcat.shift, 0.0), bu2.fstats, bu2)
-            emit_bn_fwd(bu2, n)
+            emit_conv_fwd(up, _v(d_in_t), _v(zcat), d_in_ld, gcat, n)
+            emit_conv_fwd(c3, _v(zcat, 0), _v(zu2), (gcat.scale, gcat.shift, 0.0), bu2, n)
             both(Launch("join:" + pfx, lib.rd_bn_add_act,
                         (_v(zu2), _p(bu2.scale), _p(bu2.shift), _v(zcat, co), _p(gcat.scale, co), _p(gcat.shift, co),
                          _v(out_t), int(B * ho * wo), co, 0.0, act)))
@@ -405,19 +429,18 @@ class LatefusionEngine:
             g_t = self.act(B, ho, wo, co)
             dzcat = self.act(B, ho, wo, 2 * co)
             dzu2 = self.act(B, ho, wo, co)
+            tj = new_tail([bwd_job(bu2, 0, _p(bu2.bstats[0]), _p(bu2.bstats[1]), n),
+                           bwd_job(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)])
             bw.append(Launch("join_bwd:" + L["pfx"], lib.rd_join_bwd,
                              (_v(d_out), _v(L["out"]), _v(L["zu2"]), _v(L["zcat"], co), _v(g_t), npix, co, 0.0,
-                              _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), act)))
-            emit_bn_bwd(bu2, 0, _p(bu2.bstats[0]), _p(bu2.bstats[1]), n)
-            emit_bn_bwd(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)
+                              _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), C.byref(tj), act)))
             bw.append(Launch("bn_bwd_apply:bottom", lib.rd_bn_bwd_apply,
                              (_v(g_t), _v(L["zcat"], co), _v(dzcat, co), _p(gcat.cA, co), _p(gcat.cB, co), _p(gcat.cC, co), npix, co, act)))
             bw.append(Launch("bn_bwd_apply:u2", lib.rd_bn_bwd_apply,
                              (_v(g_t), _v(L["zu2"]), _v(dzu2), _p(bu2.cA), _p(bu2.cB), _p(bu2.cC), npix, co, act)))
             emit_wgrad(bw, L["c3"], _v(dzu2), _v(L["zcat"], 0), ld=(gcat.scale, gcat.shift, 0.0))
             emit_conv(bw, L["c3"], "d", _v(dzu2), _v(dzcat, 0), epi=1, zsrc=_v(L["zcat"], 0), ep=(gcat.scale, gcat.shift, 0.0),
-                      stats=gcat.bstats[:2])
-            emit_bn_bwd(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)
+                      stats=gcat.bstats[:2], tail=new_tail([bwd_job(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)]))
             bw.append(Launch("bn_bwd_apply:u1", lib.rd_bn_bwd_apply,
                              (_v(dzcat, 0), _v(L["zcat"], 0), _v(dzcat, 0), _p(gcat.cA), _p(gcat.cB), _p(gcat.cC), npix, co, act)))
             emit_wgrad(bw, L["up"], _v(dzcat), _v(L["x_in"]), ld=L["x_ld"])
@@ -429,15 +452,14 @@ class LatefusionEngine:
             else:
                 g_c2 = self.act(B, h32, w32, 256)
                 emit_conv(bw, L["up"], "d", _v(dzcat), _v(g_c2), epi=1, zsrc=_v(zc2), ep=(bc2.scale, bc2.shift, 1.0),
-                          stats=bc2.bstats[:2])
+                          stats=bc2.bstats[:2], tail=new_tail([bwd_job(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)]))
         npf = int(B * h32 * w32)
-        emit_bn_bwd(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)
         bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
                          (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act)))
         emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
         g_f = self.act(B, h32, w32, 512)
-        emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2])
-        emit_bn_bwd(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)
+        emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2],
+                  tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)]))
         bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
                          (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act)))
         emit_wgrad(bw, cf, _v(g_f), _v(concat))
@@ -451,22 +473,23 @@ class LatefusionEngine:
                 npix = int(B * ho * wo)
                 b1, b2, bd = Bk["b1"], Bk["b2"], Bk["bd"]
                 g_t, dz2, g1 = self.act(B, ho, wo, cw), self.act(B, ho, wo, cw), self.act(B, ho, wo, cw)
+                jobs = [bwd_job(b2, 0, _p(b2.bstats[0]), _p(b2.bstats[1]), n)]
+                if bd:
+                    jobs.append(bwd_job(bd, 0, _p(b2.bstats[0]), _p(b2.bstats[2]), n))
+                tj = new_tail(jobs)
                 bw.append(Launch("join_bwd:" + Bk["pfx"], lib.rd_join_bwd,
                                  (d_out_v, Bk["out_v"], _v(Bk["z2"]), _v(Bk["zd"]) if bd else NULLV, _v(g_t), npix, cw, 0.0,
-                                  _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), act)))
-                emit_bn_bwd(b2, 0, _p(b2.bstats[0]), _p(b2.bstats[1]), n)
+                                  _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), C.byref(tj), act)))
                 bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
                                  (_v(g_t), _v(Bk["z2"]), _v(dz2), _p(b2.cA), _p(b2.cB), _p(b2.cC), npix, cw, act)))
                 dzd = None
                 if bd:
                     dzd = self.act(B, ho, wo, cw)
-                    emit_bn_bwd(bd, 0, _p(b2.bstats[0]), _p(b2.bstats[2]), n)
                     bw.append(Launch("bn_bwd_apply:ds", lib.rd_bn_bwd_apply,
                                      (_v(g_t), _v(Bk["zd"]), _v(dzd), _p(bd.cA), _p(bd.cB), _p(bd.cC), npix, cw, act)))
                 emit_wgrad(bw, Bk["c2"], _v(dz2), _v(Bk["z1"]), ld=(b1.scale, b1.shift, 0.0))
                 emit_conv(bw, Bk["c2"], "d", _v(dz2), _v(g1), epi=1, zsrc=_v(Bk["z1"]), ep=(b1.scale, b1.shift, 0.0),
-                          stats=b1.bstats[:2])
-                emit_bn_bwd(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)
+                          stats=b1.bstats[:2], tail=new_tail([bwd_job(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)]))
                 bw.append(Launch("bn_bwd_apply:bn1", lib.rd_bn_bwd_apply,
                                  (_v(g1), _v(Bk["z1"]), _v(g1), _p(b1.cA), _p(b1.cB), _p(b1.cC), npix, cw, act)))
                 x_in_v = _v(Bk["x_in"])
@@ -483,11 +506,11 @@ class LatefusionEngine:
             dpool.append(d_out_v)
 
         gz_stem = self.act(B, H2, W2, 80)
+        tj = new_tail([bwd_job(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem),
+                       bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)])
         bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
                          (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
-                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), act)))
-        emit_bn_bwd(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem)
-        emit_bn_bwd(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)
+                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act)))
         bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
                          (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act)))
         emit_wgrad(bw, stem, _v(gz_stem), _v(xs))

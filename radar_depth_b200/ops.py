@@ -44,7 +44,7 @@ def pack_weights(wflat: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Ten
 
 def conv_fprop(plan, src: View, wpk, dst: View, ld=None, epi: int = 0, addend: Optional[View] = None,
                zsrc: Optional[View] = None, ep=None, stats: Optional[Tuple[torch.Tensor, int]] = None,
-               max_ctas: Optional[int] = None, dbg=None, dbg_flags: int = 0):
+               max_ctas: Optional[int] = None, dbg=None, dbg_flags: int = 0, tail=None):
     """Launch one tcgen05 convolution program.  ``wpk``: packed weights (tensor or raw pointer);
     ``ld`` = (scale, shift, slope) fuses the producer's BN+activation on load; ``ep`` likewise for the
     activation-gradient epilogue (epi=1); ``stats`` = (fp64 tensor [2, stride], stride)."""
@@ -71,6 +71,8 @@ def conv_fprop(plan, src: View, wpk, dst: View, ld=None, epi: int = 0, addend: O
         p.stats, p.stats_stride = None, 0
     if max_ctas is not None:
         p.max_ctas = max_ctas
+    if tail is not None:
+        p.tail = tail            # _lib.BnTail: BatchNorm finalisation fused into the kernel tail
     _lib.call("rd_conv_fprop", C.byref(p), stream_ptr())
 
 

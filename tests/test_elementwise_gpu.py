@@ -110,11 +110,26 @@ def test_residual_join_forward_backward_vs_autograd(name, act, td, with_ds):
     torch.testing.assert_close(out.float(), nhwc(out_ref.detach()), **tol(act))
     g = torch.empty_like(z)
     st = torch.zeros(3, C, device="cuda", dtype=torch.float64)
+    # the BatchNorm-backward finalisation rides in the tail of join_bwd (rd_bn_tail, last block): it must give exactly
+    # what the stand-alone rd_bn_bwd_finalize computes from the same statistics
+    import ctypes
+    fused = torch.zeros(5, C, device="cuda")                  # dgamma dbeta A B C
+    counter = torch.zeros(1, device="cuda", dtype=torch.float64)
+    tail = _lib.BnTail()
+    tail.counter, tail.njobs = ptr(counter), 1
+    j = tail.job[0]
+    j.kind, j.C, j.count = 2, C, float(n)
+    j.sum_a, j.sum_b, j.gamma = ptr(st[0]), ptr(st[1]), ptr(bn_a.weight.data)
+    j.v0, j.v1, j.v2, j.v3 = ptr(va[2]), ptr(va[3]), ptr(fused[0]), ptr(fused[1])
+    j.cA, j.cB, j.cC = ptr(fused[2]), ptr(fused[3]), ptr(fused[4])
     call("rd_join_bwd", view(dout), view(out), view(z), view(idt) if with_ds else NULLV, view(g), n, C, 0.0, ptr(st[0]), ptr(st[1]),
-         ptr(st[2]), act, stream_ptr())
+         ptr(st[2]), ctypes.byref(tail), act, stream_ptr())
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     call("rd_bn_bwd_finalize", ptr(st[0]), ptr(st[1]), float(n), ptr(bn_a.weight.data), ptr(va[2]), ptr(va[3]), C, 1, ptr(dg), ptr(db),
          ptr(va[4]), ptr(va[5]), ptr(va[6]), stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(fused[0], dg) and torch.equal(fused[1], db)
+    assert torch.equal(fused[2], va[4]) and torch.equal(fused[3], va[5]) and torch.equal(fused[4], va[6])
     dz = torch.empty_like(z)
     call("rd_bn_bwd_apply", view(g), view(z), view(dz), ptr(va[4]), ptr(va[5]), ptr(va[6]), n, C, act, stream_ptr())
     t = dict(rtol=3e-2, atol=3e-2) if act == _lib.RD_BF16 else dict(rtol=1e-4, atol=1e-5)
@@ -176,7 +191,7 @@ def test_maxpool_forward_backward_vs_autograd(name, act, td, H, W, ties):
     g = torch.empty(B, H, W, C, device="cuda", dtype=td)
     st = torch.zeros(2, C, device="cuda", dtype=torch.float64)
     call("rd_maxpool_bwd", view(dpa), view(dpb), ptr(amax), view(z), ptr(sc), ptr(sh), B, H, W, C, split, 0.0, 0.2, Ho, Wo, view(g),
-         ptr(st[0]), ptr(st[1]), act, stream_ptr())
+         ptr(st[0]), ptr(st[1]), None, act, stream_ptr())
     gref = nhwc(zc.grad).cuda() / sc          # gradient w.r.t. the BN output's pre-activation y... undo the affine
     torch.testing.assert_close(g.float(), gref, **(dict(rtol=2e-2, atol=2e-2) if act == _lib.RD_BF16 else dict(rtol=1e-5, atol=1e-5)))
     # the statistics are accumulated from the fp32 values before the store rounds them (bf16: ~2^-9 per element)

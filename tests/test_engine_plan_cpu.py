@@ -16,8 +16,8 @@ def test_engine_plans_every_program(cin, hw, b, act):
     eng = LatefusionEngine(m, cin, hw, act)
     eng.adopt("cpu")
     eng.configure(b, *hw)
-    assert len(eng.fwd) == 128 and len(eng.fwd_eval) == 128
-    assert len(eng.bwd) == (229 if cin > 4 else 228)
+    assert len(eng.fwd) == 74 and len(eng.fwd_eval) == 128     # training: BatchNorm finalisation rides in the conv tails
+    assert len(eng.bwd) == (175 if cin > 4 else 174)
     names = [L.name for L in eng.fwd]
     assert names[0] == "pack_weights" and names[-1] == "bilinear"
     assert sum(n.startswith("conv_f:") for n in names) == 49          # 55 reference convs: two stems fused (-1), 4x2 5x5s fused (-4), conv3 in the head kernel (-1)

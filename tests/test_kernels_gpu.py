@@ -65,8 +65,32 @@ def test_fprop_and_dgrad(name, mk, src_hw, dst_hw, act):
         wpk = ops.pack_weights(w, torch.from_numpy(plan.pack_idx).cuda())
         out = torch.full((B, d_hw[0], d_hw[1], gg.N), float("nan"), device="cuda", dtype=ops.act_torch_dtype(act))
         stats = torch.zeros(2, gg.N, dtype=torch.float64, device="cuda")
-        ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), stats=(stats, gg.N))
+        # BatchNorm finalisation fused into the kernel tail (last CTA): must equal rd_bn_finalize on the same sums
+        Cn = gg.N
+        gamma, beta = torch.rand(Cn, device="cuda") + 0.5, torch.randn(Cn, device="cuda")
+        rm, rv = torch.randn(Cn, device="cuda"), torch.rand(Cn, device="cuda") + 0.5
+        rm2, rv2 = rm.clone(), rv.clone()
+        nbt, nbt2 = torch.zeros(1, dtype=torch.int64, device="cuda"), torch.zeros(1, dtype=torch.int64, device="cuda")
+        fused, alone = torch.zeros(4, Cn, device="cuda"), torch.zeros(4, Cn, device="cuda")
+        counter = torch.zeros(1, dtype=torch.float64, device="cuda")
+        count = float(B * d_hw[0] * d_hw[1])
+        tail = _lib.BnTail()
+        tail.counter, tail.njobs = counter.data_ptr(), 1
+        j = tail.job[0]
+        j.kind, j.C, j.count, j.momentum, j.eps = 1, Cn, count, 0.1, 1e-5
+        j.sum_a, j.sum_b, j.gamma, j.beta = stats[0].data_ptr(), stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        j.running_mean, j.running_var, j.nbt = rm.data_ptr(), rv.data_ptr(), nbt.data_ptr()
+        j.v0, j.v1, j.v2, j.v3 = (fused[i].data_ptr() for i in range(4))
+        ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), stats=(stats, gg.N), tail=tail)
         assert ops.device_error() == 0
+        _lib.call("rd_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), count, gamma.data_ptr(), beta.data_ptr(),
+                  rm2.data_ptr(), rv2.data_ptr(), nbt2.data_ptr(), Cn, 1, 0.1, 1e-5, *(alone[i].data_ptr() for i in range(4)),
+                  ops.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(fused, alone) and int(nbt) == 1 == int(nbt2), (name, tag)
+        # running statistics: same formula, but the compiler may contract (1-m)*r + m*x differently in the two kernels
+        torch.testing.assert_close(rm, rm2, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(rv, rv2, rtol=1e-6, atol=1e-7)
         wref = w.bfloat16().float() if act == _lib.RD_BF16 else w
         ref = cp.gconv_reference(gg, x.float(), wref, d_hw)
         covered = torch.zeros(gg.OS, gg.OS, dtype=torch.bool)

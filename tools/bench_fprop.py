@@ -38,12 +38,22 @@ for ov in overrides:
         ts = []
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg_flags=fl); e1.record()
+            e0.record()
+            for _r in range(4):      # back to back: the queue hides the host launch latency
+                ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg_flags=fl)
+            e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / 4)
         dbg = torch.zeros(6, ncta, dtype=torch.int64, device="cuda")
         ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg=dbg, dbg_flags=fl)
         torch.cuda.synchronize()
         d = dbg.double().mean(dim=1).cpu().numpy() / 1e3
         ms = statistics.median(ts)
         print(f"   {nm:8s} {ms * 1e3:7.1f} us {flops / ms / 1e9:7.1f} TF | kcyc/CTA loader wait {d[0]:6.1f} fill {d[1]:6.1f} | issuer wait {d[2]:6.1f} issue {d[3]:6.1f} | epi wait {d[4]:6.1f} work {d[5]:6.1f}")
+    dbg = torch.zeros(6, ncta, dtype=torch.int64, device="cuda")
+    ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), ld=ld, stats=(stats, Cout), dbg=dbg, dbg_flags=8)
+    torch.cuda.synchronize()
+    d = dbg.double().mean(dim=1).cpu().numpy() / 1e3
+    dm = dbg.double().max(dim=1).values.cpu().numpy() / 1e3
+    print(f"   timeline kcyc since entry (mean/max over CTAs): prologue {d[0]:.1f}/{dm[0]:.1f} loaders done {d[1]:.1f}/{dm[1]:.1f} first stage consumed {d[2]:.1f}/{dm[2]:.1f} "
+          f"last commit {d[3]:.1f}/{dm[3]:.1f} first acc ready {d[4]:.1f}/{dm[4]:.1f} epilogue done {d[5]:.1f}/{dm[5]:.1f}")

@@ -20,11 +20,11 @@ else:
 x = torch.randn(B, shw[0], shw[1], g.Cx, device="cuda").bfloat16()
 dy = torch.randn(B, dhw[0], dhw[1], g.N, device="cuda").bfloat16()
 flops = 2.0 * B * (dhw[0] // g.OS) * (dhw[1] // g.OS) * len(g.taps) * g.Cx * g.N
-for nc, ks, maxc in itertools.product((32,), (256,), (0,)):
-    if nc > g.Cx or g.Cx % nc:
+for nc, ks, maxc in itertools.product((None,), (None,), (0,)):
+    if nc is not None and (nc > g.Cx or g.Cx % nc):
         continue
     try:
-        plan = cp.plan_wgrad(g, B, shw, dhw, _lib.RD_BF16, ks_target=ks, nc=nc)
+        plan = cp.plan_wgrad(g, B, shw, dhw, _lib.RD_BF16) if nc is None else cp.plan_wgrad(g, B, shw, dhw, _lib.RD_BF16, ks_target=ks, nc=nc)
     except Exception as e:  # noqa
         print(nc, ks, "infeasible", e)
         continue
@@ -60,5 +60,5 @@ for nc, ks, maxc in itertools.product((32,), (256,), (0,)):
         print(f"      {nm}: {e0.elapsed_time(e1) * 1e3:7.1f} us  [loader wait {d2[0]:6.1f} fill {d2[1]:6.1f} | issuer wait {d2[2]:6.1f} issue {d2[3]:6.1f}]")
     print(f"      kcycles/CTA: loader wait {d[0]:7.1f} fill {d[1]:7.1f} | issuer wait {d[2]:7.1f} issue {d[3]:7.1f} | tiles/CTA {tiles_per_cta:.1f}")
     i = plan.info
-    print(f"{name} nc={nc:3d} ks_t={ks:3d} -> KS={i['geo']['KS']:3d} Wl={i['geo']['Wl']:3d} Ht={i['geo']['Ht']:2d} tg={i['tg_size']:2d}x{i['ntg']} NS={i['NS']} "
+    print(f"{name} nc={nc} ks_t={ks} -> KS={i['geo']['KS']:3d} Wl={i['geo']['Wl']:3d} Ht={i['geo']['Ht']:2d} tg={i['tg_size']:2d}x{i['ntg']} NS={i['NS']} "
           f"gx={mc:3d} ctas={mc * plan.params.ncob * plan.params.ncib * plan.params.ntg:4d}  {ms * 1e3:8.1f} us  {flops / ms / 1e9:7.1f} TFLOP/s")

@@ -55,6 +55,9 @@ for name, ms in sorted(rows, key=lambda r: -r[1])[:70]:
     if kind in ("conv_f", "conv_d", "wgrad") and lname in flops:
         tf = f"{flops[lname] / (ms * 1e-3) / 1e12:8.1f} TFLOP/s"
     print(f"{ms:8.4f} ms  {100 * ms / tot:5.1f}%  {name:60s} {tf}")
+import json, os
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(dict(rows=rows, flops=flops), open(f"gpurun_out/layers_all_{prec}_b{b}.json", "w"))
 agg = {}
 for name, ms in rows:
     k = name.split(":")[0]

@@ -21,9 +21,11 @@ for _ in range(2):
 torch.cuda.synchronize()
 eng = m._engine
 st = torch.cuda.current_stream().cuda_stream
+torch.cuda.profiler.start()      # ncu --profile-from-start off: only the replayed launches are captured
 for L in eng.fwd + eng.bwd:
     if any(p == L.name or (p.endswith("*") and L.name.startswith(p[:-1])) for p in pats):
         for _ in range(reps):
             assert L.fn(*L.args, st) == 0
         torch.cuda.synchronize()
         print("replayed", L.name)
+torch.cuda.profiler.stop()
