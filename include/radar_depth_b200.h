@@ -84,7 +84,10 @@ typedef struct rd_bn_job {
 typedef struct rd_bn_tail {
     uint32_t* counter; /* zero before the launch; NULL = no fused finalisation */
     int32_t njobs;
-    int32_t pad_;
+    int32_t slots;     /* >1: the statistics are accumulated into `slots` copies (block b adds to copy b % slots, copy k
+                          of an array lives slot_stride doubles after copy k-1) and summed by the finalising CTA: same-
+                          address fp64 atomics serialise in L2, this divides that tail by `slots`.  0/1 = one copy. */
+    int64_t slot_stride;
     rd_bn_job job[RD_MAX_BN_JOBS];
 } rd_bn_tail;
 

@@ -39,7 +39,8 @@ RD_MAX_BN_JOBS = 2
 
 class BnTail(C.Structure):
     """rd_bn_tail: BatchNorm finalisation(s) executed by the last CTA of the statistics-producing kernel."""
-    _fields_ = [("counter", C.c_void_p), ("njobs", C.c_int32), ("pad_", C.c_int32), ("job", BnJob * RD_MAX_BN_JOBS)]
+    _fields_ = [("counter", C.c_void_p), ("njobs", C.c_int32), ("slots", C.c_int32), ("slot_stride", C.c_int64),
+                ("job", BnJob * RD_MAX_BN_JOBS)]
 
 
 class ConvParams(C.Structure):

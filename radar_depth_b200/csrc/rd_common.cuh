@@ -204,14 +204,30 @@ struct FastDiv {
 // Executed by every thread of the LAST block of the statistics-producing kernel (after the ticket); the fp64 sums
 // were accumulated with L2 atomics by all blocks, hence the .cg loads.
 template <typename TAIL>
+__device__ __forceinline__ int tail_slots(const TAIL& t) { return (t.counter && t.slots > 1) ? t.slots : 1; }
+__device__ __forceinline__ double slot_sum(const double* p, int c, int slots, long long stride) {
+    // eight independent L2 loads in flight per round (a dependent load-add chain would pay the L2 latency per copy)
+    double s = 0.0;
+    for (int k0 = 0; k0 < slots; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (k0 + u < slots) ? __ldcg(p + (size_t)(k0 + u) * stride + c) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    return s;
+}
+template <typename TAIL>
 __device__ __forceinline__ void bn_tail_run(const TAIL& t, int tid, int nthreads) {
+    const int slots = tail_slots(t);
+    const long long sstr = t.slot_stride;
     for (int j = 0; j < t.njobs; ++j) {
         const auto& J = t.job[j];
         if (J.kind == 1) {
             if (tid == 0 && J.nbt) *J.nbt += 1;
             for (int c = tid; c < J.C; c += nthreads) {
-                const double m = __ldcg(J.sum_a + c) / J.count;
-                double var = __ldcg(J.sum_b + c) / J.count - m * m;
+                const double m = slot_sum(J.sum_a, c, slots, sstr) / J.count;
+                double var = slot_sum(J.sum_b, c, slots, sstr) / J.count - m * m;
                 if (var < 0.0) var = 0.0;
                 const float mean = (float)m;
                 const float invstd = (float)(1.0 / sqrt(var + (double)J.eps));
@@ -226,7 +242,7 @@ __device__ __forceinline__ void bn_tail_run(const TAIL& t, int tid, int nthreads
             }
         } else if (J.kind == 2) {
             for (int c = tid; c < J.C; c += nthreads) {
-                const double sg = __ldcg(J.sum_a + c), sgz = __ldcg(J.sum_b + c);
+                const double sg = slot_sum(J.sum_a, c, slots, sstr), sgz = slot_sum(J.sum_b, c, slots, sstr);
                 const double mu = J.v0[c], r = J.v1[c], g = J.gamma[c];
                 const double dg = r * (sgz - mu * sg);
                 J.v2[c] += (float)dg;

@@ -366,9 +366,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         }
         if (want_stats) {
             asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            double* sdst = p.stats + (size_t)((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned)tail_slots(p.tail)) * p.tail.slot_stride;
             for (int i = tid; i < p.N; i += 128) {
-                atomicAdd(&p.stats[nb * p.N + i], (double)stats_s[i]);
-                atomicAdd(&p.stats[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
+                atomicAdd(&sdst[nb * p.N + i], (double)stats_s[i]);
+                atomicAdd(&sdst[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
             }
             if (p.tail.counter) {
                 // last CTA to get here finalises the BatchNorm(s) fed by these statistics (rd_bn_tail)

@@ -120,7 +120,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
 // Block-level per-channel reduction helper: each thread owns one 8-channel group (fixed for its lifetime) and
 // NA accumulators per channel; smem partials then one fp64 atomic per channel per block.
 template <int NA>
-__device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, int C, float* red_s, double* const* outs) {
+__device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, int C, float* red_s, double* const* outs,
+                                                     const rd_bn_tail& tail) {
     // red_s: [copies][NA][C] floats (zeroed here).  With fewer than 32 channel groups many threads of a warp own the
     // same group: lanes are first combined with shuffles (power-of-two group counts) and every warp gets a private
     // copy, so that at most a handful of shared-memory atomics ever collide on one address.
@@ -142,6 +143,7 @@ __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, in
         writer = lane < groups;
     }
     float* mine = red_s + (priv ? warp * NA * C : 0);
+    const size_t slot_off = (size_t)(blockIdx.x % (unsigned)tail_slots(tail)) * tail.slot_stride;   // see rd_bn_tail.slots
     if (writer) {
 #pragma unroll
         for (int a = 0; a < NA; ++a)
@@ -153,7 +155,7 @@ __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, in
         const int a = i / C, c = i - a * C;
         float s = 0.f;
         for (int w = 0; w < copies; ++w) s += red_s[w * NA * C + i];
-        atomicAdd(outs[a] + c, (double)s);
+        atomicAdd(outs[a] + slot_off + c, (double)s);
     }
 }
 
@@ -219,8 +221,8 @@ __global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VVie
         }
     }
     double* outs[3] = {sum_g, sum_gz, sum_gzid};
-    if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs);
-    else block_channel_reduce<2>(acc, cg, C, red_s, outs);
+    if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs, tail);
+    else block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
     block_bn_tail(tail);
 }
 
@@ -267,7 +269,9 @@ __global__ void grad_stats_kernel(VView g, VView z, size_t npix, int C, double* 
         }
     }
     double* outs[2] = {sum_g, sum_gz};
-    block_channel_reduce<2>(acc, cg, C, red_s, outs);
+    rd_bn_tail tail;
+    tail.counter = nullptr; tail.slots = 1; tail.slot_stride = 0; tail.njobs = 0;
+    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -387,7 +391,7 @@ __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restri
         }
     }
     double* outs[2] = {sum_g, sum_gz};
-    block_channel_reduce<2>(acc, cg, C, red_s, outs);
+    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
     block_bn_tail(tail);
 }
 

@@ -31,6 +31,10 @@ import torch
 from . import _lib, convplan as cp
 from ._lib import RD_BF16, RD_F32, View
 
+# copies of every statistics array (rd_bn_tail.slots spreads same-address fp64 atomics).  Measured on B200 (same box,
+# bench.py): 1 -> 11.02, 4 -> 11.01, 16 -> 11.16 ms/step: the conv CTAs do not finish close enough together for the atomics
+# to queue up, and the finalising CTA pays for summing the copies.  Kept at 1.
+STAT_SLOTS = int(os.environ.get("RD_STAT_SLOTS", "1"))
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -55,8 +59,9 @@ class BNGroup:
         d = eng.device
         self.vec = eng.hold(torch.zeros(7, self.C, dtype=torch.float32, device=d))    # scale shift mean invstd A B C
         self.scale, self.shift, self.mean, self.invstd, self.cA, self.cB, self.cC = self.vec.unbind(0)
-        self.fstats = eng.alloc_stats(2 * self.C).view(2, self.C)
-        self.bstats = eng.alloc_stats(3 * self.C).view(3, self.C)
+        # [slot][row][C]; launches are handed slot 0, block b accumulates into slot b % STAT_SLOTS
+        self.fstats = eng.alloc_stats(STAT_SLOTS * 2 * self.C).view(STAT_SLOTS, 2, self.C)[0]
+        self.bstats = eng.alloc_stats(STAT_SLOTS * 3 * self.C).view(STAT_SLOTS, 3, self.C)[0]
 
 
 class Launch:
@@ -159,7 +164,7 @@ class LatefusionEngine:
         self._keep = []
         self._buffers = []
         self._graphs = {}
-        self.stats = torch.zeros(1 << 16, dtype=torch.float64, device=self.device)
+        self.stats = torch.zeros(1 << 20, dtype=torch.float64, device=self.device)
         self._stats_used = 0
         self.convs = []                    # (name, GConv, fplan, dplan, wplan)
         self._wpk_tables: List[np.ndarray] = []
@@ -245,11 +250,13 @@ class LatefusionEngine:
         # BatchNorm finalisation is fused into the tail of the kernel that produces its statistics (rd_bn_tail: the
         # last CTA turns the fp64 sums into scale/shift or into the backward coefficients).  Only the eval-mode
         # forward, which has no statistics pass, still uses the stand-alone rd_bn_finalize launch.
-        def new_tail(jobs) -> "_lib.BnTail":
+        def new_tail(jobs, rows: int, Ctot: int) -> "_lib.BnTail":
+            """rows x Ctot = shape of one copy of the statistics array the launch accumulates into."""
             t = _lib.BnTail()
             assert 1 <= len(jobs) <= _lib.RD_MAX_BN_JOBS
             t.counter = _p(self.alloc_stats(1))            # 8-byte slot of the fp64 arena, zeroed with the statistics
             t.njobs = len(jobs)
+            t.slots, t.slot_stride = STAT_SLOTS, rows * Ctot
             for i, j in enumerate(jobs):
                 t.job[i] = j
             self._keep.append(t)
@@ -295,7 +302,7 @@ class LatefusionEngine:
 
         def emit_conv_fwd(rec, src, dst, ld, grp: BNGroup, count: float):
             """conv + (training) statistics epilogue + fused BatchNorm finalisation; eval: conv, then running-stat affine."""
-            emit_conv(self.fwd, rec, "f", src, dst, ld=ld, stats=grp.fstats, tail=new_tail(fwd_jobs(grp, count)))
+            emit_conv(self.fwd, rec, "f", src, dst, ld=ld, stats=grp.fstats, tail=new_tail(fwd_jobs(grp, count), 2, grp.C))
             emit_conv(self.fwd_eval, rec, "f", src, dst, ld=ld, stats=None, tag="(eval)")
             emit_bn_eval(grp, count)
 
@@ -430,7 +437,7 @@ class LatefusionEngine:
             dzcat = self.act(B, ho, wo, 2 * co)
             dzu2 = self.act(B, ho, wo, co)
             tj = new_tail([bwd_job(bu2, 0, _p(bu2.bstats[0]), _p(bu2.bstats[1]), n),
-                           bwd_job(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)])
+                           bwd_job(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)], 3, bu2.C)
             bw.append(Launch("join_bwd:" + L["pfx"], lib.rd_join_bwd,
                              (_v(d_out), _v(L["out"]), _v(L["zu2"]), _v(L["zcat"], co), _v(g_t), npix, co, 0.0,
                               _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), C.byref(tj), act)))
@@ -440,7 +447,7 @@ class LatefusionEngine:
                              (_v(g_t), _v(L["zu2"]), _v(dzu2), _p(bu2.cA), _p(bu2.cB), _p(bu2.cC), npix, co, act)))
             emit_wgrad(bw, L["c3"], _v(dzu2), _v(L["zcat"], 0), ld=(gcat.scale, gcat.shift, 0.0))
             emit_conv(bw, L["c3"], "d", _v(dzu2), _v(dzcat, 0), epi=1, zsrc=_v(L["zcat"], 0), ep=(gcat.scale, gcat.shift, 0.0),
-                      stats=gcat.bstats[:2], tail=new_tail([bwd_job(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)]))
+                      stats=gcat.bstats[:2], tail=new_tail([bwd_job(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)], 3, gcat.C))
             bw.append(Launch("bn_bwd_apply:u1", lib.rd_bn_bwd_apply,
                              (_v(dzcat, 0), _v(L["zcat"], 0), _v(dzcat, 0), _p(gcat.cA), _p(gcat.cB), _p(gcat.cC), npix, co, act)))
             emit_wgrad(bw, L["up"], _v(dzcat), _v(L["x_in"]), ld=L["x_ld"])
@@ -452,14 +459,14 @@ class LatefusionEngine:
             else:
                 g_c2 = self.act(B, h32, w32, 256)
                 emit_conv(bw, L["up"], "d", _v(dzcat), _v(g_c2), epi=1, zsrc=_v(zc2), ep=(bc2.scale, bc2.shift, 1.0),
-                          stats=bc2.bstats[:2], tail=new_tail([bwd_job(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)]))
+                          stats=bc2.bstats[:2], tail=new_tail([bwd_job(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)], 3, bc2.C))
         npf = int(B * h32 * w32)
         bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
                          (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act)))
         emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
         g_f = self.act(B, h32, w32, 512)
         emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2],
-                  tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)]))
+                  tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)], 3, bf.C))
         bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
                          (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act)))
         emit_wgrad(bw, cf, _v(g_f), _v(concat))
@@ -476,7 +483,7 @@ class LatefusionEngine:
                 jobs = [bwd_job(b2, 0, _p(b2.bstats[0]), _p(b2.bstats[1]), n)]
                 if bd:
                     jobs.append(bwd_job(bd, 0, _p(b2.bstats[0]), _p(b2.bstats[2]), n))
-                tj = new_tail(jobs)
+                tj = new_tail(jobs, 3, b2.C)
                 bw.append(Launch("join_bwd:" + Bk["pfx"], lib.rd_join_bwd,
                                  (d_out_v, Bk["out_v"], _v(Bk["z2"]), _v(Bk["zd"]) if bd else NULLV, _v(g_t), npix, cw, 0.0,
                                   _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), C.byref(tj), act)))
@@ -489,7 +496,7 @@ class LatefusionEngine:
                                      (_v(g_t), _v(Bk["zd"]), _v(dzd), _p(bd.cA), _p(bd.cB), _p(bd.cC), npix, cw, act)))
                 emit_wgrad(bw, Bk["c2"], _v(dz2), _v(Bk["z1"]), ld=(b1.scale, b1.shift, 0.0))
                 emit_conv(bw, Bk["c2"], "d", _v(dz2), _v(g1), epi=1, zsrc=_v(Bk["z1"]), ep=(b1.scale, b1.shift, 0.0),
-                          stats=b1.bstats[:2], tail=new_tail([bwd_job(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)]))
+                          stats=b1.bstats[:2], tail=new_tail([bwd_job(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)], 3, b1.C))
                 bw.append(Launch("bn_bwd_apply:bn1", lib.rd_bn_bwd_apply,
                                  (_v(g1), _v(Bk["z1"]), _v(g1), _p(b1.cA), _p(b1.cB), _p(b1.cC), npix, cw, act)))
                 x_in_v = _v(Bk["x_in"])
@@ -507,7 +514,7 @@ class LatefusionEngine:
 
         gz_stem = self.act(B, H2, W2, 80)
         tj = new_tail([bwd_job(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem),
-                       bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)])
+                       bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)], 3, g_stem.C)
         bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
                          (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
                           0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act)))
@@ -545,6 +552,8 @@ class LatefusionEngine:
 
     # ------------------------------------------------------------------ execution
     def _run(self, prog: List[Launch]):
+        # (Weight-gradient launches on a second, event-forked stream were tried: 10.91 vs 10.92 ms/step on B200 --
+        # full-grid kernels with ~200 KB of shared memory per CTA do not overlap; the program stays single-stream.)
         st = torch.cuda.current_stream().cuda_stream
         lib = self.lib
         for L in prog:

@@ -1,4 +1,5 @@
 """Per-launch CUDA-event timing of one training step (eager), with algorithmic TFLOP/s per convolution program."""
+import os
 import statistics
 import sys
 import torch
@@ -30,6 +31,25 @@ for rec in eng.convs:
     if rec["name"] == "stem":
         f = 2.0 * b * p.Hb * p.Wb * (49 * 3 * 64 + 49 * (g.Cx // 4 - 3 if g.Cx == 16 else 2) * 16)
     flops[rec["name"]] = f
+def ew_bytes(L):
+    """Algorithmic bytes of the HBM-bound launches (tensors read + written, bf16 = 2 B)."""
+    k = L.name.split(":")[0]
+    es = 2 if prec == "bf16" else 4
+    a = L.args
+    if k == "bn_bwd_apply":
+        return 3 * a[6] * a[7] * es
+    if k == "join_bwd":
+        return (4 + (1 if a[3].ptr else 0)) * a[5] * a[6] * es
+    if k == "join":
+        return (2 + (1 if a[3].ptr else 0)) * a[7] * a[8] * es
+    if k == "maxpool":
+        return (a[3] * a[4] * a[5] * a[6] + a[3] * a[13] * a[14] * a[6]) * es + a[3] * a[13] * a[14] * a[6]
+    if k == "maxpool_bwd":
+        return (2 * a[6] * a[7] * a[8] * a[9] + a[6] * a[13] * a[14] * a[9]) * es + a[6] * a[13] * a[14] * a[9]
+    return 0
+ebytes = {}
+for L in eng.fwd + eng.bwd:
+    ebytes[L.name] = ebytes.get(L.name, 0) + ew_bytes(L)
 st = torch.cuda.current_stream().cuda_stream
 rows = []
 for prog in (eng.fwd, eng.bwd):
@@ -48,12 +68,14 @@ for prog in (eng.fwd, eng.bwd):
         rows.append((L.name, ms))
 tot = sum(r[1] for r in rows)
 print(f"total {tot:.3f} ms over {len(rows)} launches, b={b} {prec}")
-for name, ms in sorted(rows, key=lambda r: -r[1])[:70]:
+for name, ms in sorted(rows, key=lambda r: -r[1])[:int(os.environ.get('TOPN', '70'))]:
     kind, _, lname = name.partition(":")
     lname = lname.replace("(eval)", "")
     tf = ""
     if kind in ("conv_f", "conv_d", "wgrad") and lname in flops:
         tf = f"{flops[lname] / (ms * 1e-3) / 1e12:8.1f} TFLOP/s"
+    elif ebytes.get(name, 0) > 0:
+        tf = f"{ebytes[name] / (ms * 1e-3) / 1e9:8.0f} GB/s"
     print(f"{ms:8.4f} ms  {100 * ms / tot:5.1f}%  {name:60s} {tf}")
 import json, os
 os.makedirs("gpurun_out", exist_ok=True)
