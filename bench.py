@@ -337,8 +337,19 @@ def kernel_roofline(model, d_in, d_tg, crit, b):
         total_ms = sum(v[0] for v in per.values())
         flops = FLOP_FWD_BWD_PER_IMAGE * b
         achieved = flops / (conv_ms * 1e-3) / 1e12
+        # DRAM bytes per conv launch from the committed ncu launch list of this same command (profiles/): only valid for
+        # the configuration that capture was taken on (b=16 bf16)
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")) as fh:
+                if b == 16:
+                    traffic = json.load(fh)["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write per conv launch, ncu launch list (cold cache per launch), bytes",
+                "peak_source": peaks["source"] + " (sustained bf16)",
                 "kernel": "conv_fprop_kernel + conv_wgrad_kernel (tcgen05 implicit-GEMM programs)",
                 "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "conv_ms_per_step": conv_ms,
                 "all_kernels_ms_per_step": total_ms, "conv_share_of_step": conv_ms / total_ms,
