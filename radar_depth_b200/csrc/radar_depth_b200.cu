@@ -2,6 +2,8 @@
 // (declared in include/radar_depth_b200.h) around the sm_100a kernels in rd_*.cuh.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <cstdint>
 #include <mutex>
 #include <string>
 #include <algorithm>
@@ -30,6 +32,46 @@ constexpr int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
 template <typename K>
 int set_smem(K kernel, int bytes) {
     return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TmapEncodeFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+bool tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RD_TMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+// bf16 NHWC view [B][H][W][pitch] (channels coff .. coff+C) as the 5-D tensor (8, W, H, C/8, B); box (8, box_w, box_rows, 2, 1)
+bool encode_nhwc_map(CUtensorMap* map, const rd_view& v, int B, int H, int W, int C, int box_w, int box_rows) {
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc || box_w > 256 || box_rows > 256 || C % 16) return false;
+    const cuuint64_t pitch_b = (cuuint64_t)v.pitch * 2;
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
+    cuuint64_t strides[4] = {pitch_b, (cuuint64_t)W * pitch_b, 16, (cuuint64_t)H * W * pitch_b};
+    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_rows, 2, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    void* base = (void*)((char*)v.ptr + (size_t)v.coff * 2);
+    if (((uintptr_t)base & 15) || (pitch_b & 15)) return false;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int num_sms() {
@@ -116,14 +158,29 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     if (p->max_ctas > 0 && gx > p->max_ctas) gx = p->max_ctas;
     dim3 grid(gx, p->nblk, 1), block(rd::kFpropThreads, 1, 1);
     cudaStream_t st = (cudaStream_t)stream;
+    // Raw bf16 stride-1 source tiles go through TMA: one box (8 ch, Wl, plane_rows, 2 chunks) per 16-channel stage.  TMA
+    // writes the two chunk planes plane_rows*Wl slots apart, so the kernel gets that chunk stride; the slots a tap shift
+    // reads past a plane (junk accumulator rows, never stored) must still lie inside the stage.
+    rd_conv_params q = *p;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    int use_tma = 0;
+    if (tma_enabled() && p->act_dtype == RD_BF16 && p->ld_scale == nullptr && p->S == 1) {
+        const long long cs = (long long)p->plane_rows * p->Wl;
+        if ((cs + max_shift + (long long)p->MB * 128) * 16 <= p->istage_bytes &&
+            encode_nhwc_map(&map, p->src, p->B, p->srcH, p->srcW, p->Cin, p->Wl, p->plane_rows)) {
+            use_tma = 1;
+            q.chunk_stride = (int32_t)cs;
+        }
+    }
     if (p->act_dtype == RD_BF16) {
         static bool once = false;
         if (!once) { int rc = set_smem(rd::conv_fprop_kernel<rd::bf16, 1>, kMaxSmem); if (rc) return rc; once = true; }
-        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(*p);
+        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(q, map, use_tma);
     } else if (p->act_dtype == RD_F32) {
         static bool once = false;
         if (!once) { int rc = set_smem(rd::conv_fprop_kernel<float, 3>, kMaxSmem); if (rc) return rc; once = true; }
-        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(*p);
+        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(q, map, 0);
     } else {
         return fail(RD_EINVAL, "rd: bad act_dtype");
     }

@@ -5,6 +5,7 @@
 // bounded: a barrier that does not flip within RD_WAIT_SPINS polls records a code in a global
 // error word and traps, so a protocol bug surfaces as a CUDA error instead of hanging the GPU.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -85,6 +86,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
             smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------- TMA tensor load (5-D tile) global -> shared
+// Box of the NHWC activation seen as (8 channels, W, H, C/8, B): lands as [chunk][row][col] x 16 B, out-of-image
+// coordinates are zero-filled by the hardware (= the convolution's zero padding).
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
         : "memory");
 }
 

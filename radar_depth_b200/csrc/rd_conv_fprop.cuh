@@ -78,7 +78,8 @@ __device__ __forceinline__ int reduce16_owner_channel(int lane) {
 }
 
 template <typename T, int SPLIT>
-__global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __grid_constant__ rd_conv_params p) {
+__global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __grid_constant__ rd_conv_params p,
+                                                                      const __grid_constant__ CUtensorMap src_map, const int use_tma) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* in_full = bars;                       // [kMaxStages]
@@ -114,8 +115,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // ---- one-time setup
     // raw bf16 source tiles are staged with cp.async (one arrival per loader thread), others through registers
     const bool src_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr);
+    // raw stride-1 tiles: ONE elected thread issues a TMA box load per stage (use_tma is decided by the launcher, which
+    // also encodes src_map and sets p.chunk_stride = plane_rows * Wl, the chunk pitch TMA writes)
+    const bool src_tma = src_async && use_tma;
     if (tid == 0) {
-        for (int i = 0; i < p.IS; ++i) { mbar_init(&in_full[i], src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps); mbar_init(&in_empty[i], 1); }
+        for (int i = 0; i < p.IS; ++i) {
+            mbar_init(&in_full[i], src_tma ? 1 : (src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps));
+            mbar_init(&in_empty[i], 1);
+        }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         fence_mbar_init();
@@ -155,6 +162,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         if (tl_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
+        if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
+        else
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -163,6 +172,22 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             for (int c = 0; c < ncblk; ++c) {
                 const long long t0_ = p.dbg ? clock64() : 0;
                 mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
+                if (src_tma) {
+                    if (!(p.dbg_flags & 2)) {
+                        mbar_arrive_expect_tx(&in_full[st.stage], (uint32_t)(p.plane_rows * p.Wl * 32));
+                        tma_load_5d(a_ring + (size_t)st.stage * p.istage_bytes, &src_map, 0, x0 + p.sx_min, y0 + p.sy_min, c * 2, img,
+                                    &in_full[st.stage]);
+                    } else {
+                        mbar_arrive(&in_full[st.stage]);
+                    }
+                    st.advance();
+                    if (p.dbg) {
+                        const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+                        if (tl_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry;
+                        else { const long long t1_ = clock64(); p.dbg[0 * ncta + cta] += t1_ - t0_; }
+                    }
+                    continue;
+                }
                 const long long t1_ = p.dbg ? clock64() : 0;
                 uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
                 if (p.dbg_flags & 2) {

@@ -3,6 +3,7 @@
 // as a function of loader warps per CTA.  One CTA per SM, no consumers: only the copy rate matters.
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,13 +40,14 @@ __global__ void __launch_bounds__(512, 1) k(const uint8_t* __restrict__ src, int
     if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const int grid = argc > 1 ? atoi(argv[1]) : 148;
     const size_t bytes = 64ull << 20;          // 64 MiB: L2 resident after the first pass
     uint8_t* src; cudaMalloc(&src, bytes + (8 << 20)); cudaMemset(src, 1, bytes + (8 << 20));
     long long* d; cudaMalloc(&d, 148 * 8);
     const int rows = 10, Wl = 64, iters = 200;
-    for (int mode = 0; mode < 4; ++mode)
-        for (int pitch : {32, 128, 256, 1024})
+    for (int mode = 0; mode < 1; ++mode)
+        for (int pitch : {128})
             for (int nchunks : {2, 4, 8})
                 for (int warps : {4, 8, 16}) {
                     if (nchunks * 16 > pitch) continue;
@@ -53,10 +55,10 @@ int main() {
                     if (smem > 200 * 1024) continue;
                     auto launch = [&](int it) {
                         switch (mode) {
-                            case 0: cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<0><<<148, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
-                            case 1: cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<1><<<148, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
-                            case 2: cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<2><<<148, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
-                            default: cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<3><<<148, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
+                            case 0: cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<0><<<grid, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
+                            case 1: cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<1><<<grid, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
+                            case 2: cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<2><<<grid, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
+                            default: cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); k<3><<<grid, warps * 32, smem>>>(src, pitch, nchunks, rows, Wl, it, d, bytes); break;
                         }
                     };
                     launch(20);
@@ -64,9 +66,9 @@ int main() {
                     launch(iters);
                     cudaError_t e = cudaDeviceSynchronize();
                     long long c[148]; cudaMemcpy(c, d, sizeof(c), cudaMemcpyDeviceToHost);
-                    double avg = 0; for (int i = 0; i < 148; ++i) avg += c[i]; avg /= 148;
+                    double avg = 0; for (int i = 0; i < grid; ++i) avg += c[i]; avg /= grid;
                     const double b = (double)iters * rows * Wl * nchunks * 16;
-                    printf("mode %d pitch %4d nchunks %d warps %2d : %6.2f B/clk/SM  (%s)\n", mode, pitch, nchunks, warps, b / avg, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+                    printf("grid %3d mode %d pitch %4d nchunks %d warps %2d : %6.2f B/clk/SM  (%s)\n", grid, mode, pitch, nchunks, warps, b / avg, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
                 }
     return 0;
 }
