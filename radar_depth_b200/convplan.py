@@ -399,14 +399,18 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
     ntg = -(-ntaps // tg_cap)
     tg_size = -(-ntaps // ntg)
     best = None
-    for KS in (32, 64, 96, 128, 192, 256, 384, 512):
-        if KS > max(ks_target, 32):
+    for KS0 in (32, 64, 96, 128, 192, 256, 384, 512):
+        if KS0 > max(ks_target, 32):
             continue
-        for Wl in range(halo_x + 1, min(Wb + halo_x, KS) + 1):
+        for Wl in range(halo_x + 1, min(Wb + halo_x, KS0) + 1):
             Wt = Wl - halo_x
-            Ht = min(KS // Wl, Hb)
+            Ht = min(KS0 // Wl, Hb)
             if Ht < 1:
                 continue
+            # A tile of exactly KS = Ht*Wl slots lets the gradient tile be one dense TMA box (rd_conv_wgrad: TMA writes the
+            # chunk planes of a box back to back, so a plane must not have a tail); such tiles are preferred.
+            tma_g = parts == 1 and g.OS == 1 and (Ht * Wl) % 16 == 0
+            KS = Ht * Wl if tma_g else KS0
             xrows = Ht + halo_y
             xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
             GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
@@ -420,10 +424,10 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
             ty, tx = -(-Hb // Ht), -(-Wb // Wt)
             load = (Mc // 8) * GPS + (Nc // 8) * XPS
             mma = (KS // 16) * tg_size * max(Nc, 32) / 2.0 * (3 if parts == 2 else 1)
-            cost = ty * tx * (max(mma, load * 0.35 * parts) + 300.0)
+            cost = ty * tx * (max(mma, load * 0.35 * parts * (0.6 if tma_g else 1.0)) + 300.0)
             if best is None or cost < best[0]:
                 best = (cost, dict(KS=KS, Wl=Wl, Wt=Wt, Ht=Ht, xrows=xrows, xslots=xslots, g_bytes=g_bytes,
-                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad, GPS=GPS, XPS=XPS))
+                                   stage=stage, tiles_y=ty, tiles_x=tx, pad=pad, GPS=GPS, XPS=XPS, tma_g=tma_g))
     return best
 
 

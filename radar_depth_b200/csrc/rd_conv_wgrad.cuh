@@ -32,12 +32,15 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 template <typename T, int SPLIT>
-__global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ rd_wgrad_params p) {
+__global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ rd_wgrad_params p,
+                                                                      const __grid_constant__ CUtensorMap g_map,
+                                                                      const __grid_constant__ CUtensorMap x_map, const int tma_mode) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* full = bars;
     uint64_t* empty = bars + 8;
     uint64_t* tmem_full = bars + 16;
+    uint64_t* tma_full = bars + 24;                // [8] TMA landing barriers (gradient tiles need a fix-up hop, see below)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgOffTmemSlot);
     float* ld_sc = reinterpret_cast<float*>(smem + kWgOffLdScale);
     float* ld_sh = reinterpret_cast<float*>(smem + kWgOffLdShift);
@@ -61,11 +64,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
 
     // raw bf16 tiles are staged with cp.async (one arrival per loader thread), transformed tiles through registers
     // (one arrival per loader warp)
-    const bool g_async = (SPLIT == 1) && (sizeof(T) == 2);
-    const bool x_async = g_async && (p.ld_scale == nullptr);
-    const uint32_t full_count = (uint32_t)(((g_async || x_async) ? 32 * kWgLoaderWarps : 0) + ((!g_async || !x_async) ? kWgLoaderWarps : 0));
+    // Staging modes per operand.  TMA (raw bf16, stride 1; decided by the launcher, which also encodes the tensor maps and
+    // hands the kernel the dense chunk strides TMA writes): ONE thread issues a box load per stage.  Otherwise raw bf16
+    // tiles are staged with cp.async (one arrival per loader thread) and transformed tiles through registers (one arrival
+    // per loader warp).  A TMA box of the gradient tile is Wl columns wide, so its Wl-Wt junk columns hold the neighbour
+    // tile's pixels and must be cleared before the contraction: the TMA lands on tma_full[stage], the worker warps then
+    // zero those columns and arrive on full[stage].
+    const bool g_tma = (tma_mode & 1) != 0, x_tma = (tma_mode & 2) != 0, any_tma = g_tma || x_tma;
+    const bool g_async = (SPLIT == 1) && (sizeof(T) == 2) && !g_tma;
+    const bool x_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr) && !x_tma;
+    const bool g_reg = !g_tma && !g_async, x_reg = !x_tma && !x_async;
+    const int nworkers = any_tma ? kWgLoaderWarps - 1 : kWgLoaderWarps;      // warp 4 drives the TMA unit
+    const bool warp_arrives = g_reg || x_reg || g_tma;
+    const uint32_t full_count = (uint32_t)((warp_arrives ? nworkers : 0) + ((g_async || x_async) ? 32 * nworkers : 0) +
+                                           ((x_tma && !g_tma) ? 1 : 0));
     if (tid == 0) {
-        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], full_count); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], full_count); mbar_init(&empty[i], 1); mbar_init(&tma_full[i], 1); }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
@@ -101,6 +115,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         // allows and never wait for memory.  Tiles with a fused transform are staged through registers and
         // signalled with one ordinary arrival per warp.  The generic->async proxy fence is executed by the consumer
         // (UMMA warp) after it has observed full[stage]: a producer-side fence would have to drain the copies.
+        const int widx = any_tma ? warp - 5 : warp - 4;
+        const uint32_t g_tx = (uint32_t)(p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)(p.Wl * p.x_plane_rows * x_chunks * 16);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -110,21 +126,54 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             mbar_wait(&empty[st.stage], st.phase ^ 1, 0x500 + st.stage);
             const long long tw1 = p.dbg ? clock64() : 0;
             uint8_t* sbase = ring + (size_t)st.stage * p.stage_bytes;
+            if (any_tma && warp == 4) {
+                // ---- TMA issuer
+                if (lane == 0) {
+                    uint64_t* bar = g_tma ? &tma_full[st.stage] : &full[st.stage];
+                    if (!(p.dbg_flags & 2)) {
+                        mbar_arrive_expect_tx(bar, (g_tma ? g_tx : 0u) + (x_tma ? x_tx : 0u));
+                        if (g_tma) tma_load_5d(sbase, &g_map, 0, x0, y0, co0 >> 3, img, bar);
+                        if (x_tma) tma_load_5d(sbase + p.g_bytes, &x_map, 0, x0 + p.sx_min, y0 + p.sy_min, ci0 >> 3, img, bar);
+                    } else {
+                        mbar_arrive(bar);
+                    }
+                }
+                st.advance();
+                if (p.dbg && lane == 0) {
+                    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+                    const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
+                    p.dbg[0 * ncta + cta] += tw1 - tw0;
+                }
+                continue;
+            }
+            // ---- worker warps
             if (!(p.dbg_flags & 2)) {
-                if (g_async) stage_tile_async<T>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
-                if (x_async) stage_tile_async<T>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+                if (g_async) stage_tile_async<T>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, widx, nworkers, lane);
+                if (x_async) stage_tile_async<T>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, widx, nworkers, lane);
             }
             if (g_async || x_async) cp_async_mbar_arrive_noinc(&full[st.stage]);
-            if (!g_async || !x_async) {
-                if (!(p.dbg_flags & 2)) {
-                    if (!g_async) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, warp - 4, kWgLoaderWarps, lane);
-                    if (!x_async) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, warp - 4, kWgLoaderWarps, lane);
+            if (!(p.dbg_flags & 2)) {
+                if (g_reg) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, widx, nworkers, lane);
+                if (x_reg) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, widx, nworkers, lane);
+            }
+            if (g_tma) {
+                mbar_wait(&tma_full[st.stage], st.phase, 0x520 + st.stage);
+                // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
+                const int jc = p.Wl - p.Wt;
+                const int items = p.Ht * jc * g_chunks;
+                const FastDiv fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
+                for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
+                    const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
+                    const int j = (int)fd_ht.div((uint32_t)q), r = q - j * p.Ht;
+                    *reinterpret_cast<uint4*>(sbase + ((size_t)(j * GPS + r * p.Wl + p.Wt + c) << 4)) = make_uint4(0, 0, 0, 0);
                 }
+            }
+            if (warp_arrives) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[st.stage]);
             }
             st.advance();
-            if (p.dbg && warp == 4 && lane == 0) {
+            if (p.dbg && !any_tma && warp == 4 && lane == 0) {
                 const long long tw2 = clock64();
                 const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
                 const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
