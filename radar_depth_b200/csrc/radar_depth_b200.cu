@@ -165,7 +165,7 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     int use_tma = 0;
-    if (tma_enabled() && p->act_dtype == RD_BF16 && p->ld_scale == nullptr && p->S == 1) {
+    if (tma_enabled() && p->act_dtype == RD_BF16 && p->S == 1) {
         const long long cs = (long long)p->plane_rows * p->Wl;
         if ((cs + max_shift + (long long)p->MB * 128) * 16 <= p->istage_bytes &&
             encode_nhwc_map(&map, p->src, p->B, p->srcH, p->srcW, p->Cin, p->Wl, p->plane_rows)) {

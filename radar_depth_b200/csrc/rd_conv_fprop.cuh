@@ -25,7 +25,7 @@ namespace rd {
 constexpr int kFpropLoaderWarps = 8;
 constexpr int kFpropThreads = (4 + kFpropLoaderWarps + 2) * 32;   // epilogue x4, loaders, UMMA issuer, weight copier
 constexpr int kSmemHeader = 16384;      // barriers, tmem slot, stats, BN vectors
-constexpr int kOffTmemSlot = 256;
+constexpr int kOffTmemSlot = 384;      // (the barrier block below occupies bytes [0, 352))
 constexpr int kOffTapTable = 512;       // int[3][32]: a_shift, accumulator column, first-of-phase flag
 constexpr int kOffStats = 1024;         // float[512]
 constexpr int kOffEpScale = 3072;       // float[256]
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     uint64_t* w_empty = bars + 3 * kMaxStages;
     uint64_t* tmem_full = bars + 4 * kMaxStages;        // [2]
     uint64_t* tmem_empty = bars + 4 * kMaxStages + 2;   // [2]
+    uint64_t* tma_full = bars + 4 * kMaxStages + 4;     // [kMaxStages] TMA landing barriers of the transform-in-place mode
     int* tap_a = reinterpret_cast<int*>(smem + kOffTapTable);
     int* tap_d = tap_a + 32;
     int* tap_f = tap_a + 64;
@@ -118,10 +119,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // raw stride-1 tiles: ONE elected thread issues a TMA box load per stage (use_tma is decided by the launcher, which
     // also encodes src_map and sets p.chunk_stride = plane_rows * Wl, the chunk pitch TMA writes)
     const bool src_tma = src_async && use_tma;
+    // bf16 stride-1 tiles with a fused BatchNorm+activation: the raw box lands by TMA on tma_full[stage], seven worker
+    // warps apply the transform IN PLACE in shared memory (no global latency on their path) and arrive on in_full[stage]
+    const bool src_tma_bn = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale != nullptr) && use_tma;
     if (tid == 0) {
         for (int i = 0; i < p.IS; ++i) {
-            mbar_init(&in_full[i], src_tma ? 1 : (src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps));
+            mbar_init(&in_full[i], src_tma ? 1 : (src_tma_bn ? kFpropLoaderWarps - 1 : (src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps)));
             mbar_init(&in_empty[i], 1);
+            mbar_init(&tma_full[i], 1);
         }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
@@ -163,6 +168,49 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
         if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
+        else if (src_tma_bn && warp != 4) {
+            // ---- transform workers (warps 5..11)
+            const int widx = warp - 5, nwork = kFpropLoaderWarps - 1;
+            const int cs = p.chunk_stride;                 // = plane_rows * Wl in this mode
+            const int items = 2 * p.plane_rows * p.Wl;
+            const FastDiv fd_cs((uint32_t)cs), fd_wl((uint32_t)p.Wl);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img;
+                const int trem = tile - img * tiles_per_img;
+                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+                const int yb = ty * p.Ht + p.sy_min, xb = tx * p.Wt + p.sx_min;
+                (void)img;
+                for (int c = 0; c < ncblk; ++c) {
+                    mbar_wait(&tma_full[st.stage], st.phase, 0x120 + st.stage);
+                    uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
+                    if (!(p.dbg_flags & 2)) {
+                        for (int it = widx * 32 + lane; it < items; it += nwork * 32) {
+                            const int j = (int)fd_cs.div((uint32_t)it), sl = it - j * cs;
+                            const int r = (int)fd_wl.div((uint32_t)sl), cx = sl - r * p.Wl;
+                            const int iy = yb + r, ix = xb + cx;
+                            if (iy < 0 || iy >= p.srcH || ix < 0 || ix >= p.srcW) continue;     // zero padding stays zero
+                            uint4* d = reinterpret_cast<uint4*>(sbase) + it;
+                            uint4 u = *d;
+                            const float* sc = ld_sc + c * 16 + j * 8;
+                            const float* sh = ld_sh + c * 16 + j * 8;
+                            float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float y = fmaf(v[k], sc[k], sh[k]);
+                                v[k] = y > 0.f ? y : y * p.ld_slope;
+                            }
+                            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                            *d = u;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&in_full[st.stage]);
+                    st.advance();
+                }
+            }
+        }
+        else if (src_tma_bn && lane != 0) { /* warp 4: only lane 0 issues */ }
         else
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
@@ -172,13 +220,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             for (int c = 0; c < ncblk; ++c) {
                 const long long t0_ = p.dbg ? clock64() : 0;
                 mbar_wait(&in_empty[st.stage], st.phase ^ 1, 0x100 + st.stage);
-                if (src_tma) {
+                if (src_tma || src_tma_bn) {
+                    uint64_t* bar = src_tma ? &in_full[st.stage] : &tma_full[st.stage];
                     if (!(p.dbg_flags & 2)) {
-                        mbar_arrive_expect_tx(&in_full[st.stage], (uint32_t)(p.plane_rows * p.Wl * 32));
-                        tma_load_5d(a_ring + (size_t)st.stage * p.istage_bytes, &src_map, 0, x0 + p.sx_min, y0 + p.sy_min, c * 2, img,
-                                    &in_full[st.stage]);
+                        mbar_arrive_expect_tx(bar, (uint32_t)(p.plane_rows * p.Wl * 32));
+                        tma_load_5d(a_ring + (size_t)st.stage * p.istage_bytes, &src_map, 0, x0 + p.sx_min, y0 + p.sy_min, c * 2, img, bar);
                     } else {
-                        mbar_arrive(&in_full[st.stage]);
+                        mbar_arrive(bar);
                     }
                     st.advance();
                     if (p.dbg) {

@@ -74,10 +74,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const bool g_async = (SPLIT == 1) && (sizeof(T) == 2) && !g_tma;
     const bool x_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr) && !x_tma;
     const bool g_reg = !g_tma && !g_async, x_reg = !x_tma && !x_async;
+    const bool x_bn = x_tma && (p.ld_scale != nullptr);   // raw box by TMA, BatchNorm+activation applied in place by the workers
+    const bool hop = g_tma || x_bn;                       // TMA lands on tma_full, the workers fix up and arrive on full
     const int nworkers = any_tma ? kWgLoaderWarps - 1 : kWgLoaderWarps;      // warp 4 drives the TMA unit
-    const bool warp_arrives = g_reg || x_reg || g_tma;
+    const bool warp_arrives = g_reg || x_reg || hop;
     const uint32_t full_count = (uint32_t)((warp_arrives ? nworkers : 0) + ((g_async || x_async) ? 32 * nworkers : 0) +
-                                           ((x_tma && !g_tma) ? 1 : 0));
+                                           ((any_tma && !hop) ? 1 : 0));
     if (tid == 0) {
         for (int i = 0; i < p.NS; ++i) { mbar_init(&full[i], full_count); mbar_init(&empty[i], 1); mbar_init(&tma_full[i], 1); }
         mbar_init(tmem_full, 1);
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             if (any_tma && warp == 4) {
                 // ---- TMA issuer
                 if (lane == 0) {
-                    uint64_t* bar = g_tma ? &tma_full[st.stage] : &full[st.stage];
+                    uint64_t* bar = hop ? &tma_full[st.stage] : &full[st.stage];
                     if (!(p.dbg_flags & 2)) {
                         mbar_arrive_expect_tx(bar, (g_tma ? g_tx : 0u) + (x_tma ? x_tx : 0u));
                         if (g_tma) tma_load_5d(sbase, &g_map, 0, x0, y0, co0 >> 3, img, bar);
@@ -156,8 +158,32 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 if (g_reg) stage_tile<T, SPLIT>(tg_, sbase, GPS, img, y0, x0, co0, g_chunks, widx, nworkers, lane);
                 if (x_reg) stage_tile<T, SPLIT>(tx_, sbase + p.g_bytes, XPS, img, y0, x0, ci0, x_chunks, widx, nworkers, lane);
             }
+            if (hop) mbar_wait(&tma_full[st.stage], st.phase, 0x520 + st.stage);
+            if (x_bn && !(p.dbg_flags & 2)) {
+                // fused BatchNorm + activation of the source tile, in place (zero padding stays zero)
+                const int xitems = x_chunks * XPS;               // XPS = x_plane_rows * Wl in this mode
+                const FastDiv fd_xps((uint32_t)XPS), fd_wl((uint32_t)p.Wl);
+                uint4* xb = reinterpret_cast<uint4*>(sbase + p.g_bytes);
+                for (int it = widx * 32 + lane; it < xitems; it += nworkers * 32) {
+                    const int j = (int)fd_xps.div((uint32_t)it), sl = it - j * XPS;
+                    const int r = (int)fd_wl.div((uint32_t)sl), cx = sl - r * p.Wl;
+                    const int iy = y0 + p.sy_min + r, ix = x0 + p.sx_min + cx;
+                    if (iy < 0 || iy >= p.xH || ix < 0 || ix >= p.xW) continue;
+                    uint4 u = xb[it];
+                    const float* sc = ld_sc + ci0 + j * 8;
+                    const float* sh = ld_sh + ci0 + j * 8;
+                    float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float y = fmaf(v[k], sc[k], sh[k]);
+                        v[k] = y > 0.f ? y : y * p.ld_slope;
+                    }
+                    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                    xb[it] = u;
+                }
+            }
             if (g_tma) {
-                mbar_wait(&tma_full[st.stage], st.phase, 0x520 + st.stage);
                 // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
                 const int jc = p.Wl - p.Wt;
                 const int items = p.Ht * jc * g_chunks;
