@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             mbar_init(&tma_full[i], 1);
         }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], src_tma ? 8 : 4); }
         fence_mbar_init();
     }
     if (tid < p.ntaps) {
@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < kWarpMma) {
+    // With raw TMA staging seven of the eight loader warps have nothing to load: warps 8-11 (TMEM lane quarters 0-3 again)
+    // become a second epilogue group that takes the odd 16-column chunks.
+    const bool epi2 = src_tma;
+    if (warp >= 4 && warp < kWarpMma && !(epi2 && warp >= 8 && warp < 12)) {
         // ================= source tile loaders =================
         PipeState st(p.IS);
         TileSrc ts;
@@ -355,7 +358,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         }
         __syncwarp();
     } else {
-        // ================= epilogue (warps 0-3) =================
+        // ================= epilogue (warps 0-3, and warps 8-11 in raw-TMA mode) =================
+        const int wq = warp & 3, eg = warp >> 3, neg = epi2 ? 2 : 1;
         T* dst = reinterpret_cast<T*>(p.dst.ptr);
         const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
         const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
@@ -373,14 +377,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             mbar_wait(&tmem_full[ab], use & 1u, 0x400);
             const long long t1_ = p.dbg ? clock64() : 0;
             tc_fence_after();
-            const uint32_t t_tile = tmem_base + ab * (uint32_t)acc_cols + ((uint32_t)(warp * 32) << 16);
-            for (int cc = 0; cc < (p.N >> 4); ++cc) {
+            const uint32_t t_tile = tmem_base + ab * (uint32_t)acc_cols + ((uint32_t)(wq * 32) << 16);
+            // two groups: split the 16-column chunks between them, or (single-chunk layers) the 128-row blocks
+            const bool split_cc = (p.N >> 4) >= 2;
+            const int cc0 = split_cc ? eg : 0, ccs = split_cc ? neg : 1;
+            const int mb0 = split_cc ? 0 : eg, mbs = split_cc ? 1 : neg;
+            for (int cc = cc0; cc < (p.N >> 4); cc += ccs) {
                 float s1[16], s2[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
                 for (int ph = 0; ph < p.P; ++ph) {
-                    for (int mb = 0; mb < p.MB; ++mb) {
-                        const int m = mb * 128 + warp * 32 + lane;
+                    for (int mb = mb0; mb < p.MB; mb += mbs) {
+                        const int m = mb * 128 + wq * 32 + lane;
                         const int ly = (int)fd_wl.div((uint32_t)m), lx = m - ly * p.Wl;
                         const int oy = y0 + ly, ox = x0 + lx;
                         const int fy = oy * p.OS + p.phase_y[ph], fx = ox * p.OS + p.phase_x[ph];
@@ -438,23 +446,26 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             }
         }
         if (want_stats) {
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
-            double* sdst = p.stats + (size_t)((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned)tail_slots(p.tail)) * p.tail.slot_stride;
-            for (int i = tid; i < p.N; i += 128) {
-                atomicAdd(&sdst[nb * p.N + i], (double)stats_s[i]);
-                atomicAdd(&sdst[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
-            }
-            if (p.tail.counter) {
-                // last CTA to get here finalises the BatchNorm(s) fed by these statistics (rd_bn_tail)
-                __threadfence();
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                if (tid == 0) tmem_slot[1] = (atomicAdd(p.tail.counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1u : 0u;
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                if (tmem_slot[1]) {
-                    __threadfence();
-                    bn_tail_run(p.tail, tid, 128);
+            if (neg == 2) asm volatile("bar.sync 1, 256;\n" ::: "memory");      // both epilogue groups have added their partials
+            else asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (eg == 0) {
+                double* sdst = p.stats + (size_t)((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned)tail_slots(p.tail)) * p.tail.slot_stride;
+                for (int i = tid; i < p.N; i += 128) {
+                    atomicAdd(&sdst[nb * p.N + i], (double)stats_s[i]);
+                    atomicAdd(&sdst[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
                 }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (p.tail.counter) {
+                    // last CTA to get here finalises the BatchNorm(s) fed by these statistics (rd_bn_tail)
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                    if (tid == 0) tmem_slot[1] = (atomicAdd(p.tail.counter, 1u) == gridDim.x * gridDim.y - 1u) ? 1u : 0u;
+                    asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                    if (tmem_slot[1]) {
+                        __threadfence();
+                        bn_tail_run(p.tail, tid, 128);
+                    }
+                    asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                }
             }
         }
     }
