@@ -151,7 +151,8 @@ typedef struct rd_conv_params {
     int32_t max_ctas;        /* persistent grid cap (0 = one CTA per tile) */
     long long* dbg;          /* optional [6][gridDim.x*gridDim.y] cycle counters: loader wait/fill, issuer wait/issue, epilogue wait/work */
     int32_t dbg_flags;       /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging, 4 = skip epilogue stores */
-    int32_t pad_;
+    int32_t src_planes;      /* S = 2: number of parity planes the taps actually read, staged from plane 0 on (0 = all four);
+                                a 1x1 stride-2 convolution only ever reads plane (0,0) */
 } rd_conv_params;
 
 int rd_conv_fprop(const rd_conv_params* p, void* stream);
@@ -190,7 +191,7 @@ typedef struct rd_wgrad_params {
     int32_t max_ctas;            /* pixel-split CTAs (grid.x) */
     long long* dbg;              /* optional [4][gridDim.x*y*z] cycle counters (loader wait/fill, issuer wait/issue); NULL = off */
     int32_t dbg_flags;           /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging */
-    int32_t pad_;
+    int32_t x_planes;            /* Sx = 2: parity planes of the source the taps read, from plane 0 on (0 = all four) */
 } rd_wgrad_params;
 
 int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);

@@ -61,7 +61,7 @@ class ConvParams(C.Structure):
         ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_slope", C.c_float),
         ("stats", C.c_void_p), ("stats_stride", C.c_int32), ("tail", BnTail),
         ("IS", C.c_int32), ("WS", C.c_int32), ("istage_bytes", C.c_int32), ("wstage_bytes", C.c_int32),
-        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("pad_", C.c_int32),
+        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("src_planes", C.c_int32),
     ]
 
 
@@ -81,7 +81,7 @@ class WgradParams(C.Structure):
         ("taps", WTap * RD_MAX_TAPS),
         ("Mc", C.c_int32), ("ncob", C.c_int32), ("Nc", C.c_int32), ("ncib", C.c_int32),
         ("dw", C.c_void_p), ("NS", C.c_int32), ("stage_bytes", C.c_int32), ("g_bytes", C.c_int32),
-        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("pad_", C.c_int32),
+        ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("x_planes", C.c_int32),
     ]
 
 

@@ -369,6 +369,9 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     p.dstH, p.dstW = dH, dW
     p.IS, p.WS, p.istage_bytes, p.wstage_bytes = IS, WS, istage, wstage
     p.act_dtype = act_dtype
+    # stride-2 sources are staged as four parity planes; taps that only ever read plane (0,0) (1x1 stride-2 downsample
+    # convolutions) need just that one
+    p.src_planes = 1 if (g.S == 2 and all(t.pl == (0, 0) for t in taps)) else 0
     ntiles = geo["tiles_y"] * geo["tiles_x"] * B
     p.max_ctas = max(1, NUM_SMS // nblk)
     # gather table [nblk][ncblk][tap][part][j][n][k]
@@ -493,6 +496,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     p.Mc, p.ncob, p.Nc, p.ncib = Mc, ncob, Nc, ncib
     p.NS, p.stage_bytes, p.g_bytes = NS, geo["stage"], geo["g_bytes"]
     p.act_dtype = act_dtype
+    p.x_planes = 1 if (g.S == 2 and all(t.pl == (0, 0) for t in taps)) else 0
     ntiles = geo["tiles_y"] * geo["tiles_x"] * B
     ctas_other = ncob * ncib * ntg
     # one resident wave: every extra wave pays the CTA prologue (TMEM alloc, ring zero-fill) and the final fp32

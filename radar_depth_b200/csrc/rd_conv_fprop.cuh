@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         // ================= source tile loaders =================
         PipeState st(p.IS);
         TileSrc ts;
-        ts.ptr = p.src.ptr; ts.pitch = p.src.pitch; ts.coff = p.src.coff; ts.H = p.srcH; ts.W = p.srcW; ts.S = p.S;
+        ts.ptr = p.src.ptr; ts.pitch = p.src.pitch; ts.coff = p.src.coff; ts.H = p.srcH; ts.W = p.srcW; ts.S = p.S; ts.nplanes = p.src_planes;
         ts.plane_slots = p.plane_slots; ts.plane_rows = p.plane_rows; ts.Wl = p.Wl; ts.oy0 = p.sy_min; ts.ox0 = p.sx_min;
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tg_.ptr = p.gy.ptr; tg_.pitch = p.gy.pitch; tg_.coff = p.gy.coff; tg_.H = p.gH; tg_.W = p.gW; tg_.S = p.Sg;
         tg_.plane_slots = p.KS; tg_.plane_rows = p.Ht; tg_.Wl = p.Wl; tg_.oy0 = 0; tg_.ox0 = 0;
         tg_.vrows = p.Ht; tg_.vcols = p.Wt; tg_.sc = nullptr; tg_.sh = nullptr; tg_.slope = 1.f;
-        tx_.ptr = p.x.ptr; tx_.pitch = p.x.pitch; tx_.coff = p.x.coff; tx_.H = p.xH; tx_.W = p.xW; tx_.S = p.Sx;
+        tx_.ptr = p.x.ptr; tx_.pitch = p.x.pitch; tx_.coff = p.x.coff; tx_.H = p.xH; tx_.W = p.xW; tx_.S = p.Sx; tx_.nplanes = p.x_planes;
         tx_.plane_slots = p.x_plane_slots; tx_.plane_rows = p.x_plane_rows; tx_.Wl = p.Wl; tx_.oy0 = p.sy_min; tx_.ox0 = p.sx_min;
         tx_.vrows = p.x_plane_rows; tx_.vcols = p.Wl;
         tx_.sc = p.ld_scale ? ld_sc : nullptr; tx_.sh = ld_sh; tx_.slope = p.ld_slope;

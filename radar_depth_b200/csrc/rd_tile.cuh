@@ -18,6 +18,7 @@ struct TileSrc {
     int pitch, coff;        // NHWC view
     int H, W;               // image size of the view
     int S;                  // 1, or 2 = four parity planes
+    int nplanes = 0;        // planes to stage, from plane 0 on (0 = S*S)
     int plane_slots, plane_rows, Wl;
     int oy0, ox0;           // plane-coordinate offset of slot 0 relative to the tile origin
     int vrows, vcols;       // rows/cols (local) beyond which zeros are written
@@ -65,7 +66,7 @@ template <typename T, int SPLIT>
 __device__ __forceinline__ void stage_tile(const TileSrc& t, uint8_t* dst, int cs, int img, int y0, int x0, int c0,
                                            int nchunks, int warp_idx, int nwarps, int lane) {
     constexpr int kBatch = (sizeof(T) == 2) ? 8 : 4;
-    const int planes = t.S * t.S;
+    const int planes = t.nplanes > 0 ? t.nplanes : t.S * t.S;
     const int sh_s = t.S >> 1;                         // S is 1 or 2
     const T* src = reinterpret_cast<const T*>(t.ptr);
     const int row_items = t.Wl * nchunks;
@@ -145,7 +146,7 @@ __device__ __forceinline__ bool tile_is_raw(const TileSrc& t) {
 template <typename T>
 __device__ __forceinline__ void stage_tile_async(const TileSrc& t, uint8_t* dst, int cs, int img, int y0, int x0, int c0,
                                                  int nchunks, int warp_idx, int nwarps, int lane) {
-    const int planes = t.S * t.S;
+    const int planes = t.nplanes > 0 ? t.nplanes : t.S * t.S;
     const int sh_s = t.S >> 1;
     const T* src = reinterpret_cast<const T*>(t.ptr);
     const int row_items = t.Wl * nchunks;
