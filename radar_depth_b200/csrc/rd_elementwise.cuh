@@ -41,13 +41,15 @@ __device__ __forceinline__ T* vptr_w(const VView& v, size_t pix, int c) {
 template <typename T>
 __global__ void input_pack_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cs) {
     const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
-    const size_t total = (size_t)B * H2 * W2 * 4;      // one thread per (pixel, parity)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t total = (uint32_t)B * H2 * W2 * 4;      // one thread per (pixel, parity); launcher guarantees < 2^31
+    const FastDiv fdw((uint32_t)W2), fdh((uint32_t)H2);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int q = (int)(i & 3);
-        const size_t pix = i >> 2;
-        const int ox = (int)(pix % W2);
-        const int oy = (int)((pix / W2) % H2);
-        const int b = (int)(pix / ((size_t)W2 * H2));
+        const uint32_t pix = i >> 2;
+        const uint32_t prow = fdw.div(pix);
+        const int ox = (int)(pix - prow * W2);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * H2);
         const int iy = oy * 2 + (q >> 1), ix = ox * 2 + (q & 1);
         const bool ok = iy < H && ix < W;
         T* o = out + pix * (size_t)(4 * Cs) + q * Cs;
@@ -680,11 +682,13 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __re
 __global__ void bilinear_fwd_kernel(const float* __restrict__ in, int B, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
     const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
     const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-    const size_t total = (size_t)B * Ho * Wo;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % Wo);
-        const int oy = (int)((i / Wo) % Ho);
-        const int b = (int)(i / ((size_t)Wo * Ho));
+    const uint32_t total = (uint32_t)B * Ho * Wo;           // launcher guarantees < 2^31
+    const FastDiv fdw((uint32_t)Wo), fdh((uint32_t)Ho);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t prow = fdw.div(i);
+        const int ox = (int)(i - prow * Wo);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * Ho);
         const float sy = ry * oy, sx = rx * ox;
         const int y0 = (int)sy, x0 = (int)sx;
         const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
@@ -700,11 +704,13 @@ __global__ void bilinear_fwd_kernel(const float* __restrict__ in, int B, int Hi,
 __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, float* __restrict__ din, int Ho, int Wo) {
     const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
     const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-    const size_t total = (size_t)B * Hi * Wi;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ix = (int)(i % Wi);
-        const int iy = (int)((i / Wi) % Hi);
-        const int b = (int)(i / ((size_t)Wi * Hi));
+    const uint32_t total = (uint32_t)B * Hi * Wi;           // launcher guarantees < 2^31
+    const FastDiv fdw((uint32_t)Wi), fdh((uint32_t)Hi);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t prow = fdw.div(i);
+        const int ix = (int)(i - prow * Wi);
+        const int b = (int)fdh.div(prow);
+        const int iy = (int)(prow - (uint32_t)b * Hi);
         // candidate output rows: those with floor(ry*oy) in {iy-1, iy}
         int oy_lo, oy_hi, ox_lo, ox_hi;
         if (ry > 0.f) { oy_lo = max(0, (int)floorf((iy - 1) / ry) - 1); oy_hi = min(Ho - 1, (int)ceilf((iy + 1) / ry) + 1); }
