@@ -412,7 +412,7 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
                 continue
             # A tile of exactly KS = Ht*Wl slots lets the gradient tile be one dense TMA box (rd_conv_wgrad: TMA writes the
             # chunk planes of a box back to back, so a plane must not have a tail); such tiles are preferred.
-            tma_g = parts == 1 and g.OS == 1 and (Ht * Wl) % 16 == 0
+            tma_g = parts == 1 and (Ht * Wl) % 16 == 0 and Wl * g.OS <= 256
             KS = Ht * Wl if tma_g else KS0
             xrows = Ht + halo_y
             xslots = _round_up(KS + halo_y * Wl + halo_x, 8)

@@ -60,14 +60,16 @@ bool tma_enabled() {
     return v != 0;
 }
 // bf16 NHWC view [B][H][W][pitch] (channels coff .. coff+C) as the 5-D tensor (8, W, H, C/8, B); box (8, box_w, box_rows, 2, 1)
-bool encode_nhwc_map(CUtensorMap* map, const rd_view& v, int B, int H, int W, int C, int box_w, int box_rows, int box_chunks = 2) {
+// `step` = 2 loads every second pixel in both directions (one parity plane of a stride-2 operand): the box then spans
+// 2*box_w x 2*box_rows pixels of the tensor and still lands as box_w x box_rows slots.
+bool encode_nhwc_map(CUtensorMap* map, const rd_view& v, int B, int H, int W, int C, int box_w, int box_rows, int box_chunks = 2, int step = 1) {
     TmapEncodeFn enc = tmap_encoder();
-    if (!enc || box_w > 256 || box_rows > 256 || box_chunks > 256 || C % 8) return false;
+    if (!enc || box_w * step > 256 || box_rows * step > 256 || box_chunks > 256 || C % 8) return false;
     const cuuint64_t pitch_b = (cuuint64_t)v.pitch * 2;
     cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)B};
     cuuint64_t strides[4] = {pitch_b, (cuuint64_t)W * pitch_b, 16, (cuuint64_t)H * W * pitch_b};
-    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {8, (cuuint32_t)(box_w * step), (cuuint32_t)(box_rows * step), (cuuint32_t)box_chunks, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)step, (cuuint32_t)step, 1, 1};
     void* base = (void*)((char*)v.ptr + (size_t)v.coff * 2);
     if (((uintptr_t)base & 15) || (pitch_b & 15)) return false;
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         // signalled with one ordinary arrival per warp.  The generic->async proxy fence is executed by the consumer
         // (UMMA warp) after it has observed full[stage]: a producer-side fence would have to drain the copies.
         const int widx = any_tma ? warp - 5 : warp - 4;
-        const uint32_t g_tx = (uint32_t)(p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)(p.Wl * p.x_plane_rows * x_chunks * 16);
+        const int g_planes = p.Sg * p.Sg;
+        const uint32_t g_tx = (uint32_t)(g_planes * p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)(p.Wl * p.x_plane_rows * x_chunks * 16);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -134,7 +135,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     uint64_t* bar = hop ? &tma_full[st.stage] : &full[st.stage];
                     if (!(p.dbg_flags & 2)) {
                         mbar_arrive_expect_tx(bar, (g_tma ? g_tx : 0u) + (x_tma ? x_tx : 0u));
-                        if (g_tma) tma_load_5d(sbase, &g_map, 0, x0, y0, co0 >> 3, img, bar);
+                        if (g_tma) {
+                            for (int q = 0; q < g_planes; ++q)       // parity plane (py, px) of a stride-2 gradient: every 2nd pixel
+                                tma_load_5d(sbase + (size_t)q * g_chunks * p.KS * 16, &g_map, 0, x0 * p.Sg + (q & (p.Sg - 1)),
+                                            y0 * p.Sg + (q >> (p.Sg >> 1)), co0 >> 3, img, bar);
+                        }
                         if (x_tma) tma_load_5d(sbase + p.g_bytes, &x_map, 0, x0 + p.sx_min, y0 + p.sy_min, ci0 >> 3, img, bar);
                     } else {
                         mbar_arrive(bar);
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             if (g_tma) {
                 // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
                 const int jc = p.Wl - p.Wt;
-                const int items = p.Ht * jc * g_chunks;
+                const int items = p.Ht * jc * g_chunks * g_planes;       // planes and chunk planes are all KS slots apart
                 const FastDiv fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
                 for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
                     const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
