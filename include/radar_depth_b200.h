@@ -192,6 +192,13 @@ typedef struct rd_wgrad_params {
     long long* dbg;              /* optional [4][gridDim.x*y*z] cycle counters (loader wait/fill, issuer wait/issue); NULL = off */
     int32_t dbg_flags;           /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging */
     int32_t x_planes;            /* Sx = 2: parity planes of the source the taps read, from plane 0 on (0 = all four) */
+    /* Tap-row folding for 16-channel sources (Nc = Cin = 16, Sx = 1, one tap group): the taps form fold_rows rows of
+     * fold_len (<= 4) horizontally adjacent taps (taps[r*fold_len + i].x_shift = taps[r*fold_len].x_shift + i).  One UMMA
+     * then covers a whole row for one 8-channel chunk: its B operand is that chunk plane with an MN-chunk stride of ONE
+     * slot, i.e. N = 4 taps x 8 channels = 32 (a 4th tap of a 3-tap row is junk and ignored).  fold_rows*2 UMMAs of N=32
+     * per 16 pixels instead of ntaps UMMAs of N=16 -- small-N UMMAs cost ~40 cycles whatever N is.  0 = off. */
+    int32_t fold_rows, fold_len;
+    int32_t pad2_;
 } rd_wgrad_params;
 
 int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);

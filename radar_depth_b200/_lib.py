@@ -82,6 +82,7 @@ class WgradParams(C.Structure):
         ("Mc", C.c_int32), ("ncob", C.c_int32), ("Nc", C.c_int32), ("ncib", C.c_int32),
         ("dw", C.c_void_p), ("NS", C.c_int32), ("stage_bytes", C.c_int32), ("g_bytes", C.c_int32),
         ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("x_planes", C.c_int32),
+        ("fold_rows", C.c_int32), ("fold_len", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 

@@ -415,7 +415,7 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
             tma_g = parts == 1 and (Ht * Wl) % 16 == 0 and Wl * g.OS <= 256
             KS = Ht * Wl if tma_g else KS0
             xrows = Ht + halo_y
-            xslots = _round_up(KS + halo_y * Wl + halo_x, 8)
+            xslots = _round_up(KS + halo_y * Wl + halo_x + (4 if g.Cx == 16 else 0), 8)     # + the junk 4th tap of a folded row
             GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
             XPS = _chunk_stride(g.S * g.S * xslots, Nc // 8)
             g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
@@ -497,6 +497,15 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     p.NS, p.stage_bytes, p.g_bytes = NS, geo["stage"], geo["g_bytes"]
     p.act_dtype = act_dtype
     p.x_planes = 1 if (g.S == 2 and all(t.pl == (0, 0) for t in taps)) else 0
+    # tap-row folding (rd_wgrad_params.fold_rows): 16-channel stride-1 sources whose taps form full rows of <= 4 adjacent taps
+    p.fold_rows, p.fold_len = 0, 0
+    if parts == 1 and g.Cx == 16 and Nc == 16 and g.S == 1 and g.OS == 1 and ntg == 1 and os.environ.get("RD_WGRAD_FOLD", "1") != "0":
+        rows = sorted({t.s[0] for t in taps})
+        cols = sorted({t.s[1] for t in taps})
+        full = len(rows) * len(cols) == ntaps and cols == list(range(cols[0], cols[0] + len(cols))) and \
+            [t.s for t in taps] == [(r, c) for r in rows for c in cols]
+        if full and 2 <= len(cols) <= 4 and len(rows) * 64 <= 512:
+            p.fold_rows, p.fold_len = len(rows), len(cols)
     ntiles = geo["tiles_y"] * geo["tiles_x"] * B
     ctas_other = ncob * ncib * ntg
     # one resident wave: every extra wave pays the CTA prologue (TMEM alloc, ring zero-fill) and the final fp32

@@ -217,8 +217,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         {
             const bool leader = elect_one_sync();
             PipeState st(p.NS);
-            const uint32_t idesc = make_idesc_bf16(128, p.Nc, 1, 1);
-            const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = (uint32_t)XPS * 16u;
+            // tap-row folding (see rd_wgrad_params.fold_rows): a job = one row of taps x one 8-channel source chunk
+            const bool fold = (SPLIT == 1) && p.fold_len > 0;
+            const int njobs = fold ? p.fold_rows * x_chunks : T_n;
+            const uint32_t idesc = make_idesc_bf16(128, fold ? 32 : p.Nc, 1, 1);
+            const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = fold ? 16u : (uint32_t)XPS * 16u;
             const int KG = p.KS >> 4;
             bool first_tile = true;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -233,10 +236,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 const uint64_t db0 = make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
                 // tap-outer / k-group-inner: inside the inner loop the descriptors only advance by 16 slots, so one
                 // UMMA costs two uniform adds; the tap offsets come from the (uniform) parameter bank once per tap
-                for (int tl = 0; tl < T_n; ++tl) {
-                    const uint32_t d = tmem_u + (uint32_t)(tl * p.Nc);
+                for (int jb = 0; jb < njobs; ++jb) {
+                    const int tl = fold ? (jb >> 1) * p.fold_len : jb;                 // x_chunks == 2 when folding
+                    const uint32_t d = tmem_u + (uint32_t)(fold ? jb * 32 : jb * p.Nc);
                     uint64_t da = da0 + (uint32_t)p.taps[t0 + tl].g_off;
-                    uint64_t db = db0 + (uint32_t)p.taps[t0 + tl].x_shift;
+                    uint64_t db = db0 + (uint32_t)p.taps[t0 + tl].x_shift + (uint32_t)(fold ? (jb & 1) * XPS : 0);
                     if (leader && !(p.dbg_flags & 1)) {
                         umma_bf16(d, da, db, idesc, first_tile ? 0u : 1u);
                         if (SPLIT == 3) {
@@ -279,6 +283,28 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tc_fence_after();
         const int row = warp * 32 + lane;                 // output channel within the block
         const bool valid = has_work && row < p.Mc && (co0 + row) < p.Cout;
+        if ((SPLIT == 1) && p.fold_len > 0) {
+            // folded accumulators: job (row, chunk jx) holds columns [tap-in-row][8 channels of chunk jx]
+            const int njobs = p.fold_rows * x_chunks;
+            for (int jb = 0; jb < njobs; ++jb) {
+                const int rowi = jb >> 1, jx = jb & 1;
+                for (int cc = 0; cc < 2; ++cc) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(jb * 32 + cc * 16), v);
+                    if (valid) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int tx = cc * 2 + h;
+                            if (tx < p.fold_len) {
+                                float* out = p.dw + ((size_t)(rowi * p.fold_len + tx) * p.Cout + (co0 + row)) * p.Cin + ci0 + jx * 8;
+                                red_add_v4(out, v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
+                                red_add_v4(out + 4, v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         for (int tl = 0; tl < T_n; ++tl) {
             float* out = p.dw + ((size_t)(t0 + tl) * p.Cout + (co0 + row)) * p.Cin + ci0;
             for (int cc = 0; cc < (p.Nc >> 4); ++cc) {
