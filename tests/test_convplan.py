@@ -119,3 +119,40 @@ def test_plans_are_self_consistent(dtype):
         q = wp.params
         assert q.tg_size * q.Nc <= 512 and cp.WGRAD_HEADER + q.NS * q.stage_bytes + wp.info['geo']['pad'] <= cp.SMEM_BUDGET, name
         assert len(set(wp.scatter[0].tolist())) == wp.scatter[0].size       # each parameter has one source
+
+
+def test_wgrad_planner_folds_tap_rows_of_16_channel_sources():
+    """rd_wgrad_params.fold_rows/fold_len: 16-channel stride-1 sources whose taps form full rows of <= 4 adjacent taps
+    (3x3 convs of the depth branch / decoder layer 4, the fused 4x4 stem) get one N=32 UMMA per tap row and chunk."""
+    g = cp.gconv_standard(0, 16, 16, 3, 1, 1)
+    w = cp.plan_wgrad(g, 2, (24, 40), (24, 40))
+    assert (w.params.fold_rows, w.params.fold_len) == (3, 3) and w.params.Nc == 16 and w.params.ntg == 1
+    taps = [w.params.taps[i] for i in range(w.params.ntaps)]
+    for r in range(3):
+        for i in range(3):
+            assert taps[3 * r + i].x_shift == taps[3 * r].x_shift + i and taps[3 * r + i].g_off == taps[3 * r].g_off
+        # the junk 4th tap of a row still reads inside the staged source plane
+        assert taps[3 * r].x_shift + 3 + w.params.KS <= w.params.x_plane_slots
+    s = cp.gconv_stem(0, 10 ** 6, 1)
+    ws = cp.plan_wgrad(s, 2, (32, 48), (32, 48))
+    assert (ws.params.fold_rows, ws.params.fold_len) == (4, 4)
+    # wider sources, strided sources and the fp32 parity mode are not folded
+    assert cp.plan_wgrad(cp.gconv_standard(0, 32, 32, 3, 1, 1), 2, (24, 40), (24, 40)).params.fold_len == 0
+    assert cp.plan_wgrad(cp.gconv_standard(0, 32, 16, 3, 2, 1), 2, (24, 40), (12, 20)).params.fold_len == 0
+    assert cp.plan_wgrad(g, 2, (24, 40), (24, 40), _lib.RD_F32).params.fold_len == 0
+
+
+def test_planner_stages_one_parity_plane_for_1x1_stride2():
+    g = cp.gconv_standard(0, 128, 64, 1, 2, 0)
+    assert cp.plan_fprop(g, 2, (24, 40), (12, 20)).params.src_planes == 1
+    assert cp.plan_wgrad(g, 2, (24, 40), (12, 20)).params.x_planes == 1
+    g3 = cp.gconv_standard(0, 128, 64, 3, 2, 1)
+    assert cp.plan_fprop(g3, 2, (24, 40), (12, 20)).params.src_planes == 0
+    assert cp.plan_wgrad(g3, 2, (24, 40), (12, 20)).params.x_planes == 0
+
+
+def test_wgrad_planner_prefers_tiles_that_are_one_dense_tma_box():
+    """KS == Ht*Wl (no tail in a chunk plane) is what lets rd_conv_wgrad stage the gradient tile with one TMA box."""
+    for co, ci, hw in ((128, 128, (44, 152)), (256, 256, (22, 76)), (512, 512, (11, 38))):
+        w = cp.plan_wgrad(cp.gconv_standard(0, co, ci, 3, 1, 1), 16, hw, hw, use_tuned=False)
+        assert w.params.KS == w.params.Ht * w.params.Wl and w.params.KS % 16 == 0, (co, w.info)
