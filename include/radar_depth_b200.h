@@ -255,6 +255,14 @@ int rd_smoothness_fwd(const float* pred, const float* image, int B, int C, int H
 int rd_smoothness_bwd(const float* pred, const float* image, int B, int C, int H, int W, double* scratch,
                       const float* gout, float* gpred, int accumulate, void* stream);
 
+/* Result.evaluate / Result_multidist.evaluate (evaluation/metrics.py:34-58,91-140): all masked error statistics of one
+ * prediction in ONE pass and one device->host copy (the reference does ~10 boolean gathers and host syncs per call,
+ * every training iteration, main.py:450-458).  Pixels with target > 0 and lo <= target <= hi count (lo = 0, hi = +inf for
+ * Result).  acc = RD_METRIC_SLOTS doubles, zeroed by the call: count, sum d^2, sum |d|, sum |log10 o - log10 t|,
+ * sum |d|/t, #(max(o/t,t/o) < 1.25), # < 1.25^2, # < 1.25^3, sum (1/o - 1/t)^2, sum |1/o - 1/t|. */
+#define RD_METRIC_SLOTS 10
+int rd_depth_metrics(const float* output, const float* target, long long n, float lo, float hi, double* acc, void* stream);
+
 /* Filter_layer (multistage_model.py:87-119). */
 int rd_sid_filter(const float* radar, const float* depth, long long n, float* radar_f, float* mask, void* stream);
 

@@ -57,7 +57,8 @@ def import_reference():
     models = importlib.import_module("model.models")
     multistage = importlib.import_module("model.multistage_model")
     criteria = importlib.import_module("evaluation.criteria_new")
-    return types.SimpleNamespace(models=models, multistage=multistage, criteria=criteria)
+    metrics = importlib.import_module("evaluation.metrics")
+    return types.SimpleNamespace(models=models, multistage=multistage, criteria=criteria, metrics=metrics)
 
 
 def _subsample(t: torch.Tensor, step: int = 8) -> np.ndarray:
@@ -155,6 +156,26 @@ def run_losses(ref):
             "radar_filtered": rf.numpy(), "mask": mask.numpy()}
 
 
+_METRIC_FIELDS = ("mse", "rmse", "mae", "lg10", "absrel", "delta1", "delta2", "delta3", "irmse", "imae")
+
+
+def run_metrics(ref):
+    """Result.evaluate and Result_multidist.evaluate of the real reference (evaluation/metrics.py) on a seeded pair."""
+    g = torch.Generator().manual_seed(11)
+    tgt = torch.rand(2, 1, 48, 80, generator=g) * 110
+    tgt[torch.rand(2, 1, 48, 80, generator=g) < 0.6] = 0
+    out = (tgt * (0.7 + 0.6 * torch.rand(2, 1, 48, 80, generator=g)) + torch.rand(2, 1, 48, 80, generator=g) * 3 + 0.5)
+    r = ref.metrics.Result()
+    r.evaluate(out, tgt)
+    md = ref.metrics.Result_multidist()
+    md.evaluate(out, tgt)
+    res = {"output": out.numpy(), "target": tgt.numpy(),
+           "result": np.array([getattr(r, k) for k in _METRIC_FIELDS], dtype=np.float64),
+           "multidist": np.array([[getattr(x, k) for k in _METRIC_FIELDS] for x in md.result_lst], dtype=np.float64),
+           "valid_label": np.array(md.valid_label, dtype=np.int64), "l1": np.float64(r.mae)}
+    return res
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     ref = import_reference()
@@ -167,8 +188,12 @@ def main():
         "latefusion_train_b2_352x1216": lambda: run_latefusion(ref, 2, 352, 1216, full_pred=False),
         "multistage_fixs_train_b2_64x96": lambda: run_multistage(ref, 2, 64, 96),
         "losses_filter": lambda: run_losses(ref),
+        "metrics": lambda: run_metrics(ref),
     }
+    only = sys.argv[1:]
     for name, fn in jobs.items():
+        if only and name not in only:
+            continue
         out = fn()
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
         print(f"[golden] {name}: loss={out.get('loss', out.get('l1'))}")

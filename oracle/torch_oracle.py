@@ -336,3 +336,21 @@ def sgd_step(sd, grads, momentum_buf: Optional[dict], lr=0.01, momentum=0.9, wei
         new_buf[k] = buf
         new_sd[k] = p - lr * buf
     return new_sd, new_buf
+
+
+def depth_metrics(output: Tensor, target: Tensor, lo: float = 0.0, hi: float = float("inf")) -> Dict[str, float]:
+    """evaluation/metrics.py:34-58 (Result.evaluate) and :91-140 (one interval of Result_multidist.evaluate):
+    statistics over the pixels with target > 0 and lo <= target <= hi.  Means of an empty selection are NaN."""
+    import math
+    m = (target > 0) & (target >= lo) & (target <= hi)
+    o, t = output[m], target[m]
+    d = (o - t).abs()
+    ratio = torch.max(o / t, t / o)
+    di = (1 / o - 1 / t).abs()
+    mse = float((d ** 2).mean())
+    return dict(mse=mse, rmse=math.sqrt(mse) if mse == mse else float("nan"), mae=float(d.mean()),
+                lg10=float((torch.log(o) / math.log(10) - torch.log(t) / math.log(10)).abs().mean()),
+                absrel=float((d / t).mean()), delta1=float((ratio < 1.25).float().mean()),
+                delta2=float((ratio < 1.25 ** 2).float().mean()), delta3=float((ratio < 1.25 ** 3).float().mean()),
+                irmse=math.sqrt(float((di ** 2).mean())) if o.numel() else float("nan"), imae=float(di.mean()),
+                count=int(m.sum()))

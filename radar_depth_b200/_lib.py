@@ -113,6 +113,7 @@ _PROTOS = {
     "rd_l1_bwd": ([_P, _P, _LL, _P, _P, _P, _I, _P], _I),
     "rd_smoothness_fwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     "rd_smoothness_bwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P], _I),
+    "rd_depth_metrics": ([_P, _P, _LL, _F, _F, _P, _P], _I),
     "rd_sid_filter": ([_P, _P, _LL, _P, _P, _P], _I),
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),

@@ -745,6 +745,50 @@ __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int H
 }
 
 // ------------------------------------------------------------------------------------------------
+// depth_metrics: evaluation/metrics.py:34-58 (Result.evaluate) as one masked multi-reduction.  Element math in fp32 like
+// the reference, sums in fp64.
+__global__ void depth_metrics_kernel(const float* __restrict__ output, const float* __restrict__ target, size_t n, float lo, float hi,
+                                     double* acc) {
+    double s[RD_METRIC_SLOTS];
+#pragma unroll
+    for (int i = 0; i < RD_METRIC_SLOTS; ++i) s[i] = 0.0;
+    const float kInvLn10 = 0.43429448190325176f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = target[i];
+        if (!(t > 0.f) || !(t >= lo) || !(t <= hi)) continue;
+        const float o = output[i];
+        const float d = fabsf(o - t);
+        const float ratio = fmaxf(o / t, t / o);
+        const float di = fabsf(1.f / o - 1.f / t);
+        s[0] += 1.0;
+        s[1] += (double)(d * d);
+        s[2] += (double)d;
+        s[3] += (double)fabsf(logf(o) * kInvLn10 - logf(t) * kInvLn10);
+        s[4] += (double)(d / t);
+        s[5] += ratio < 1.25f ? 1.0 : 0.0;
+        s[6] += ratio < 1.5625f ? 1.0 : 0.0;
+        s[7] += ratio < 1.953125f ? 1.0 : 0.0;
+        s[8] += (double)(di * di);
+        s[9] += (double)di;
+    }
+    __shared__ double red[RD_METRIC_SLOTS][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < RD_METRIC_SLOTS; ++i) {
+        double v = s[i];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < RD_METRIC_SLOTS) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        atomicAdd(&acc[threadIdx.x], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MaskedL1Loss (criteria_new.py:44-54): mean |target - pred| over target > 0.  No boolean gather, no host sync:
 // acc[0] += sum, acc[1] += count (fp64), then a 1-thread finalize writes the fp32 scalar.
 __global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* acc) {

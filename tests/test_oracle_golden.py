@@ -118,3 +118,22 @@ def test_key_order_and_shapes_match_live_reference():
     for k, (shape, _) in ent.items():
         assert tuple(sd[k].shape) == tuple(shape), k
     assert len(O.multistage_entries()) == 652
+
+
+_METRIC_FIELDS = ("mse", "rmse", "mae", "lg10", "absrel", "delta1", "delta2", "delta3", "irmse", "imae")
+
+
+def test_depth_metrics_match_reference_golden(golden_dir):
+    """oracle.depth_metrics against Result.evaluate / Result_multidist.evaluate of the real reference
+    (evaluation/metrics.py, golden written by oracle/gen_golden.py)."""
+    g = _load(golden_dir, "metrics")
+    out, tgt = torch.from_numpy(g["output"]), torch.from_numpy(g["target"])
+    r = O.depth_metrics(out, tgt)
+    np.testing.assert_allclose([r[k] for k in _METRIC_FIELDS], g["result"], rtol=1e-6, atol=1e-9)
+    edges = [10., 20., 30., 40., 50., 60., 70., 80., 90., 100.]
+    for i in range(10):
+        lo = 0.0 if i == 0 else edges[i - 1]
+        hi = float("inf") if i == 9 else edges[i]
+        ri = O.depth_metrics(out, tgt, lo, hi)
+        np.testing.assert_allclose([ri[k] for k in _METRIC_FIELDS], g["multidist"][i], rtol=1e-6, atol=1e-9, equal_nan=True)
+        assert (ri["count"] > 0) == bool(g["valid_label"][i])
