@@ -214,6 +214,10 @@ int rd_bn_finalize(const double* sum, const double* sumsq, double count, const f
                    float* running_mean, float* running_var, long long* num_batches_tracked, int C, int training,
                    float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                    void* stream);
+/* Eval-mode finalisation of MANY BatchNorm layers in one launch (inference: scale/shift only depend on the parameters and
+ * the running statistics).  table = n rows of 9 device words (int64): gamma, beta, running_mean, running_var, scale,
+ * shift, save_mean, save_invstd (pointers) and C. */
+int rd_bn_finalize_eval_multi(const long long* table, int n, float eps, void* stream);
 /* BatchNorm2d backward reductions -> dgamma/dbeta (accumulated) and dz = A*g + B*z + C coefficients. */
 int rd_bn_bwd_finalize(const double* sum_g, const double* sum_gz, double count, const float* gamma,
                        const float* save_mean, const float* save_invstd, int C, int training, float* dgamma,

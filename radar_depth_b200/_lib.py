@@ -98,6 +98,7 @@ _PROTOS = {
     "rd_conv_wgrad": ([C.POINTER(WgradParams), _P], _I),
     "rd_input_pack": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "rd_bn_finalize": ([_P, _P, _D, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P], _I),
+    "rd_bn_finalize_eval_multi": ([_P, _I, _F, _P], _I),
     "rd_bn_bwd_finalize": ([_P, _P, _D, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "rd_bn_add_act": ([View, _P, _P, View, _P, _P, View, _LL, _I, _F, _I, _P], _I),
     "rd_join_bwd": ([View, View, View, View, View, _LL, _I, _F, _P, _P, _P, C.POINTER(BnTail), _I, _P], _I),

@@ -94,6 +94,28 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
     save_invstd[c] = invstd;
 }
 
+// eval-mode finalisation of many BatchNorm layers: block b handles row b of the pointer table
+__global__ void bn_finalize_eval_multi_kernel(const long long* __restrict__ table, float eps) {
+    const long long* row = table + (size_t)blockIdx.x * 9;
+    const float* gamma = reinterpret_cast<const float*>(row[0]);
+    const float* beta = reinterpret_cast<const float*>(row[1]);
+    const float* rm = reinterpret_cast<const float*>(row[2]);
+    const float* rv = reinterpret_cast<const float*>(row[3]);
+    float* scale = reinterpret_cast<float*>(row[4]);
+    float* shift = reinterpret_cast<float*>(row[5]);
+    float* save_mean = reinterpret_cast<float*>(row[6]);
+    float* save_invstd = reinterpret_cast<float*>(row[7]);
+    const int C = (int)row[8];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mean = rm[c], invstd = rsqrtf(rv[c] + eps);
+        const float sc = gamma[c] * invstd;
+        scale[c] = sc;
+        shift[c] = beta[c] - mean * sc;
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+    }
+}
+
 // bn_bwd_finalize: from sum(g), sum(g*z) -> dgamma, dbeta (accumulated into the gradient arena) and the three
 // coefficients of dz = A*g + Bz*z + Cc  (autograd of nn.BatchNorm2d in training mode).
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gz, double count,

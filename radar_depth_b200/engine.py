@@ -276,14 +276,16 @@ class LatefusionEngine:
                 jobs.append(j)
             return jobs
 
+        self._bn_eval_rows: List[List[int]] = []
+
         def emit_bn_eval(grp: BNGroup, count: float):
+            # eval mode: scale/shift depend only on parameters and running statistics -> every BatchNorm of the network is
+            # finalised by ONE launch at the head of the eval program (rd_bn_finalize_eval_multi, table built below)
             for (name, c0, Cn) in grp.members:
                 rm, rv, nbt = bn_buffers(name)
                 go, bo = o[name + ".weight"], o[name + ".bias"]
-                self.fwd_eval.append(Launch("bn_fin_eval:" + name, lib.rd_bn_finalize,
-                                            (None, None, float(count), _p(self.flat, go), _p(self.flat, bo), _p(rm), _p(rv),
-                                             None, Cn, 0, BN_MOMENTUM, BN_EPS, _p(grp.scale, c0), _p(grp.shift, c0),
-                                             _p(grp.mean, c0), _p(grp.invstd, c0))))
+                self._bn_eval_rows.append([_p(self.flat, go), _p(self.flat, bo), _p(rm), _p(rv), _p(grp.scale, c0),
+                                           _p(grp.shift, c0), _p(grp.mean, c0), _p(grp.invstd, c0), Cn])
 
         def bwd_job(grp: BNGroup, midx: int, sum_g_ptr: int, sum_gz_ptr: int, count: float):
             name, c0, Cn = grp.members[midx]
@@ -543,6 +545,9 @@ class LatefusionEngine:
         pack = Launch("pack_weights", lib.rd_pack_weights, (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel()))
         self.fwd.insert(0, pack)
         self.fwd_eval.insert(0, pack)
+        self.bn_eval_table = self.hold(torch.tensor(self._bn_eval_rows, dtype=torch.int64, device=self.device))
+        self.fwd_eval.insert(1, Launch("bn_fin_eval_all", lib.rd_bn_finalize_eval_multi,
+                                       (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams)))
         self.stats_used = self.stats[:self._stats_used]
         self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd)

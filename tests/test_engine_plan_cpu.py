@@ -16,7 +16,7 @@ def test_engine_plans_every_program(cin, hw, b, act):
     eng = LatefusionEngine(m, cin, hw, act)
     eng.adopt("cpu")
     eng.configure(b, *hw)
-    assert len(eng.fwd) == 74 and len(eng.fwd_eval) == 128     # training: BatchNorm finalisation rides in the conv tails
+    assert len(eng.fwd) == 74 and len(eng.fwd_eval) == 75      # training: BN finalisation rides in the conv tails; eval: one batched launch
     assert len(eng.bwd) == (175 if cin > 4 else 174)
     names = [L.name for L in eng.fwd]
     assert names[0] == "pack_weights" and names[-1] == "bilinear"
