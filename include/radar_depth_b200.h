@@ -276,6 +276,13 @@ int rd_pack_weights(const float* src, const int32_t* idx, void* out, long long n
 int rd_unpack_grads(const float* dw, const int32_t* idx, float* grad, long long n, void* stream);
 int rd_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first, void* stream);
 
+/* Graph cut at the bottleneck: ResNet_latefusion.pnp_forward_front returns bn2's output, pnp_forward_rear consumes it
+ * (models.py:669-707).  export: NHWC activation slice -> NCHW fp32 through an optional per-channel affine (sc/sh both
+ * NULL = plain copy; used for the bottleneck feature and for its gradient); import: NCHW fp32 -> NHWC slice. */
+int rd_feature_export(rd_view z, const float* sc, const float* sh, float* out_nchw, int B, int H, int W, int C, int act_dtype,
+                      void* stream);
+int rd_feature_import(const float* x_nchw, rd_view z, int B, int H, int W, int C, int act_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

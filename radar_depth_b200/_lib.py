@@ -119,6 +119,8 @@ _PROTOS = {
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),
     "rd_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _I, _P], _I),
+    "rd_feature_export": ([View, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "rd_feature_import": ([_P, View, _I, _I, _I, _I, _I, _P], _I),
 }
 EXPORTS = tuple(_PROTOS.keys()) + ("rd_last_error",)
 

@@ -973,4 +973,44 @@ __global__ void smoothness_kernel(const float* __restrict__ d, const float* __re
 }
 __global__ void smoothness_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] + acc[1]); }
 
+// feature_export: NHWC activation slice -> NCHW fp32, optionally through a per-channel affine (the BatchNorm that the
+// next conv would have applied on load).  feature_import: NCHW fp32 -> NHWC activation slice.  Used where the graph is
+// cut at the bottleneck (ResNet_latefusion.pnp_forward_front / pnp_forward_rear, models.py:669-707): 256 x 11 x 38 per
+// image, so one thread per 8-channel group of a pixel (16-byte NHWC access, pixel-contiguous NCHW access per channel).
+template <typename T>
+__global__ void feature_export_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, float* __restrict__ out,
+                                      int B, int HW, int C) {
+    const int groups = C >> 3;
+    const uint32_t total = (uint32_t)B * (uint32_t)HW * (uint32_t)groups;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // pixel-fastest thread order: the eight NCHW stores of a warp are 128 contiguous bytes each
+        const uint32_t p = i % (uint32_t)HW;
+        const uint32_t r = i / (uint32_t)HW;
+        const int c = (int)(r % (uint32_t)groups) * 8;
+        const uint32_t b = r / (uint32_t)groups;
+        float v[8];
+        Act<T>::load8(vptr<T>(z, (size_t)b * HW + p, c), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float y = sc ? fmaf(v[k], sc[c + k], sh[c + k]) : v[k];
+            out[((size_t)b * C + c + k) * HW + p] = y;
+        }
+    }
+}
+template <typename T>
+__global__ void feature_import_kernel(const float* __restrict__ x, VView z, int B, int HW, int C) {
+    const int groups = C >> 3;
+    const uint32_t total = (uint32_t)B * (uint32_t)HW * (uint32_t)groups;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t p = i % (uint32_t)HW;
+        const uint32_t r = i / (uint32_t)HW;
+        const int c = (int)(r % (uint32_t)groups) * 8;
+        const uint32_t b = r / (uint32_t)groups;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = x[((size_t)b * C + c + k) * HW + p];
+        Act<T>::store8(vptr_w<T>(z, (size_t)b * HW + p, c), v);
+    }
+}
+
 }  // namespace rd

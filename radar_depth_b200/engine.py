@@ -386,6 +386,10 @@ class LatefusionEngine:
         zc2 = self.act(B, h32, w32, 256)
         bc2 = BNGroup(self, [("bn2", 0, 256)])
         emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2, nf)
+        # graph cut of pnp_forward_front / pnp_forward_rear (models.py:669-707): everything up to here is the "front"
+        split_f, split_fe = len(self.fwd), len(self.fwd_eval)
+        self.bneck = self.hold(torch.zeros(B, 256, h32, w32, dtype=torch.float32, device=self.device))
+        self.d_bneck = self.hold(torch.zeros(B, 256, h32, w32, dtype=torch.float32, device=self.device))
 
         # ---- decoder (UpProj x4)
         dec = []
@@ -462,6 +466,7 @@ class LatefusionEngine:
                 g_c2 = self.act(B, h32, w32, 256)
                 emit_conv(bw, L["up"], "d", _v(dzcat), _v(g_c2), epi=1, zsrc=_v(zc2), ep=(bc2.scale, bc2.shift, 1.0),
                           stats=bc2.bstats[:2], tail=new_tail([bwd_job(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)], 3, bc2.C))
+                split_b = len(bw)          # g_c2 = d(loss)/d(bn2 output) here (slope 1: the activation mask is the identity)
         npf = int(B * h32 * w32)
         bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
                          (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act)))
@@ -550,7 +555,18 @@ class LatefusionEngine:
                                        (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams)))
         self.stats_used = self.stats[:self._stats_used]
-        self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd)
+        # programs of the graph cut (pack_weights / bn_fin_eval_all were inserted at the heads above)
+        exp = Launch("feature_export", lib.rd_feature_export,
+                     (_v(zc2), _p(bc2.scale), _p(bc2.shift), _p(self.bneck), B, h32, w32, 256, act))
+        imp = Launch("feature_import", lib.rd_feature_import, (_p(self.bneck), _v(zc2), B, h32, w32, 256, act))
+        self.front = self.fwd[:split_f + 1] + [exp]
+        self.front_eval = self.fwd_eval[:split_fe + 2] + [exp]
+        self.rear = [pack, imp] + self.fwd[split_f + 1:]
+        self.rear_eval = self.fwd_eval[:2] + [imp] + self.fwd_eval[split_fe + 2:]
+        self.rear_bwd = bw[:split_b] + [Launch("feature_export(grad)", lib.rd_feature_export,
+                                               (_v(g_c2), None, None, _p(self.d_bneck), B, h32, w32, 256, act))]
+        self.bc2 = bc2
+        self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd, h32=h32, w32=w32)
         self.dec, self.blocks_all = dec, blocks_all
         self.dbg = dict(z_stem=z_stem, gz_stem=gz_stem, p_rgb=p_rgb, p_d=p_d, amax=amax, xs=xs, concat=concat, d_concat=d_concat,
                         zf=zf, zc2=zc2, g_stem=g_stem)
@@ -583,7 +599,58 @@ class LatefusionEngine:
 
     def _bwd_body(self):
         self.dw.zero_()
+        # backward statistics and tail tickets start from zero in EVERY backward (the forward's own sums were consumed
+        # by its tails), so a second backward over the same forward (retain_graph) accumulates correctly
+        self.stats_used.zero_()
         self._run(self.bwd)
+
+    # ------------------------------------------------------------------ graph cut at the bottleneck (models.py:669-707)
+    # PnP-Depth refinement runs the front once, then iterates the rear (forward + gradient w.r.t. the bottleneck feature).
+    # These run eagerly (no CUDA graph): they are API surface, main.py never calls them.
+    def forward_front(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        B, Cc, H, W = x.shape
+        assert Cc == self.in_channels, (Cc, self.in_channels)
+        if not self.params_adopted():
+            self.adopt(x.device)
+        self.configure(B, H, W)
+        self.x_in.copy_(x)
+        if training:
+            self.stats_used.zero_()
+        self._run(self.front if training else self.front_eval)
+        return self.bneck
+
+    def forward_rear(self, feat: torch.Tensor, training: bool, image_hw=None) -> torch.Tensor:
+        B, Cc, h, w = feat.shape
+        if Cc != 256:
+            raise _lib.RdError(f"pnp_forward_rear expects the 256-channel bn2 output, got {Cc} channels")
+        if not self.params_adopted():
+            self.adopt(feat.device)
+        if self.cfg is None or (self.cfg["B"], self.cfg["h32"], self.cfg["w32"]) != (B, h, w):
+            H, W = image_hw if image_hw is not None else self.output_size     # the feature alone does not determine H, W
+            self.configure(B, H, W)
+            if (self.cfg["h32"], self.cfg["w32"]) != (h, w):
+                raise _lib.RdError(f"pnp_forward_rear: a {h}x{w} feature does not belong to a {H}x{W} image "
+                                   f"(expected {self.cfg['h32']}x{self.cfg['w32']})")
+        self.bneck.copy_(feat)
+        if training:
+            self.stats_used.zero_()
+        prog = self.rear if training else self.rear_eval
+        head = 2 if training else 3
+        self._run(prog[:head])             # pack_weights (+ eval: every BatchNorm's running-stat vectors), feature_import
+        # the decoder's first conv applies bn2 on load in the full graph; here its input already IS bn2's output
+        self.bc2.scale.fill_(1.0)
+        self.bc2.shift.zero_()
+        self._run(prog[head:])
+        return self.pred
+
+    def backward_rear(self, dpred: torch.Tensor) -> torch.Tensor:
+        """d(loss)/d(feature) of the last forward_rear (training-mode BatchNorm semantics, like autograd through the
+        reference's decoder); the decoder's parameter gradients are not produced on this path."""
+        self.dpred.copy_(dpred.reshape(self.dpred.shape))
+        self.dw.zero_()
+        self.stats_used.zero_()
+        self._run(self.rear_bwd)
+        return self.d_bneck
 
     def backward(self, dpred: torch.Tensor, accumulate: bool) -> None:
         """Fills the gradient arena from d(loss)/d(pred).  ``accumulate`` keeps what is already there."""
