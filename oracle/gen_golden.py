@@ -107,6 +107,25 @@ def run_latefusion(ref, b, h, w, seed_sd=7, in_channels=4, training=True, full_p
     return out
 
 
+def run_pnp(ref, b, h, w, training, seed_sd=7):
+    """pnp_forward_front / pnp_forward_rear of the real reference (models.py:669-707) and the gradient of the masked L1
+    loss with respect to the bottleneck feature (what a PnP-Depth refinement loop differentiates)."""
+    from oracle import torch_oracle as O
+    sd = O.synth_state_dict(O.latefusion_entries(4), seed=seed_sd)
+    model = ref.models.ResNet_latefusion(18, "upproj", (h, w), 4, pretrained=False)
+    model.load_state_dict(sd, strict=True)
+    model.train(training)
+    inputs, target = O.synth_batch(b, h, w, seed=1234)
+    with torch.no_grad():
+        feat = model.pnp_forward_front(inputs)
+    feat = feat.clone().requires_grad_(True)
+    pred = model.pnp_forward_rear(feat)
+    loss = ref.criteria.MaskedL1Loss()(pred, target)
+    loss.backward()
+    return {"loss": np.float64(loss.item()), "b": b, "h": h, "w": w, "training": training, "feature": feat.detach().numpy(),
+            "pred": pred.detach().numpy(), "dfeature": feat.grad.numpy()}
+
+
 def run_multistage(ref, b, h, w, seed_sd=7):
     from oracle import torch_oracle as O
     ent = O.multistage_entries()
@@ -187,6 +206,8 @@ def main():
         "latefusion2_c5_train_b2_64x96": lambda: run_latefusion(ref, 2, 64, 96, in_channels=5),
         "latefusion_train_b2_352x1216": lambda: run_latefusion(ref, 2, 352, 1216, full_pred=False),
         "multistage_fixs_train_b2_64x96": lambda: run_multistage(ref, 2, 64, 96),
+        "pnp_train_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, True),
+        "pnp_eval_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, False),
         "losses_filter": lambda: run_losses(ref),
         "metrics": lambda: run_metrics(ref),
     }

@@ -195,16 +195,17 @@ def _upproj(x, sd, p, training, nb):
     return F.relu(x1 + x2)
 
 
-def latefusion_forward(sd, x: Tensor, output_size, training: bool = True,
-                       new_buffers: Optional[dict] = None, prefix: str = "") -> Tensor:
-    """ResNet_latefusion.forward (models.py:627-664) / ResNet_latefusion2.forward
-    (multistage_model.py:232-276)."""
-    assert x.shape[1] >= 4                                   # multistage_model.py:233
+def _scoped(sd, new_buffers, prefix):
     if prefix:
-        sd = _PrefixView(sd, prefix)
-        nb = _PrefixSink(new_buffers, prefix) if new_buffers is not None else None
-    else:
-        nb = new_buffers
+        return _PrefixView(sd, prefix), (_PrefixSink(new_buffers, prefix) if new_buffers is not None else None)
+    return sd, new_buffers
+
+
+def latefusion_front(sd, x: Tensor, training: bool = True, new_buffers: Optional[dict] = None, prefix: str = "") -> Tensor:
+    """ResNet_latefusion.pnp_forward_front (models.py:669-700): both encoders, the concat and the two 1x1 conv+BN
+    pairs; returns bn2's output (256 channels at 1/32 resolution)."""
+    assert x.shape[1] >= 4                                   # multistage_model.py:233
+    sd, nb = _scoped(sd, new_buffers, prefix)
     xi, xd = x[:, :3], x[:, 3:]
     xi = F.relu(_bn(_conv(xi, sd, "conv1", 2, 3), sd, "bn1", training, nb))
     xi = F.max_pool2d(xi, 3, 2, 1)
@@ -214,11 +215,25 @@ def latefusion_forward(sd, x: Tensor, output_size, training: bool = True,
     xd = _encoder(xd, sd, "_depth", training, nb)
     f = torch.cat((xi, xd), dim=1)
     f = _bn(_conv(f, sd, "conv_fusion"), sd, "bn_fusion", training, nb)     # no activation, models.py:652-657
-    f = _bn(_conv(f, sd, "conv2"), sd, "bn2", training, nb)
+    return _bn(_conv(f, sd, "conv2"), sd, "bn2", training, nb)
+
+
+def latefusion_rear(sd, f: Tensor, output_size, training: bool = True, new_buffers: Optional[dict] = None,
+                    prefix: str = "") -> Tensor:
+    """ResNet_latefusion.pnp_forward_rear (models.py:702-707): decoder, 3x3 head, bilinear resize."""
+    sd, nb = _scoped(sd, new_buffers, prefix)
     for li in range(1, 5):
         f = _upproj(f, sd, f"decoder.layer{li}", training, nb)
     f = _conv(f, sd, "conv3", 1, 1)
     return F.interpolate(f, size=tuple(output_size), mode="bilinear", align_corners=True)
+
+
+def latefusion_forward(sd, x: Tensor, output_size, training: bool = True,
+                       new_buffers: Optional[dict] = None, prefix: str = "") -> Tensor:
+    """ResNet_latefusion.forward (models.py:627-664) / ResNet_latefusion2.forward
+    (multistage_model.py:232-276) = rear(front(x))."""
+    f = latefusion_front(sd, x, training, new_buffers, prefix)
+    return latefusion_rear(sd, f, output_size, training, new_buffers, prefix)
 
 
 class _PrefixView:

@@ -566,6 +566,16 @@ class LatefusionEngine:
         self.rear_bwd = bw[:split_b] + [Launch("feature_export(grad)", lib.rd_feature_export,
                                                (_v(g_c2), None, None, _p(self.d_bneck), B, h32, w32, 256, act))]
         self.bc2 = bc2
+        # BatchNorm-backward jobs of the backward program: (job view, batch count).  See _bn_backward_mode.
+        self._bwd_jobs = []
+        for L in bw:
+            for a in L.args:
+                obj = getattr(a, "_obj", None)
+                tail = obj if isinstance(obj, _lib.BnTail) else getattr(obj, "tail", None)
+                if isinstance(tail, _lib.BnTail):
+                    for i in range(tail.njobs):
+                        if tail.job[i].kind == 2:
+                            self._bwd_jobs.append((tail.job[i], float(tail.job[i].count)))
         self.cfg = dict(key=key, B=B, H=H, W=W, Hd=Hd, Wd=Wd, h32=h32, w32=w32)
         self.dec, self.blocks_all = dec, blocks_all
         self.dbg = dict(z_stem=z_stem, gz_stem=gz_stem, p_rgb=p_rgb, p_d=p_d, amax=amax, xs=xs, concat=concat, d_concat=d_concat,
@@ -596,6 +606,15 @@ class LatefusionEngine:
         if training:
             self.stats_used.zero_()
         self._run(self.fwd if training else self.fwd_eval)
+
+    def _bn_backward_mode(self, training: bool) -> None:
+        """Eval-mode BatchNorm (running statistics) is a per-channel affine map, so its backward is dz = gamma*invstd*g
+        without the two batch-mean terms.  Those terms carry 1/count in rd_bn_tail's coefficients (cB, cC), so an
+        infinite count turns every job into the eval-mode backward (dgamma/dbeta and cA are the same expressions; mean
+        and invstd already hold the running statistics after an eval forward).  Eager launches only: a captured graph
+        keeps the counts it was captured with."""
+        for job, count in self._bwd_jobs:
+            job.count = count if training else float("inf")
 
     def _bwd_body(self):
         self.dw.zero_()
@@ -643,21 +662,35 @@ class LatefusionEngine:
         self._run(prog[head:])
         return self.pred
 
-    def backward_rear(self, dpred: torch.Tensor) -> torch.Tensor:
-        """d(loss)/d(feature) of the last forward_rear (training-mode BatchNorm semantics, like autograd through the
-        reference's decoder); the decoder's parameter gradients are not produced on this path."""
+    def backward_rear(self, dpred: torch.Tensor, training: bool) -> torch.Tensor:
+        """d(loss)/d(feature) of the last forward_rear, in the BatchNorm mode that forward ran in.  The decoder's
+        parameter gradients are not produced on this path (the gradient arena is left as it was)."""
         self.dpred.copy_(dpred.reshape(self.dpred.shape))
+        keep = self.gflat.clone()          # the BatchNorm tails and the head add dgamma/dbeta/dW into the arena
         self.dw.zero_()
         self.stats_used.zero_()
-        self._run(self.rear_bwd)
+        self._bn_backward_mode(training)
+        try:
+            self._run(self.rear_bwd)
+        finally:
+            self._bn_backward_mode(True)
+        self.gflat.copy_(keep)
         return self.d_bneck
 
-    def backward(self, dpred: torch.Tensor, accumulate: bool) -> None:
-        """Fills the gradient arena from d(loss)/d(pred).  ``accumulate`` keeps what is already there."""
+    def backward(self, dpred: torch.Tensor, accumulate: bool, training: bool = True) -> None:
+        """Fills the gradient arena from d(loss)/d(pred).  ``accumulate`` keeps what is already there.  ``training`` is
+        the mode the forward ran in (eval-mode forwards are differentiated with the running statistics, eagerly)."""
         self.dpred.copy_(dpred.reshape(self.dpred.shape))
         if not accumulate:
             self.gflat.zero_()
-        self._replay("bwd", self._bwd_body)
+        if training:
+            self._replay("bwd", self._bwd_body)
+            return
+        self._bn_backward_mode(False)
+        try:
+            self._bwd_body()
+        finally:
+            self._bn_backward_mode(True)
 
     # ------------------------------------------------------------------ CUDA graphs
     # The launch programs are static per input shape, so after one eager (warm-up) execution each program is

@@ -158,6 +158,7 @@ class _LatefusionFn(torch.autograd.Function):
         module._fwd_serial += 1
         ctx.module, ctx.serial = module, module._fwd_serial
         ctx.need_dx = x.requires_grad
+        ctx.training = module.training
         return pred.clone()
 
     @staticmethod
@@ -168,10 +169,30 @@ class _LatefusionFn(torch.autograd.Function):
                                "forward of the same model; call backward before the next forward")
         eng = module._engine
         accumulate = eng.grads_bound()
-        eng.backward(dpred.contiguous(), accumulate)
+        eng.backward(dpred.contiguous(), accumulate, ctx.training)
         eng.bind_grads()
         dx = eng.input_grad() if ctx.need_dx else None
         return dx, None, None
+
+
+class _RearFn(torch.autograd.Function):
+    """pnp_forward_rear with a gradient w.r.t. its input feature (decoder parameters get no gradient on this path)."""
+
+    @staticmethod
+    def forward(ctx, feat, module):
+        eng = module._get_engine()
+        pred = eng.forward_rear(feat.detach().float().contiguous(), module.training, module._image_hw())
+        module._fwd_serial += 1
+        ctx.module, ctx.serial, ctx.training = module, module._fwd_serial, module.training
+        return pred.clone()
+
+    @staticmethod
+    def backward(ctx, dpred):
+        module = ctx.module
+        if ctx.serial != module._fwd_serial:
+            raise RuntimeError("radar_depth_b200: the activations of this rear pass were overwritten by a later forward "
+                               "of the same model; call backward before the next forward")
+        return module._engine.backward_rear(dpred.contiguous(), ctx.training).clone(), None
 
 
 class ResNet_latefusion(nn.Module):
@@ -250,11 +271,25 @@ class ResNet_latefusion(nn.Module):
         eng = self._get_engine()
         return eng.forward(x, self.training).clone()
 
-    # API surface of models.py:669-707; main.py never calls them
+    # API surface of models.py:669-707 (PnP-Depth refinement); main.py never calls them.  front = encoder
+    # + fusion 1x1s up to bn2's output, rear = decoder + head + bilinear.  rear(front(x)) == forward(x).  The usual PnP
+    # loop differentiates the rear with respect to the FEATURE, which is what the rear's autograd node provides;
+    # parameter gradients are only produced by the un-cut forward().
     def pnp_forward_front(self, x):
-        raise NotImplementedError("pnp_forward_front/rear split the graph at the bottleneck for PnP refinement, which "
-                                  "is outside the B200 hot path")
+        assert x.shape[1] >= 4
+        if not x.is_cuda:
+            raise _lib.RdError("radar_depth_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        self._fwd_serial += 1                        # the activations of an earlier forward() are overwritten
+        return self._get_engine().forward_front(x.float().contiguous(), self.training).clone()
 
     def pnp_forward_rear(self, x):
-        raise NotImplementedError("pnp_forward_front/rear split the graph at the bottleneck for PnP refinement, which "
-                                  "is outside the B200 hot path")
+        if not x.is_cuda:
+            raise _lib.RdError("radar_depth_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _RearFn.apply(x, self)
+        self._fwd_serial += 1
+        return self._get_engine().forward_rear(x.detach().float().contiguous(), self.training, self._image_hw()).clone()
+
+    def _image_hw(self):
+        eng = self._engine
+        return (eng.cfg["H"], eng.cfg["W"]) if eng is not None and eng.cfg is not None else None

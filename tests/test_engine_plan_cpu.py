@@ -26,3 +26,42 @@ def test_engine_plans_every_program(cin, hw, b, act):
     covered = (eng.unpack_idx >= 0).sum().item()
     n_conv = sum(p.numel() for n, p in m.named_parameters() if p.dim() == 4 and n != "conv3.weight")
     assert covered == n_conv
+
+
+def test_graph_cut_programs_partition_the_forward():
+    """pnp_forward_front / pnp_forward_rear (reference models.py:669-707): front + rear cover the forward program exactly
+    once (plus the feature export / import at the cut), in both BatchNorm modes; the rear's backward is the prefix of the
+    backward program that ends with the data gradient of decoder.layer1's 5x5 pair."""
+    m = ResNet_latefusion(18, "upproj", (64, 96), 4, pretrained=False)
+    eng = LatefusionEngine(m, 4, (64, 96), _lib.RD_F32)
+    eng.adopt("cpu")
+    eng.configure(2, 64, 96)
+    f, r = [L.name for L in eng.front], [L.name for L in eng.rear]
+    assert f[-1] == "feature_export" and f[-2] == "conv_f:conv2"
+    assert r[:2] == ["pack_weights", "feature_import"] and r[2] == "conv_f:decoder.layer1.up5x5" and r[-1] == "bilinear"
+    assert f[:-1] + r[2:] == [L.name for L in eng.fwd]
+    fe, re_ = [L.name for L in eng.front_eval], [L.name for L in eng.rear_eval]
+    assert fe[-1] == "feature_export" and fe[-2] == "conv_f:conv2(eval)"
+    assert re_[:3] == ["pack_weights", "bn_fin_eval_all", "feature_import"]
+    assert fe[:-1] + re_[3:] == [L.name for L in eng.fwd_eval]
+    rb = [L.name for L in eng.rear_bwd]
+    assert rb[0] == "bilinear_bwd" and rb[-2] == "conv_d:decoder.layer1.up5x5" and rb[-1] == "feature_export(grad)"
+    assert rb[:-1] == [L.name for L in eng.bwd[:len(rb) - 1]]
+    assert eng.bneck.shape == (2, 256, 2, 3)
+
+
+def test_eval_mode_backward_switches_every_batchnorm_job():
+    """Eval-mode BatchNorm backward = the training formula with an infinite batch count (the two batch-mean terms
+    vanish); every one of the 62 BatchNorm layers has exactly one backward job and the switch is reversible."""
+    m = ResNet_latefusion(18, "upproj", (64, 96), 4, pretrained=False)
+    eng = LatefusionEngine(m, 4, (64, 96), _lib.RD_F32)
+    eng.adopt("cpu")
+    eng.configure(2, 64, 96)
+    n_bn = sum(1 for mod in m.modules() if mod.__class__.__name__ == "BatchNorm2d")
+    assert len(eng._bwd_jobs) == n_bn
+    counts = [float(j.count) for j, _ in eng._bwd_jobs]
+    assert all(c == c0 and c > 0 and c != float("inf") for c, (_, c0) in zip(counts, eng._bwd_jobs))
+    eng._bn_backward_mode(False)
+    assert all(float(j.count) == float("inf") for j, _ in eng._bwd_jobs)
+    eng._bn_backward_mode(True)
+    assert [float(j.count) for j, _ in eng._bwd_jobs] == counts

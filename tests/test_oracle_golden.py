@@ -63,6 +63,28 @@ def test_latefusion_eval_matches_reference_golden(golden_dir):
     assert abs(float(O.masked_l1(pred, target)) - float(g["loss"])) < 1e-4
 
 
+@pytest.mark.parametrize("name,training", [("pnp_train_b2_64x96", True), ("pnp_eval_b2_64x96", False)])
+def test_pnp_front_rear_match_reference_golden(golden_dir, name, training):
+    """latefusion_front / latefusion_rear against pnp_forward_front / pnp_forward_rear of the real reference
+    (models.py:669-707), incl. the gradient of the masked L1 loss w.r.t. the bottleneck feature."""
+    g = _load(golden_dir, name)
+    sd = O.synth_state_dict(O.latefusion_entries(4))
+    inputs, target = O.synth_batch(2, 64, 96)
+    with torch.no_grad():
+        feat = O.latefusion_front(sd, inputs, training=training)
+    _close(feat.numpy(), g["feature"])
+    f = torch.from_numpy(g["feature"]).clone().requires_grad_(True)
+    pred = O.latefusion_rear(sd, f, (64, 96), training=training)
+    loss = O.masked_l1(pred, target)
+    loss.backward()
+    _close(pred.detach().numpy(), g["pred"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    _close(f.grad.numpy(), g["dfeature"], tol=2e-2)          # sign() of the L1 gradient flips on fp32 noise
+    with torch.no_grad():                                      # rear(front(x)) is the un-cut forward
+        full = O.latefusion_forward(sd, inputs, (64, 96), training=training)
+    _close(full.numpy(), g["pred"])
+
+
 def test_latefusion_full_size_matches_reference_golden(golden_dir):
     g = _load(golden_dir, "latefusion_train_b2_352x1216")
     sd = O.synth_state_dict(O.latefusion_entries(4))
