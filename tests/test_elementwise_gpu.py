@@ -244,6 +244,64 @@ def test_masked_l1_forward_backward_vs_reference_formula():
         crit(pred[0], tgt)
 
 
+@pytest.mark.parametrize("name,act,td", ACTS)
+def test_feature_export_import_roundtrip(name, act, td):
+    """rd_feature_export / rd_feature_import (graph cut of pnp_forward_front / rear): NHWC slice of a wider buffer <-> NCHW
+    fp32, with and without the per-channel affine; bit-exact in fp32, one bf16 rounding in bf16."""
+    torch.manual_seed(5)
+    B, H, W, Cc, pitch, coff = 2, 3, 5, 24, 40, 8
+    buf = torch.randn(B, H, W, pitch, device="cuda").to(td)
+    sc, sh = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda")
+    out = torch.full((B, Cc, H, W), float("nan"), device="cuda")
+    call("rd_feature_export", view(buf, coff), ptr(sc), ptr(sh), ptr(out), B, H, W, Cc, act, stream_ptr())
+    sl = buf[..., coff:coff + Cc].float()
+    ref = torch.addcmul(sh.view(1, 1, 1, -1), sl, sc.view(1, 1, 1, -1)).permute(0, 3, 1, 2)
+    torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-6)
+    call("rd_feature_export", view(buf, coff), None, None, ptr(out), B, H, W, Cc, act, stream_ptr())
+    assert torch.equal(out, sl.permute(0, 3, 1, 2))
+    x = torch.randn(B, Cc, H, W, device="cuda")
+    dst = torch.full((B, H, W, pitch), 7.0, device="cuda").to(td)
+    call("rd_feature_import", ptr(x), view(dst, coff), B, H, W, Cc, act, stream_ptr())
+    assert torch.equal(dst[..., coff:coff + Cc].float(), x.permute(0, 2, 3, 1).to(td).float())
+    assert bool((dst[..., :coff] == 7).all()) and bool((dst[..., coff + Cc:] == 7).all())      # neighbours untouched
+    with pytest.raises(_lib.RdError):
+        call("rd_feature_export", view(buf, coff), ptr(sc), None, ptr(out), B, H, W, Cc, act, stream_ptr())
+
+
+def test_masked_l1_edge_cases_follow_the_reference():
+    """criteria_new.py:50-53 is unguarded: no valid pixel -> mean of an empty selection = NaN (loss and gradient are not
+    "fixed" here either); one valid pixel -> |t - p| and a single +-1 gradient; non-contiguous / fp64 inputs are accepted;
+    pred == target on a valid pixel has sign 0."""
+    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+    crit = MaskedL1Loss()
+    pred = torch.rand(1, 1, 8, 12, device="cuda").requires_grad_(True)
+    loss = crit(pred, torch.zeros(1, 1, 8, 12, device="cuda"))
+    assert torch.isnan(loss)
+    tgt = torch.zeros(1, 1, 8, 12, device="cuda")
+    tgt[0, 0, 3, 5] = 7.5
+    pred = torch.full((1, 1, 8, 12), 2.0, device="cuda", requires_grad=True)
+    loss = crit(pred, tgt)
+    loss.backward()
+    assert float(loss) == 5.5
+    exp = torch.zeros_like(tgt)
+    exp[0, 0, 3, 5] = -1.0
+    assert torch.equal(pred.grad, exp)
+    # exact hit on a valid pixel: sign(0) = 0 like torch's abs backward; the count still includes it
+    tgt2 = tgt.clone()
+    tgt2[0, 0, 0, 0] = 2.0
+    pred2 = torch.full((1, 1, 8, 12), 2.0, device="cuda", requires_grad=True)
+    loss2 = crit(pred2, tgt2)
+    loss2.backward()
+    assert float(loss2) == 2.75 and float(pred2.grad[0, 0, 0, 0]) == 0.0 and float(pred2.grad[0, 0, 3, 5]) == -0.5
+    # a transposed (non-contiguous) fp64 pair gives the same number as the reference formula
+    torch.manual_seed(8)
+    p3 = (torch.rand(2, 1, 12, 8, device="cuda", dtype=torch.float64) * 20).transpose(2, 3)
+    t3 = (torch.rand(2, 1, 12, 8, device="cuda", dtype=torch.float64) * 20).transpose(2, 3)
+    t3 = torch.where(t3 > 10, t3, torch.zeros_like(t3))
+    ref = (t3 - p3)[t3 > 0].abs().mean()
+    assert abs(float(crit(p3, t3)) - float(ref)) < 1e-5
+
+
 def test_sid_filter_matches_reference_formula():
     torch.manual_seed(4)
     d = torch.rand(2, 1, 20, 30, device="cuda") * 80
