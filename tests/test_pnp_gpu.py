@@ -69,7 +69,9 @@ def test_rear_of_front_is_the_uncut_forward(precision, training, tol):
     if training:                       # each BatchNorm was updated exactly once by front + rear, as by the un-cut forward
         for k, v in m.state_dict().items():
             if k in bufs:
-                assert torch.allclose(v.float(), bufs[k].float(), rtol=1e-4, atol=1e-6), k
+                # (bf16 mode: the decoder sees the feature rounded to bf16 once more, so its batch statistics move a little)
+                rt, at = (1e-4, 1e-6) if precision == "fp32" else (3e-2, 3e-3)
+                assert torch.allclose(v.float(), bufs[k].float(), rtol=rt, atol=at), k
 
 
 def test_rear_rejects_a_feature_of_the_wrong_shape():
