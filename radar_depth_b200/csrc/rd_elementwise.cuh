@@ -609,10 +609,15 @@ __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VVi
 // ------------------------------------------------------------------------------------------------
 // Head: conv3 3x3 16->1 (models.py:587,661) as a bandwidth kernel, fp32 output at decoder resolution.
 template <typename T>
-__global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16][3][3] OIHW with O=1*/, int B, int H, int W,
-                                     float* __restrict__ out) {
-    __shared__ float ws[144];
-    for (int i = threadIdx.x; i < 144; i += blockDim.x) ws[i] = w[i];
+__global__ void __launch_bounds__(256) head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16][3][3] OIHW with O=1*/, int B,
+                                                            int H, int W, float* __restrict__ out) {
+    // weights re-laid as [tap][16]: a tap's 16 channel weights are four broadcast LDS.128 (the [c][tap] order cost one
+    // LDS per FMA and made the kernel shared-memory-issue bound); four independent accumulator chains
+    __shared__ __align__(16) float ws[9 * 16];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) {
+        const int c = i / 9, t = i - c * 9;
+        ws[t * 16 + c] = w[i];
+    }
     __syncthreads();
     const uint32_t total = (uint32_t)B * H * W;
     const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
@@ -621,10 +626,12 @@ __global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16]
         const int ox = (int)(pix - prow * W);
         const int b = (int)fdh.div(prow);
         const int oy = (int)(prow - (uint32_t)b * H);
-        float acc = 0.f;
-        for (int dy = 0; dy < 3; ++dy) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {                  // one row of taps (six 16-byte loads) in flight per thread
             const int iy = oy + dy - 1;
             if (iy < 0 || iy >= H) continue;
+#pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int ix = ox + dx - 1;
                 if (ix < 0 || ix >= W) continue;
@@ -632,11 +639,18 @@ __global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16]
                 const size_t ip = ((size_t)b * H + iy) * W + ix;
                 Act<T>::load8(vptr<T>(x, ip, 0), v);
                 Act<T>::load8(vptr<T>(x, ip, 8), v + 8);
+                const float4* wt = reinterpret_cast<const float4*>(ws + (dy * 3 + dx) * 16);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc = fmaf(v[c], ws[c * 9 + dy * 3 + dx], acc);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 ww = wt[q];
+                    acc[q] = fmaf(v[4 * q + 0], ww.x, acc[q]);
+                    acc[q] = fmaf(v[4 * q + 1], ww.y, acc[q]);
+                    acc[q] = fmaf(v[4 * q + 2], ww.z, acc[q]);
+                    acc[q] = fmaf(v[4 * q + 3], ww.w, acc[q]);
+                }
             }
         }
-        out[pix] = acc;
+        out[pix] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
 }
 
@@ -646,13 +660,17 @@ __global__ void head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16]
 template <typename T>
 __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w,
                                                              int B, int H, int W, VView dx, float* dw /*[144]*/) {
-    __shared__ float ws[144];
+    __shared__ __align__(16) float ws[144];            // [half][tap][8]: a tap's 8 weights of one half = two LDS.128
     __shared__ float dws[144];
-    for (int i = threadIdx.x; i < 144; i += blockDim.x) { ws[i] = w[i]; dws[i] = 0.f; }
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) {
+        const int c = i / 9, t = i - c * 9;
+        ws[(c >> 3) * 72 + t * 8 + (c & 7)] = w[i];
+        dws[i] = 0.f;
+    }
     __syncthreads();
     const uint32_t total = (uint32_t)B * H * W * 2u;
     const int half = threadIdx.x & 1;                  // blockDim and the grid stride are even: fixed per thread
-    const float* wh = ws + half * 72;                  // this half's [8][9] weights (two-address broadcast reads)
+    const float4* wh = reinterpret_cast<const float4*>(ws + half * 72);   // two-address broadcast reads
     float wacc[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
@@ -677,9 +695,11 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __re
                 const int qy = oy - (dy - 1), qx = ox - (dx_ - 1);
                 const bool ok = qy >= 0 && qy < H && qx >= 0 && qx < W;
                 const float d = ok ? __ldg(dc3 + ((size_t)b * H + qy) * W + qx) : 0.f;
+                const float4 w0 = wh[(dy * 3 + dx_) * 2], w1 = wh[(dy * 3 + dx_) * 2 + 1];
+                const float wt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    dxa[c] = fmaf(d, wh[c * 9 + dy * 3 + dx_], dxa[c]);
+                    dxa[c] = fmaf(d, wt[c], dxa[c]);
                     wacc[dy * 3 + dx_][c] = fmaf(d, xv[c], wacc[dy * 3 + dx_][c]);
                 }
             }
