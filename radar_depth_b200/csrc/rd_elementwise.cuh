@@ -187,26 +187,64 @@ __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, in
 // bn_add_act: out = act( z*sc + sh + identity )   -- the residual join of BasicBlock (models.py:104-110) and
 // UpProjModule (models.py:205-208).  identity is either a materialised activation (id_sc == nullptr) or another
 // raw conv output with its own BN (downsample branch / bottom branch).  With idv.ptr == nullptr: plain BN+act.
+// eight consecutive floats of a 16-byte aligned shared-memory vector as two LDS.128
+__device__ __forceinline__ void lds8(const float* p, float* v) {
+    const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+
+// Per-channel vectors are staged in shared memory once per block (two LDS.128 per vector and item instead of eight
+// L1 loads per vector), and every thread keeps TWO items (four 16-byte loads) in flight per iteration: with one item
+// the resident threads of an SM held ~48 KB in flight, below what the HBM latency-bandwidth product needs.
 template <typename T>
-__global__ void bn_add_act_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, VView idv,
-                                  const float* __restrict__ id_sc, const float* __restrict__ id_sh, VView out,
-                                  size_t npix, int C, float slope) {
+__global__ void __launch_bounds__(256) bn_add_act_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, VView idv,
+                                                         const float* __restrict__ id_sc, const float* __restrict__ id_sh, VView out,
+                                                         size_t npix, int C, float slope) {
+    extern __shared__ __align__(16) float coef_s[];                 // [sc | sh | id_sc | id_sh][C]
+    const bool has_id = idv.ptr != nullptr, id_bn = id_sc != nullptr;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        coef_s[i] = sc[i];
+        coef_s[C + i] = sh[i];
+        if (id_bn) { coef_s[2 * C + i] = id_sc[i]; coef_s[3 * C + i] = id_sh[i]; }
+    }
+    __syncthreads();
     const int groups = C >> 3;
     const uint32_t total = (uint32_t)npix * (uint32_t)groups;       // launcher guarantees npix * groups < 2^31
+    const uint32_t stride = gridDim.x * blockDim.x;
     const FastDiv fdg((uint32_t)groups);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t pix = fdg.div(i);
-        const int c = (int)(i - pix * groups) * 8;
-        float v[8], r[8];
-        Act<T>::load8(vptr<T>(z, pix, c), v);
-        if (idv.ptr) Act<T>::load8(vptr<T>(idv, pix, c), r);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float y = fmaf(v[k], sc[c + k], sh[c + k]);
-            if (idv.ptr) y += id_sc ? fmaf(r[k], id_sc[c + k], id_sh[c + k]) : r[k];
-            v[k] = y > 0.f ? y : y * slope;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        const uint32_t i1 = i0 + stride;
+        const bool two = i1 < total;
+        const uint32_t pix0 = fdg.div(i0), pix1 = fdg.div(two ? i1 : i0);
+        const int c0 = (int)(i0 - pix0 * groups) * 8, c1 = (int)((two ? i1 : i0) - pix1 * groups) * 8;
+        float v0[8], r0[8], v1[8], r1[8];
+        Act<T>::load8(vptr<T>(z, pix0, c0), v0);
+        if (has_id) Act<T>::load8(vptr<T>(idv, pix0, c0), r0);
+        if (two) {
+            Act<T>::load8(vptr<T>(z, pix1, c1), v1);
+            if (has_id) Act<T>::load8(vptr<T>(idv, pix1, c1), r1);
         }
-        Act<T>::store8(vptr_w<T>(out, pix, c), v);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float* v = u ? v1 : v0;
+            const float* r = u ? r1 : r0;
+            const int c = u ? c1 : c0;
+            float a[8], b[8], ia[8], ib[8];
+            lds8(coef_s + c, a);
+            lds8(coef_s + C + c, b);
+            if (id_bn) {
+                lds8(coef_s + 2 * C + c, ia);
+                lds8(coef_s + 3 * C + c, ib);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float y = fmaf(v[k], a[k], b[k]);
+                if (has_id) y += id_bn ? fmaf(r[k], ia[k], ib[k]) : r[k];
+                v[k] = y > 0.f ? y : y * slope;
+            }
+            Act<T>::store8(vptr_w<T>(out, u ? pix1 : pix0, c), v);
+        }
     }
 }
 
@@ -252,20 +290,45 @@ __global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VVie
 
 // bn_bwd_apply: dz = A*g + Bz*z + Cc (per channel).  dz may alias g.
 template <typename T>
-__global__ void bn_bwd_apply_kernel(VView g, VView z, VView dz, const float* __restrict__ A, const float* __restrict__ Bz,
-                                    const float* __restrict__ Cc, size_t npix, int C) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(VView g, VView z, VView dz, const float* __restrict__ A,
+                                                           const float* __restrict__ Bz, const float* __restrict__ Cc, size_t npix, int C) {
+    extern __shared__ __align__(16) float coef_s[];                 // [A | Bz | Cc][C], see bn_add_act_kernel
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        coef_s[i] = A[i];
+        coef_s[C + i] = Bz[i];
+        coef_s[2 * C + i] = Cc[i];
+    }
+    __syncthreads();
     const int groups = C >> 3;
     const uint32_t total = (uint32_t)npix * (uint32_t)groups;
+    const uint32_t stride = gridDim.x * blockDim.x;
     const FastDiv fdg((uint32_t)groups);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t pix = fdg.div(i);
-        const int c = (int)(i - pix * groups) * 8;
-        float gv[8], zv[8];
-        Act<T>::load8(vptr<T>(g, pix, c), gv);
-        Act<T>::load8(vptr<T>(z, pix, c), zv);
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        const uint32_t i1 = i0 + stride;
+        const bool two = i1 < total;
+        const uint32_t pix0 = fdg.div(i0), pix1 = fdg.div(two ? i1 : i0);
+        const int c0 = (int)(i0 - pix0 * groups) * 8, c1 = (int)((two ? i1 : i0) - pix1 * groups) * 8;
+        float g0[8], z0[8], g1[8], z1[8];
+        Act<T>::load8(vptr<T>(g, pix0, c0), g0);
+        Act<T>::load8(vptr<T>(z, pix0, c0), z0);
+        if (two) {
+            Act<T>::load8(vptr<T>(g, pix1, c1), g1);
+            Act<T>::load8(vptr<T>(z, pix1, c1), z1);
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) gv[k] = fmaf(A[c + k], gv[k], fmaf(Bz[c + k], zv[k], Cc[c + k]));
-        Act<T>::store8(vptr_w<T>(dz, pix, c), gv);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float* gv = u ? g1 : g0;
+            const float* zv = u ? z1 : z0;
+            const int c = u ? c1 : c0;
+            float a[8], b[8], cc[8];
+            lds8(coef_s + c, a);
+            lds8(coef_s + C + c, b);
+            lds8(coef_s + 2 * C + c, cc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gv[k] = fmaf(a[k], gv[k], fmaf(b[k], zv[k], cc[k]));
+            Act<T>::store8(vptr_w<T>(dz, u ? pix1 : pix0, c), gv);
+        }
     }
 }
 
