@@ -278,6 +278,13 @@ template <> struct Act<bf16> {
         v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
         v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
     }
+    // the same load split in two, so that several loads can be in flight while their data stays packed (4 registers)
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& u, float* v) {
+        v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+        v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
+    }
     static __device__ __forceinline__ void store8(bf16* p, const float* v) {
         uint4 u;
         u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -294,6 +301,16 @@ template <> struct Act<float> {
         float4 a = *reinterpret_cast<const float4*>(p);
         float4 b = *reinterpret_cast<const float4*>(p + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw load_raw(const float* p) {
+        Raw r;
+        r.a = *reinterpret_cast<const float4*>(p);
+        r.b = *reinterpret_cast<const float4*>(p + 4);
+        return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& r, float* v) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
     }
     static __device__ __forceinline__ void store8(float* p, const float* v) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) bn_add_act_kernel(VView z, const float* _
 // join_bwd: g = dout * act'(out);  stats: sum g, sum g*z (main BN) and optionally sum g*zid (identity-branch BN).
 // Writes g (may alias dout).  Autograd of the residual join + ReLU.
 template <typename T>
-__global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
+__global__ void __launch_bounds__(256, 3) join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
                                 double* sum_g, double* sum_gz, double* sum_gzid, const __grid_constant__ rd_bn_tail tail) {
     extern __shared__ float red_s[];
     const int groups = C >> 3;
@@ -264,22 +264,44 @@ __global__ void join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VVie
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
     if (pl < ppb) {
-        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += (size_t)gridDim.x * ppb) {
-            float d[8], o[8], zz[8], zi[8];
-            const int c = cg * 8;
-            Act<T>::load8(vptr<T>(dout, pix, c), d);
-            Act<T>::load8(vptr<T>(outv, pix, c), o);
-            Act<T>::load8(vptr<T>(z, pix, c), zz);
-            if (zid.ptr) Act<T>::load8(vptr<T>(zid, pix, c), zi);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float gg = o[k] > 0.f ? d[k] : d[k] * slope;
-                d[k] = gg;
-                acc[0][k] += gg;
-                acc[1][k] += gg * zz[k];
-                if (zid.ptr) acc[2][k] += gg * zi[k];
+        // two pixels (six to eight 16-byte loads) in flight per thread: the grid is capped at 3 blocks per SM by the
+        // atomic tail, and with one pixel per iteration those threads held less than the HBM latency-bandwidth product
+        const size_t step = (size_t)gridDim.x * ppb;
+        const int c = cg * 8;
+        const bool has_id = zid.ptr != nullptr;
+        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npix; pix += 2 * step) {
+            const size_t pix1 = pix + step;
+            const bool two = pix1 < npix;
+            typedef typename Act<T>::Raw Raw;
+            Raw rd0, ro0, rz0, ri0, rd1, ro1, rz1, ri1;
+            rd0 = Act<T>::load_raw(vptr<T>(dout, pix, c));
+            ro0 = Act<T>::load_raw(vptr<T>(outv, pix, c));
+            rz0 = Act<T>::load_raw(vptr<T>(z, pix, c));
+            if (has_id) ri0 = Act<T>::load_raw(vptr<T>(zid, pix, c));
+            if (two) {
+                rd1 = Act<T>::load_raw(vptr<T>(dout, pix1, c));
+                ro1 = Act<T>::load_raw(vptr<T>(outv, pix1, c));
+                rz1 = Act<T>::load_raw(vptr<T>(z, pix1, c));
+                if (has_id) ri1 = Act<T>::load_raw(vptr<T>(zid, pix1, c));
             }
-            Act<T>::store8(vptr_w<T>(g, pix, c), d);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                float d[8], o[8], zz[8], zi[8];
+                Act<T>::unpack(u ? rd1 : rd0, d);
+                Act<T>::unpack(u ? ro1 : ro0, o);
+                Act<T>::unpack(u ? rz1 : rz0, zz);
+                if (has_id) Act<T>::unpack(u ? ri1 : ri0, zi);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float gg = o[k] > 0.f ? d[k] : d[k] * slope;
+                    d[k] = gg;
+                    acc[0][k] += gg;
+                    acc[1][k] += gg * zz[k];
+                    if (has_id) acc[2][k] += gg * zi[k];
+                }
+                Act<T>::store8(vptr_w<T>(g, u ? pix1 : pix, c), d);
+            }
         }
     }
     double* outs[3] = {sum_g, sum_gz, sum_gzid};

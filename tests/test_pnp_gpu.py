@@ -48,7 +48,7 @@ def test_front_and_rear_match_reference_golden_fp32_mode(name, training):
     assert r_pred < 1e-3
     assert abs(float(loss) - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
     assert f.grad.shape == f.shape
-    assert r_grad < 0.25 and c_grad > 0.98
+    assert r_grad < 5e-2 and c_grad > 0.999        # measured on B200: 1.1e-2 / 0.99994 (train), 2.1e-3 / 0.999998 (eval)
     # no parameter gradient is produced (or disturbed) on the cut path
     assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in m.parameters())
 
@@ -73,7 +73,9 @@ def test_rear_of_front_is_the_uncut_forward(precision, training, tol):
         for k, v in m.state_dict().items():
             if k in bufs:
                 # (bf16 mode: the decoder sees the feature rounded to bf16 once more, so its batch statistics move a little)
-                rt, at = (1e-4, 1e-6) if precision == "fp32" else (3e-2, 3e-3)
+                # fp32 mode: run-to-run noise of the atomically summed statistics, measured > 1e-4 relative on layer4's
+                # 12-sample channels; a BatchNorm updated twice (or not at all) would be off by ~0.1 * (batch - running)
+                rt, at = (1e-3, 1e-4) if precision == "fp32" else (3e-2, 3e-3)
                 assert torch.allclose(v.float(), bufs[k].float(), rtol=rt, atol=at), k
 
 
