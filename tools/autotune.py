@@ -1,6 +1,8 @@
 """Measures tile choices for every convolution program of resnet18_latefusion at a given batch / size on the GPU and
 writes radar_depth_b200/tuned_tiles.json (committed: the table travels with the repo, the planner falls back to its
-cost model for shapes that are missing).  usage: python tools/autotune.py [batch] [H] [W]"""
+cost model for shapes that are missing).  usage: python tools/autotune.py [batch] [H] [W] [in_channels]
+(in_channels = 5 measures the stage-2 network of ResNet_multistage, whose stem has a second depth channel and a data
+gradient; the table is keyed by batch, so BASELINE configs[3] wants `tools/autotune.py 8` and `tools/autotune.py 8 352 1216 5`.)"""
 import json
 import os
 import sys
@@ -12,6 +14,7 @@ from radar_depth_b200.engine import LatefusionEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 352
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 1216
+CIN = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 act = _lib.RD_BF16
 table = cp.tuned_table().copy()
 cp._TUNED = {}                       # plan from the cost model while tuning
@@ -52,8 +55,8 @@ def fprop_candidates(g, src_hw, dst_hw):
     return out
 
 
-m = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False)
-eng = LatefusionEngine(m, 4, (H, W), act)
+m = ResNet_latefusion(18, "upproj", (H, W), CIN, pretrained=False)
+eng = LatefusionEngine(m, CIN, (H, W), act)
 eng.adopt("cpu")
 eng.configure(B, H, W)
 seen = set()
