@@ -82,6 +82,10 @@ class LatefusionEngine:
         self.device = None
         self.flat = None
         self.gflat = None
+        self._plist = None                 # [(owner module, attribute, parameter, arena offset, numel, shape)]
+        self._blist: List[torch.Tensor] = []
+        self._gviews: List[torch.Tensor] = []
+        self._adopt_checks = 0
         self.offs: Dict[str, Tuple[int, tuple]] = {}
         self.cfg = None
         self._stats_chunks: List[torch.Tensor] = []
@@ -91,17 +95,28 @@ class LatefusionEngine:
         self._graphs = {}
 
     # ------------------------------------------------------------------ parameter arena
+    # Host-side bookkeeping runs on every forward / backward: it walks cached (owner module, attribute, parameter) triples
+    # instead of module.named_parameters() (0.5 ms per traversal of the 150-module tree) and re-binds cached gradient
+    # views instead of slicing the arena anew (163 x 2 torch ops); measured 4.0 -> 0.3 ms of Python per engine and step.
     def params_adopted(self) -> bool:
-        if self.flat is None:
+        if self.flat is None or self._plist is None or self.flat.device != self.device:
             return False
-        base, end = self.flat.data_ptr(), self.flat.data_ptr() + self.flat.numel() * 4
-        for _, p in self.module.named_parameters(recurse=True):
-            if not (p.is_cuda and base <= p.data_ptr() < end):
-                return False
-        for b in self.module.buffers():
-            if not b.is_cuda:
+        self._adopt_checks += 1
+        if self._adopt_checks % 128 == 0 and not self._param_set_unchanged():
+            return False                   # a parameter was ADDED to the module since adoption (full walk, rarely)
+        base = self.flat.data_ptr()
+        for owner, attr, p, off, _, _ in self._plist:
+            if owner._parameters.get(attr) is not p or p.data_ptr() != base + 4 * off:
+                return False               # parameter object replaced, or its storage moved (.to(), .data = ...)
+        for b in self._blist:
+            if b.device != self.device:
                 return False
         return True
+
+    def _param_set_unchanged(self) -> bool:
+        cur = [id(p) for _, p in self.module.named_parameters()]
+        return cur == [id(e[2]) for e in self._plist] and \
+            [id(b) for b in self.module.buffers()] == [id(b) for b in self._blist]
 
     def adopt(self, device) -> None:
         """Flatten the module's parameters into one fp32 arena; parameters become views of it."""
@@ -123,20 +138,29 @@ class LatefusionEngine:
             if b.device != self.device:
                 raise RuntimeError("move the module to the CUDA device before the first forward (model.cuda())")
         self.flat, self.gflat, self.offs, self.nparams = flat, gflat, offs, total
+        self._plist = []
+        for n, p in named:
+            owner_name, _, attr = n.rpartition(".")
+            owner = self.module.get_submodule(owner_name) if owner_name else self.module
+            assert owner._parameters[attr] is p
+            self._plist.append((owner, attr, p, offs[n][0], p.numel(), offs[n][1]))
+        self._blist = list(self.module.buffers())
+        self._gviews = [gflat[off:off + n].view(shape) for _, _, _, off, n, shape in self._plist]
+        self._adopt_checks = 0
         self.cfg = None
 
     def bind_grads(self) -> None:
-        for n, p in self.module.named_parameters():
-            off, shape = self.offs[n]
-            if p.grad is None or p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
-                p.grad = self.gflat[off:off + p.numel()].view(shape)
+        """param.grad = its view of the gradient arena (the SAME view object every step; a .grad that already aliases
+        the right arena slot -- e.g. after optimizer.zero_grad(set_to_none=False) -- is left alone)."""
+        for e, v in zip(self._plist, self._gviews):
+            g = e[2].grad
+            if g is not v and (g is None or g.data_ptr() != v.data_ptr()):
+                e[2].grad = v
 
     def grads_bound(self) -> bool:
-        for n, p in self.module.named_parameters():
-            if p.grad is None:
-                return False
-            off, _ = self.offs[n]
-            if p.grad.data_ptr() != self.gflat.data_ptr() + 4 * off:
+        for e, v in zip(self._plist, self._gviews):
+            g = e[2].grad
+            if g is not v and (g is None or g.data_ptr() != v.data_ptr()):
                 return False
         return True
 
