@@ -229,8 +229,12 @@ int rd_bn_add_act(rd_view z, const float* sc, const float* sh, rd_view idv, cons
 int rd_join_bwd(rd_view dout, rd_view out, rd_view z, rd_view zid, rd_view g, long long npix, int C, float slope,
                 double* sum_g, double* sum_gz, double* sum_gzid, const rd_bn_tail* tail /* may be NULL */, int act_dtype,
                 void* stream);
+/* dz = A*g + B*z + C per channel: the elementwise half of autograd's nn.BatchNorm2d backward (every BatchNorm of
+ * models.py:539-594; coefficients from rd_bn_bwd_finalize or a rd_bn_tail job).  dz may alias g. */
 int rd_bn_bwd_apply(rd_view g, rd_view z, rd_view dz, const float* coefA, const float* coefB, const float* coefC,
                     long long npix, int C, int act_dtype, void* stream);
+/* sum g, sum g*z over a tensor whose gradient is already final (BatchNorm backward reductions without an activation
+ * mask, e.g. bn_fusion / bn2 of models.py:652-657 when their gradient comes from an elementwise producer). */
 int rd_grad_stats(rd_view g, rd_view z, long long npix, int C, double* sum_g, double* sum_gz, int act_dtype, void* stream);
 
 /* nn.MaxPool2d(3,2,1) over act(bn(z)) (models.py:546-547,564-565), both stems at once; stores the arg-max. */
