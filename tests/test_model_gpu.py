@@ -113,7 +113,7 @@ def test_eval_forward_parity_fp32_mode():
 
 @pytest.mark.parametrize("h,w,tol", [(64, 96, 0.4), (352, 1216, 0.2)])
 def test_train_step_bf16_mode_within_autocast_level(h, w, tol):
-    """bf16 throughput mode.  Calibration (tools/ref_gpu_baseline.py, B200, these synthetic weights, 352x1216): the
+    """bf16 throughput mode.  Calibration (tests/tools/ref_gpu_baseline.py, B200, these synthetic weights, 352x1216): the
     reference's own ops under torch.autocast(bf16)+channels_last differ from their fp32 run by 0.133 rel-L2 in the
     prediction (5.7e-2 at default init); this path measures 0.132.  Tiny maps (12 samples per
     BatchNorm channel at 64x96) amplify rounding further.  Weight gradients in bf16 are only checked near the loss
