@@ -53,10 +53,11 @@ def test_front_and_rear_match_reference_golden_fp32_mode(name, training):
     assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in m.parameters())
 
 
-@pytest.mark.parametrize("precision,training,tol", [("fp32", True, 1e-3), ("fp32", False, 1e-6), ("bf16", True, 0.1), ("bf16", False, 1e-6)])
+@pytest.mark.parametrize("precision,training,tol", [("fp32", True, 1e-3), ("fp32", False, 1e-6), ("bf16", True, 0.25), ("bf16", False, 1e-6)])
 def test_rear_of_front_is_the_uncut_forward(precision, training, tol):
     """rear(front(x)) == forward(x) on the same engine.  Measured on B200: bit-identical in eval mode (both precisions);
-    in training mode 8e-5 (fp32) / 4e-2 (bf16: the imported feature is rounded to bf16 once more) -- the batch
+    in training mode 8e-5 (fp32) / 4e-2 (bf16: the imported feature is rounded to bf16 once more; bound = the bf16-mode
+    bound of smoke(), the level at which the reference's own autocast run differs from its fp32 run) -- the batch
     statistics are summed with fp64 atomics whose order varies from launch to launch, and the 12-sample BatchNorm
     channels of a 64x96 image amplify the last-bit differences; the bar is north_star's 1e-3."""
     m, _ = _build(4, (64, 96), precision, training=training)
