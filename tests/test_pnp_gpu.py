@@ -58,8 +58,9 @@ def test_rear_of_front_is_the_uncut_forward(precision, training, tol):
     """rear(front(x)) == forward(x) on the same engine.  Measured on B200: bit-identical in eval mode (both precisions);
     in training mode 8e-5 (fp32) / 4e-2 (bf16: the imported feature is rounded to bf16 once more; bound = the bf16-mode
     bound of smoke(), the level at which the reference's own autocast run differs from its fp32 run) -- the batch
-    statistics are summed with fp64 atomics whose order varies from launch to launch, and the 12-sample BatchNorm
-    channels of a 64x96 image amplify the last-bit differences; the bar is north_star's 1e-3."""
+    statistics are summed with atomics whose order varies from launch to launch (fp32 shared-memory atomics per CTA in
+    the conv epilogue, rd_conv_fprop.cuh:429-435, then fp64 L2 atomics across CTAs), and the variance E[z^2] - mean^2 of
+    the 12-sample BatchNorm channels of a 64x96 image amplifies the last-bit differences; the bar is north_star's 1e-3."""
     m, _ = _build(4, (64, 96), precision, training=training)
     x = _inputs(2, 64, 96, 4)[0].cuda()
     with torch.no_grad():
