@@ -3,8 +3,13 @@
 images/s for one forward + MaskedL1 + backward (+ gradient all-reduce + SGD) training step of
 resnet18_latefusion --decoder upproj, per-GPU batch 16, 352x1216, synthetic RGB + sparse radar.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch 16] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--arch latefusion|multistage] [--batch B]
+                    [--precision bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+--arch latefusion (default) is BASELINE.json configs[1]/[2] (per-GPU b=16); --arch multistage is configs[3]/[4]:
+resnet18_multistage_uncertainty_fixs, per-GPU b=8, the fixs uncertainty loss of main.py:416-429 (two MaskedL1 + 0.1 *
+Smoothness), stage 2 initialised from the stage-1 (latefusion) weights like multistage_model.py:40-49.
 
 Prints ONE JSON line (rank 0).  `value`: device-timed throughput with inputs resident in HBM.  `e2e`: the same step
 through the public API (model(inputs) -> MaskedL1Loss -> backward -> optimizer.step) with the H2D copy of the batch
@@ -30,8 +35,10 @@ if ROOT not in sys.path:
 
 H, W = 352, 1216
 # algorithmic conv FLOPs per image (2*MAC, Unpool's structural zeros excluded, no dgrad for the stems)
-FLOP_FWD_BWD_PER_IMAGE = 120.167e9
-METRIC = "images/sec fwd+bwd resnet18_latefusion b=16 352x1216"
+FLOP_FWD_BWD_PER_IMAGE = {"latefusion": 120.167e9, "multistage": 240.8e9}
+METRICS = {"latefusion": "images/sec fwd+bwd resnet18_latefusion b=16 352x1216",
+           "multistage": "images/sec fwd+bwd resnet18_multistage_uncertainty_fixs b=8 352x1216"}
+DEFAULT_BATCH = {"latefusion": 16, "multistage": 8}
 
 
 def _peaks():
@@ -102,24 +109,25 @@ def synth_host_batch(b, seed, p_lidar=0.05):
     return inputs, target
 
 
-def cpu_reference_throughput(steps: int, warmup: int, batch: int = 2):
+def cpu_reference_throughput(steps: int, warmup: int, batch: int = 2, arch: str = "latefusion"):
     """Times the CPU oracle (the reference's PyTorch path restated in oracle/) on the host cores: bounded sample."""
     import torch
     from oracle import torch_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.synth_state_dict(O.latefusion_entries(4))
+    kind = "latefusion" if arch == "latefusion" else "multistage_fixs"
+    sd = O.synth_state_dict(O.latefusion_entries(4) if arch == "latefusion" else O.multistage_entries())
     inputs, target = O.synth_batch(batch, H, W)
     for _ in range(max(warmup, 1)):
-        O.train_step(sd, inputs, target, "latefusion")
+        O.train_step(sd, inputs, target, kind)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.train_step(sd, inputs, target, "latefusion")
+        O.train_step(sd, inputs, target, kind)
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     return dict(value=batch / med, unit="images/s", cores=cores, kind="port",
-                sample=f"{steps} timed fwd+loss+bwd iterations of b={batch} 352x1216 fp32 (oracle/torch_oracle.train_step, "
+                sample=f"{steps} timed fwd+loss+bwd iterations of {arch} b={batch} 352x1216 fp32 (oracle/torch_oracle.train_step, "
                        f"torch {torch.__version__} CPU kernels, {cores} threads), median {med:.3f} s/iter"), med
 
 
@@ -128,11 +136,11 @@ def run_reference(args):
     if rank != 0:
         return
     steps = min(args.steps, 6)
-    base, med = cpu_reference_throughput(steps, min(args.warmup, 2))
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s", "n_gpus": args.gpus,
+    base, med = cpu_reference_throughput(steps, min(args.warmup, 2), arch=args.arch)
+    line = {"impl": "reference", "metric": METRICS[args.arch], "value": base["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "resnet18_latefusion upproj fwd+MaskedL1+bwd, 352x1216, CPU sample b=2 per step",
+            "config": {"workload": f"resnet18_{args.arch} upproj fwd+loss+bwd, 352x1216, CPU sample b=2 per step",
                        "global_batch": 2, "note": "the reference has no GPU kernels of its own; this arm is its PyTorch CPU path "
                                                   "(oracle port) on the box's host cores"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -146,11 +154,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
+    ap.add_argument("--arch", default="latefusion", choices=["latefusion", "multistage"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 16 latefusion / 8 multistage)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch CUDA-event profile of one step to this file")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.arch]
     if args.impl == "reference":
         run_reference(args)
         return
@@ -158,7 +170,8 @@ def main():
     import torch
     import torch.distributed as dist
     from radar_depth_b200.model.models import ResNet_latefusion
-    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss
+    from radar_depth_b200.model.multistage_model import ResNet_multistage
+    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss, SmoothnessLoss
     from radar_depth_b200.optim import FusedSGD
     from radar_depth_b200 import ddp
 
@@ -175,11 +188,32 @@ def main():
     b = args.batch
 
     torch.manual_seed(0)
-    model = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False).cuda()
-    model.precision = args.precision
+    crit = MaskedL1Loss()
+    if args.arch == "latefusion":
+        model = ResNet_latefusion(18, "upproj", (H, W), 4, pretrained=False).cuda()
+        model.precision = args.precision
+        nets = [model]
+
+        def loss_fn(out, x, t):
+            return crit(out, t)
+    else:
+        model = ResNet_multistage(18, "upproj", (H, W), pretrained=False)
+        # configs[3]: "init from latefusion weights" = multistage_model.py:40-49 with a random latefusion state
+        sd1 = model.stage1.state_dict()
+        model.stage2.load_state_dict(model.filter_state_dict(dict(sd1), model.stage2.state_dict()), strict=False)
+        model.register_parameter("w_stage1", torch.nn.Parameter(torch.tensor(1.0)))      # main.py:166-172
+        model.register_parameter("w_stage2", torch.nn.Parameter(torch.tensor(1.0)))
+        model = model.cuda()
+        model.stage1.precision = model.stage2.precision = args.precision
+        nets = [model.stage1, model.stage2]
+        smooth = SmoothnessLoss()
+
+        def loss_fn(out, x, t):                                                          # main.py:416-429
+            d1, d2 = crit(out["stage1"], t), crit(out["stage2"], t)
+            return torch.exp(-model.w_stage1) * (d1 + 0.1 * smooth(out["stage1"], x)) + torch.exp(-model.w_stage2) * d2 + \
+                model.w_stage1 + model.w_stage2
     model.train()
     ddp.broadcast_parameters(model)
-    crit = MaskedL1Loss()
     opt = FusedSGD(model, lr=0.01, momentum=0.9, weight_decay=1e-4)
 
     h_in, h_tg = synth_host_batch(b, 1234 + rank, p_lidar=0.05)
@@ -190,7 +224,7 @@ def main():
 
     def step(x, t):
         pred = model(x)
-        loss = crit(pred, t)
+        loss = loss_fn(pred, x, t)
         opt.zero_grad()
         loss.backward()
         collectives[0] = ddp.allreduce_gradients(model)
@@ -273,13 +307,20 @@ def main():
     h2d = h_in.numel() * 4 + h_tg.numel() * 4
     d2h = 4
 
-    eng = model._engine
-    launches = eng.launches_per_step() + 3 + 1 + 1        # + l1 fwd (2 kernels) + l1 bwd + sgd + pack is inside fwd
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
+    engs = [n._engine for n in nets]
+    # engine programs + per engine one SGD kernel; losses: MaskedL1 = l1_fwd + ordered_sum + finalize + l1_bwd (4 kernels),
+    # Smoothness = image_sum + smoothness x3 + ordered_sum x3 + finalize (8), SID filter (1)
+    launches = sum(e.launches_per_step() for e in engs) + len(engs) + (4 if args.arch == "latefusion" else 4 + 4 + 8 + 1)
+    eng = engs[0]
+    line = {"metric": METRICS[args.arch], "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32(bf16x3 split)", "data": "synthetic",
-            "config": {"workload": "resnet18_latefusion --decoder upproj, fwd + MaskedL1 + bwd + grad all-reduce + SGD, "
-                                   f"per-GPU b={b}, 352x1216 RGB + sparse radar (BASELINE.json configs[1])",
+            "config": {"workload": ("resnet18_latefusion --decoder upproj, fwd + MaskedL1 + bwd + grad all-reduce + SGD, "
+                                    f"per-GPU b={b}, 352x1216 RGB + sparse radar (BASELINE.json configs[1])") if args.arch == "latefusion"
+                       else ("resnet18_multistage_uncertainty_fixs --decoder upproj, fwd + fixs loss (2x MaskedL1 + 0.1 Smoothness) + bwd + "
+                             f"grad all-reduce + SGD, per-GPU b={b}, 352x1216, stage 2 initialised from the latefusion weights "
+                             "(BASELINE.json configs[3])"),
+                       "arch": args.arch, "deterministic": bool(eng.det),
                        "global_batch": world * b, "parallelism": f"dp{world}", "cuda_graphs": bool(eng.use_graphs),
                        "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
                        "collectives_per_step": collectives[0], "loss_after_warmup": loss0,
@@ -290,9 +331,9 @@ def main():
 
     # ---- roofline of the tcgen05 convolution programs: per-launch CUDA-event timing on the launch stream
     if rank == 0 and not args.no_kernel_timing:
-        line["roofline"] = kernel_roofline(model, d_in, d_tg, crit, b)
+        line["roofline"] = kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, args.arch, args.dump_launches)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_reference_throughput(4, 1)
+        base, _ = cpu_reference_throughput(4, 1, arch=args.arch)
         line["cpu_baseline"] = base
     if rank == 0:
         print(json.dumps(line))
@@ -300,63 +341,111 @@ def main():
         dist.destroy_process_group()
 
 
-def kernel_roofline(model, d_in, d_tg, crit, b):
-    """Times every launch of one training step with CUDA events (eager, same stream) and aggregates the tcgen05
-    convolution programs: achieved = algorithmic conv FLOPs of the step / summed duration of those launches."""
+def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
+    """Times every launch of one training step with CUDA events (eager, same stream).  The headline entry aggregates the
+    tcgen05 convolution programs (achieved = algorithmic conv FLOPs of the step / summed duration of those launches).
+    `classes` splits the launches by the roof that bounds them: convolution programs whose arithmetic
+    intensity (Launch.meta: algorithmic FLOPs / bytes) is above the ridge of the measured peaks count against the tensor
+    roof, the others and every elementwise kernel against the HBM roof."""
     import torch
-    eng = model._engine
     peaks = _peaks()
-    saved = eng.use_graphs
-    eng.use_graphs = False
+    ridge = peaks["bf16_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
+    saved = [e.use_graphs for e in engs]
+    for e in engs:
+        e.use_graphs = False
     try:
         per = {}
         for rep in range(3):
-            pred = model(d_in)           # warm (eager)
-            loss = crit(pred, d_tg)
+            out = model(d_in)            # warm (eager)
+            loss = loss_fn(out, d_in, d_tg)
             loss.backward()
         torch.cuda.synchronize()
         st = torch.cuda.current_stream().cuda_stream
         reps = 3
-        for prog_name, prog in (("fwd", eng.fwd), ("bwd", eng.bwd)):
-            for L in prog:
-                # `reps` launches back to back inside one event pair (the queue hides host launch latency)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    rc = L.fn(*L.args, st)
-                    assert rc == 0, L.name
-                e1.record()
-                torch.cuda.synchronize()
-                t = e0.elapsed_time(e1) / reps
-                kind = L.name.split(":")[0]
-                per.setdefault(kind, [0.0, 0])
-                per[kind][0] += t
-                per[kind][1] += 1
+        cls = {"tensor_bound_convs": [0.0, 0, 0.0, 0.0], "hbm_bound_convs": [0.0, 0, 0.0, 0.0], "elementwise": [0.0, 0, 0.0, 0.0]}
+        worst = []
+        from radar_depth_b200 import determinism
+        for eng in engs:
+            for prog_name, prog in (("fwd", eng.fwd), ("bwd", eng.bwd)):
+                for L in prog:
+                    # `reps` launches back to back inside one event pair (the queue hides host launch latency)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    with determinism.mode(eng.det_scratch if eng.det else None):
+                        e0.record()
+                        for _ in range(reps):
+                            rc = L.fn(*L.args, st)
+                            assert rc == 0, L.name
+                        e1.record()
+                    torch.cuda.synchronize()
+                    t = e0.elapsed_time(e1) / reps
+                    kind = L.name.split(":")[0]
+                    per.setdefault(kind, [0.0, 0])
+                    per[kind][0] += t
+                    per[kind][1] += 1
+                    meta = L.meta or {}
+                    is_conv = kind in ("conv_f", "conv_d", "wgrad")
+                    if is_conv:
+                        key = "tensor_bound_convs" if meta["flops"] / meta["bytes"] >= ridge else "hbm_bound_convs"
+                    else:
+                        key = "elementwise"
+                    c = cls[key]
+                    c[0] += t
+                    c[1] += 1
+                    c[2] += meta.get("flops", 0.0)
+                    c[3] += meta.get("bytes", 0.0)
+                    if meta.get("bytes"):
+                        frac = (meta["flops"] / (t * 1e-3) / 1e12 / peaks["bf16_sustained"]) if key == "tensor_bound_convs" \
+                            else (meta["bytes"] / (t * 1e-3) / 1e9 / peaks["hbm"])
+                        worst.append((t, L.name, key, round(frac, 3)))
         conv_ms = sum(v[0] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
         conv_n = sum(v[1] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
         total_ms = sum(v[0] for v in per.values())
-        flops = FLOP_FWD_BWD_PER_IMAGE * b
+        flops = FLOP_FWD_BWD_PER_IMAGE[arch] * b
         achieved = flops / (conv_ms * 1e-3) / 1e12
+        classes = {}
+        for k, (ms, n, fl, by) in cls.items():
+            ent = {"launches": n, "ms_per_step": round(ms, 4), "algorithmic_gflop": round(fl / 1e9, 2), "algorithmic_gbytes": round(by / 1e9, 3)}
+            if ms > 0:
+                if k == "tensor_bound_convs":
+                    ent.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, unit="TFLOP/s", peak=peaks["bf16_sustained"])
+                else:
+                    ent.update(bound="hbm", achieved=by / (ms * 1e-3) / 1e9, unit="GB/s", peak=peaks["hbm"])
+                ent["frac"] = ent["achieved"] / ent["peak"]
+            classes[k] = ent
+        worst.sort(reverse=True)
+        if dump_path:
+            os.makedirs(os.path.dirname(dump_path) or ".", exist_ok=True)
+            with open(dump_path, "w") as fh:
+                fh.write(f"# {arch} b={b}: per-launch CUDA-event times of one step (eager, {reps} back-to-back launches each); "
+                         f"frac = fraction of the roof that bounds the launch (tensor {peaks['bf16_sustained']} TFLOP/s sustained / HBM {peaks['hbm']} GB/s)\n")
+                fh.write(f"# total {total_ms:.3f} ms over {sum(v[1] for v in per.values())} launches; by kind: "
+                         + json.dumps({k: round(v[0], 4) for k, v in sorted(per.items())}) + "\n")
+                for t, n, k, f in worst:
+                    fh.write(f"{t:9.4f} ms  {k:20s} {f:6.3f}  {n}\n")
         # DRAM bytes per conv launch from the committed ncu launch list of this same command (profiles/): only valid for
-        # the configuration that capture was taken on (b=16 bf16)
-        traffic = None
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")) as fh:
-                if b == 16:
-                    traffic = json.load(fh)["traffic_bytes_per_launch"]
-        except Exception:
-            traffic = None
+        # the configuration that capture was taken on (latefusion b=16 bf16)
+        traffic, traffic_src = None, None
+        for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    if b == 16 and arch == "latefusion":
+                        traffic, traffic_src = json.load(fh)["traffic_bytes_per_launch"], name
+                        break
+            except Exception:
+                continue
         return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write per conv launch, ncu launch list (cold cache per launch), bytes",
+                "traffic_note": f"dram__bytes_read+write per conv launch, ncu launch list (cold cache per launch), bytes; profiles/{traffic_src}",
                 "peak_source": peaks["source"] + " (sustained bf16)",
                 "kernel": "conv_fprop_kernel + conv_wgrad_kernel (tcgen05 implicit-GEMM programs)",
                 "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "conv_ms_per_step": conv_ms,
                 "all_kernels_ms_per_step": total_ms, "conv_share_of_step": conv_ms / total_ms,
                 "by_kind_ms": {k: round(v[0], 4) for k, v in sorted(per.items())},
-                "algorithmic_flop_per_step": flops}
+                "algorithmic_flop_per_step": flops, "ridge_flop_per_byte": round(ridge, 1), "classes": classes,
+                "slowest_launches": [dict(ms=round(t, 4), name=n, cls=k, frac_of_roof=f) for t, n, k, f in worst[:12]]}
     finally:
-        eng.use_graphs = saved
+        for e, u in zip(engs, saved):
+            e.use_graphs = u
 
 
 if __name__ == "__main__":

@@ -45,6 +45,17 @@ int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params, 2: rd_bn_tai
 /* reads and clears the device-side error word (0 = none).  Synchronises the stream. */
 int rd_device_error(void* stream);
 
+/* Deterministic mode.  The reference's training step is reproducible on its CPU path; its cuDNN path is not
+ * (torch.backends.cudnn.deterministic is never set, main.py:11,47).  With on != 0 every launch issued by the CALLING THREAD
+ * afterwards (the flag is thread-local and read at launch time, so it is baked into a captured CUDA graph) replaces its
+ * floating-point atomics by fixed-order sums: BatchNorm statistics (conv epilogues, rd_join_bwd, rd_maxpool_bwd), weight
+ * gradients (rd_conv_wgrad, rd_head_conv_bwd) and the loss sums (rd_l1_fwd, rd_smoothness_*) become bit-identical from run
+ * to run.  scratch = caller-owned device buffer (256-byte aligned, >= 1 MiB and >= max over the weight-gradient launches of
+ * max_ctas * ntaps * Cout * Cin * 4 bytes) that holds the per-CTA partials; launches that use it must be stream-ordered.
+ * The parity mode (act_dtype RD_F32) of the Python layer switches it on by default. */
+int rd_set_deterministic(int on, void* scratch, long long scratch_bytes);
+int rd_get_deterministic(void);
+
 /* NHWC view of a [B, H, W, C] slice living inside a [B, H, W, pitch] buffer. */
 typedef struct rd_view {
     void* ptr;

@@ -126,7 +126,7 @@ def run_pnp(ref, b, h, w, training, seed_sd=7):
             "pred": pred.detach().numpy(), "dfeature": feat.grad.numpy()}
 
 
-def run_multistage(ref, b, h, w, seed_sd=7):
+def run_multistage(ref, b, h, w, seed_sd=7, full_pred=True):
     from oracle import torch_oracle as O
     ent = O.multistage_entries()
     sd = O.synth_state_dict(ent, seed=seed_sd)
@@ -150,7 +150,8 @@ def run_multistage(ref, b, h, w, seed_sd=7):
     return {
         "loss": np.float64(loss.item()), "l1_stage1": np.float64(d1.item()), "l1_stage2": np.float64(d2.item()),
         "smooth": np.float64(s.item()), "b": b, "h": h, "w": w,
-        "stage1": o["stage1"].detach().numpy(), "stage2": o["stage2"].detach().numpy(),
+        "stage1": o["stage1"].detach().numpy() if full_pred else _subsample(o["stage1"]),
+        "stage2": o["stage2"].detach().numpy() if full_pred else _subsample(o["stage2"]),
         "mask_sum": np.float64(o["mask"].sum().item()),
         "radar_filtered_sum": np.float64(o["radar_filtered"].sum().item()),
         "grad_names": names, "grad_norms": norms, "grad_heads": heads,
@@ -206,6 +207,7 @@ def main():
         "latefusion2_c5_train_b2_64x96": lambda: run_latefusion(ref, 2, 64, 96, in_channels=5),
         "latefusion_train_b2_352x1216": lambda: run_latefusion(ref, 2, 352, 1216, full_pred=False),
         "multistage_fixs_train_b2_64x96": lambda: run_multistage(ref, 2, 64, 96),
+        "multistage_fixs_train_b2_352x1216": lambda: run_multistage(ref, 2, 352, 1216, full_pred=False),   # configs[3] shape
         "pnp_train_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, True),
         "pnp_eval_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, False),
         "losses_filter": lambda: run_losses(ref),

@@ -94,6 +94,8 @@ _PROTOS = {
     "rd_version": ([], _I),
     "rd_sizeof": ([_I], _I),
     "rd_device_error": ([_P], _I),
+    "rd_set_deterministic": ([_I, _P, _LL], _I),
+    "rd_get_deterministic": ([], _I),
     "rd_conv_fprop": ([C.POINTER(ConvParams), _P], _I),
     "rd_conv_wgrad": ([C.POINTER(WgradParams), _P], _I),
     "rd_input_pack": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),

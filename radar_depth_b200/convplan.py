@@ -235,7 +235,7 @@ class FpropPlan:
     info: dict = field(default_factory=dict)
 
 
-def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16):
+def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16, budget=SMEM_BUDGET):
     """Tile search.  The cost model was fitted to per-role cycle counters measured on B200 (tools/bench_fprop.py):
     UMMA ~max(48, N/2) cycles each, epilogue ~40 cycles per 16 columns per 32 rows (overlapped with the next tile
     when two accumulator sets fit in TMEM), ~2.5k cycles of pipeline hand-off per tile, and a strong preference for
@@ -258,7 +258,7 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
             plane_rows = Ht + halo_y
             plane_slots = _round_up(M + halo_y * Wl + halo_x, 8)
             istage = _round_up(parts * 2 * _chunk_stride(planes * plane_slots, 2) * 16, 128)
-            if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > SMEM_BUDGET:
+            if FPROP_HEADER + 2 * istage + 2 * wstage_bytes > budget:
                 continue
             ty, tx = -(-Hb // Ht), -(-Wb // Wt)
             mma = MB * ntaps * max(N, 96) / 2.0 * (3 if parts == 2 else 1)
@@ -281,8 +281,10 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
 
 
 def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, n_per_cta: Optional[int] = None,
-               tile_override: Optional[dict] = None, use_tuned: bool = True) -> FpropPlan:
+               tile_override: Optional[dict] = None, use_tuned: bool = True, smem_reserve: int = 0) -> FpropPlan:
+    """smem_reserve: bytes of dynamic shared memory the launcher needs behind the rings (deterministic statistics)."""
     assert g.Cx % 16 == 0 and g.N % 16 == 0, (g.Cx, g.N)
+    budget = SMEM_BUDGET - smem_reserve
     parts = 2 if act_dtype == _lib.RD_F32 else 1
     taps, phases = g.sorted_taps()
     P = len(phases)
@@ -313,9 +315,9 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     wstage = _round_up(max(grp_n) * tap_bytes, 128)
     if tile_override is None and use_tuned:
         tile_override = tuned_table().get(tune_key("f", g, B, src_hw, dst_hw, act_dtype))
-    geo = tile_override or _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B)
+    geo = None
     if tile_override:
-        geo = dict(geo)
+        geo = dict(tile_override)
         geo.setdefault("Wl", geo["Wt"] + halo_x)
         geo.setdefault("MB", -(-geo["Ht"] * geo["Wl"] // 128))
         M = geo["MB"] * 128
@@ -323,17 +325,21 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
         geo["plane_slots"] = _round_up(M + halo_y * geo["Wl"] + halo_x, 8)
         geo["istage"] = _round_up(parts * 2 * _chunk_stride(g.S * g.S * geo["plane_slots"], 2) * 16, 128)
         geo["tiles_y"], geo["tiles_x"] = -(-Hb // geo["Ht"]), -(-Wb // geo["Wt"])
+        if FPROP_HEADER + 2 * geo["istage"] + 2 * wstage > budget:
+            geo = None                                     # a measured tile that no longer fits (smem_reserve): re-plan
+    if geo is None:
+        geo = _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B, budget)
     istage = geo["istage"]
     # ring depths within the shared-memory budget
-    avail = SMEM_BUDGET - FPROP_HEADER
+    avail = budget - FPROP_HEADER
     IS = 2
     WS = 2
     while True:
         grown = False
-        if WS < 4 and FPROP_HEADER + IS * istage + (WS + 1) * wstage <= SMEM_BUDGET:
+        if WS < 4 and FPROP_HEADER + IS * istage + (WS + 1) * wstage <= budget:
             WS += 1
             grown = True
-        if IS < 3 and FPROP_HEADER + (IS + 1) * istage + WS * wstage <= SMEM_BUDGET:
+        if IS < 3 and FPROP_HEADER + (IS + 1) * istage + WS * wstage <= budget:
             IS += 1
             grown = True
         if not grown:

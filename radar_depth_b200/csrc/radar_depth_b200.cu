@@ -29,10 +29,27 @@ int check_cuda(cudaError_t e, const char* what) {
 
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
 
-template <typename K>
-int set_smem(K kernel, int bytes) {
-    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+constexpr int kMaxDevices = 64;
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remembered per device, so a
+// process that drives several GPUs opts in on each of them.  `done` is the caller's per-kernel table.
+template <typename K>
+int set_smem(K kernel, int bytes, bool* done) {
+    const int dev = current_device();
+    if (done[dev]) return RD_OK;
+    int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+    if (rc == RD_OK) done[dev] = true;
+    return rc;
+}
+
+// ---- deterministic mode (rd_set_deterministic): thread-local, read by the launchers at launch time
+thread_local int g_det = 0;
+thread_local char* g_scratch = nullptr;
+thread_local long long g_scratch_bytes = 0;
 
 // ---- TMA tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -77,14 +94,13 @@ bool encode_nhwc_map(CUtensorMap* map, const rd_view& v, int B, int H, int W, in
 }
 
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 }  // namespace
@@ -92,7 +108,19 @@ int num_sms() {
 extern "C" {
 
 const char* rd_last_error(void) { return g_err.c_str(); }
-int rd_version(void) { return 1; }
+int rd_version(void) { return 2; }
+
+int rd_set_deterministic(int on, void* scratch, long long scratch_bytes) {
+    if (on && (!scratch || scratch_bytes < (1ll << 20) || ((uintptr_t)scratch & 255))) {
+        g_det = 0;
+        return fail(RD_EINVAL, "rd: deterministic mode needs a 256-byte aligned device scratch buffer of at least 1 MiB");
+    }
+    g_det = on ? 1 : 0;
+    g_scratch = on ? (char*)scratch : nullptr;
+    g_scratch_bytes = on ? scratch_bytes : 0;
+    return RD_OK;
+}
+int rd_get_deterministic(void) { return g_det; }
 
 int rd_sizeof(int which) {
     switch (which) {
@@ -152,18 +180,28 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     RD_REQUIRE(p->stats == nullptr || p->stats_stride >= p->nblk * p->N, "stats_stride too small");
     RD_REQUIRE(p->tail.counter == nullptr || p->stats != nullptr, "a fused BatchNorm finalisation needs the statistics epilogue");
     { const char* e = check_tail(p->tail); if (e) return fail(RD_EINVAL, e); }
-    const long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes;
-    RD_REQUIRE(smem <= kMaxSmem, "shared memory budget exceeded");
     const int ntiles = p->tiles_y * p->tiles_x * p->B;
     RD_REQUIRE(ntiles > 0 && p->nblk >= 1, "empty problem");
     int gx = ntiles;
     if (p->max_ctas > 0 && gx > p->max_ctas) gx = p->max_ctas;
+    // deterministic statistics: per-warp arrays behind the rings, per-CTA partials in the registered scratch buffer
+    float* det_part = nullptr;
+    long long det_smem = 0;
+    if (g_det && p->stats != nullptr) {
+        RD_REQUIRE(p->tail.counter != nullptr, "deterministic statistics need the fused BatchNorm finalisation (rd_bn_tail)");
+        det_smem = 8ll * 2 * p->N * 4;
+        RD_REQUIRE((long long)gx * p->nblk * 2 * p->N * 4 <= g_scratch_bytes, "deterministic mode: scratch buffer too small");
+        det_part = (float*)g_scratch;
+    }
+    const long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes + det_smem;
+    RD_REQUIRE(smem <= kMaxSmem, "shared memory budget exceeded");
     dim3 grid(gx, p->nblk, 1), block(rd::kFpropThreads, 1, 1);
     cudaStream_t st = (cudaStream_t)stream;
     // Raw bf16 stride-1 source tiles go through TMA: one box (8 ch, Wl, plane_rows, 2 chunks) per 16-channel stage.  TMA
     // writes the two chunk planes plane_rows*Wl slots apart, so the kernel gets that chunk stride; the slots a tap shift
     // reads past a plane (junk accumulator rows, never stored) must still lie inside the stage.
     rd_conv_params q = *p;
+    if (det_part) q.tail.slots = 1;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     int use_tma = 0;
@@ -176,13 +214,13 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
         }
     }
     if (p->act_dtype == RD_BF16) {
-        static bool once = false;
-        if (!once) { int rc = set_smem(rd::conv_fprop_kernel<rd::bf16, 1>, kMaxSmem); if (rc) return rc; once = true; }
-        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(q, map, use_tma);
+        static bool done[kMaxDevices] = {false};
+        { int rc = set_smem(rd::conv_fprop_kernel<rd::bf16, 1>, kMaxSmem, done); if (rc) return rc; }
+        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(q, map, use_tma, det_part);
     } else if (p->act_dtype == RD_F32) {
-        static bool once = false;
-        if (!once) { int rc = set_smem(rd::conv_fprop_kernel<float, 3>, kMaxSmem); if (rc) return rc; once = true; }
-        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(q, map, 0);
+        static bool done[kMaxDevices] = {false};
+        { int rc = set_smem(rd::conv_fprop_kernel<float, 3>, kMaxSmem, done); if (rc) return rc; }
+        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(q, map, 0, det_part);
     } else {
         return fail(RD_EINVAL, "rd: bad act_dtype");
     }

@@ -205,12 +205,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Exact n / d for n * d < 2^32 with one multiply-high (d is a runtime constant of the launch).
+// n / d with one multiply-high (d is a runtime constant of the launch), m = floor((2^32-1)/d) + 1.
+// FastDivS: exact only while n * d < 2^32 -- for tile-local indices (n < 2^16) in the convolution loaders.
+struct FastDivS {
+    uint32_t m, d;
+    __device__ __forceinline__ FastDivS() : m(0), d(1) {}
+    __device__ __forceinline__ explicit FastDivS(uint32_t d_) : m(d_ > 1 ? 0xFFFFFFFFu / d_ + 1u : 0u), d(d_) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
+};
+// FastDiv: exact for every n < 2^31 (flat pixel indices of whole tensors).  The multiply-high estimate is the true
+// quotient or one above it (m*d - 2^32 lies in (0, d]), so one multiply-compare corrects it.  The uncorrected form
+// returned row+1 for the last pixels of a B=16 352x1216 prediction (n*d > 2^32).
 struct FastDiv {
     uint32_t m, d;
     __device__ __forceinline__ FastDiv() : m(0), d(1) {}
     __device__ __forceinline__ explicit FastDiv(uint32_t d_) : m(d_ > 1 ? 0xFFFFFFFFu / d_ + 1u : 0u), d(d_) {}
-    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const {
+        if (d <= 1) return n;
+        uint32_t q = __umulhi(n, m);
+        if (q * d > n) --q;
+        return q;
+    }
 };
 
 // ---------------------------------------------------------------- fused BatchNorm finalisation (rd_bn_tail)

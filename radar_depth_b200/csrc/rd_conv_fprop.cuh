@@ -79,7 +79,8 @@ __device__ __forceinline__ int reduce16_owner_channel(int lane) {
 
 template <typename T, int SPLIT>
 __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __grid_constant__ rd_conv_params p,
-                                                                      const __grid_constant__ CUtensorMap src_map, const int use_tma) {
+                                                                      const __grid_constant__ CUtensorMap src_map, const int use_tma,
+                                                                      float* const det_part) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* in_full = bars;                       // [kMaxStages]
@@ -100,6 +101,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     float* ld_sh = reinterpret_cast<float*>(smem + kOffLdShift);
     uint8_t* a_ring = smem + kSmemHeader;
     uint8_t* w_ring = a_ring + (size_t)p.IS * p.istage_bytes;
+    // Deterministic mode (det_part != nullptr, rd_set_deterministic): every epilogue warp sums its statistics into a
+    // private [2][N] array behind the rings (plain adds, fixed tile order), the CTA adds those arrays in warp order, stores
+    // its partial to det_part[cta][2][N], and the last CTA adds the partials of all CTAs in index order -- no
+    // floating-point atomics anywhere, so two runs give bit-identical BatchNorm statistics.
+    float* det_s = reinterpret_cast<float*>(w_ring + (size_t)p.WS * p.wstage_bytes);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWarpMma = 4 + kFpropLoaderWarps, kWarpW = kWarpMma + 1;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             const int widx = warp - 5, nwork = kFpropLoaderWarps - 1;
             const int cs = p.chunk_stride;                 // = plane_rows * Wl in this mode
             const int items = 2 * p.plane_rows * p.Wl;
-            const FastDiv fd_cs((uint32_t)cs), fd_wl((uint32_t)p.Wl);
+            const FastDivS fd_cs((uint32_t)cs), fd_wl((uint32_t)p.Wl);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int trem = tile - img * tiles_per_img;
@@ -364,7 +370,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
         const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
         const bool want_stats = p.stats != nullptr;
-        const FastDiv fd_wl((uint32_t)p.Wl);
+        const FastDivS fd_wl((uint32_t)p.Wl);
+        float* det_mine = det_part ? det_s + (size_t)(eg * 4 + wq) * 2 * p.N : nullptr;
+        if (det_mine) {
+            for (int i = lane; i < 2 * p.N; i += 32) det_mine[i] = 0.f;
+            __syncwarp();
+        }
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
             const int img = tile / tiles_per_img;
@@ -431,8 +442,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     const float r2 = reduce16_lanes(s2, lane);
                     if ((lane & 1) == 0) {
                         const int chn = cc * 16 + reduce16_owner_channel(lane);
-                        atomicAdd(&stats_s[chn], r1);
-                        atomicAdd(&stats_s[256 + chn], r2);
+                        if (det_mine) {
+                            det_mine[chn] += r1;                 // this lane pair is the only writer of the entry
+                            det_mine[p.N + chn] += r2;
+                        } else {
+                            atomicAdd(&stats_s[chn], r1);
+                            atomicAdd(&stats_s[256 + chn], r2);
+                        }
                     }
                 }
             }
@@ -449,10 +465,19 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             if (neg == 2) asm volatile("bar.sync 1, 256;\n" ::: "memory");      // both epilogue groups have added their partials
             else asm volatile("bar.sync 1, 128;\n" ::: "memory");
             if (eg == 0) {
-                double* sdst = p.stats + (size_t)((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned)tail_slots(p.tail)) * p.tail.slot_stride;
-                for (int i = tid; i < p.N; i += 128) {
-                    atomicAdd(&sdst[nb * p.N + i], (double)stats_s[i]);
-                    atomicAdd(&sdst[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
+                if (det_part) {
+                    float* mypart = det_part + (size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 2 * p.N;
+                    for (int i = tid; i < 2 * p.N; i += 128) {
+                        float s = 0.f;
+                        for (int w = 0; w < 4 * neg; ++w) s += det_s[(size_t)w * 2 * p.N + i];
+                        mypart[i] = s;
+                    }
+                } else {
+                    double* sdst = p.stats + (size_t)((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned)tail_slots(p.tail)) * p.tail.slot_stride;
+                    for (int i = tid; i < p.N; i += 128) {
+                        atomicAdd(&sdst[nb * p.N + i], (double)stats_s[i]);
+                        atomicAdd(&sdst[p.stats_stride + nb * p.N + i], (double)stats_s[256 + i]);
+                    }
                 }
                 if (p.tail.counter) {
                     // last CTA to get here finalises the BatchNorm(s) fed by these statistics (rd_bn_tail)
@@ -462,6 +487,22 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     asm volatile("bar.sync 2, 128;\n" ::: "memory");
                     if (tmem_slot[1]) {
                         __threadfence();
+                        if (det_part) {
+                            // channel ch belongs to N block ch / N: add the partials of that block's CTAs in x order
+                            for (int ch = tid; ch < (int)gridDim.y * p.N; ch += 128) {
+                                const int y = ch / p.N, i = ch - y * p.N;
+                                double a = 0.0, b = 0.0;
+                                for (unsigned x = 0; x < gridDim.x; ++x) {
+                                    const float* q = det_part + (size_t)(x + gridDim.x * y) * 2 * p.N;
+                                    a += (double)__ldcg(q + i);
+                                    b += (double)__ldcg(q + p.N + i);
+                                }
+                                p.stats[ch] = a;
+                                p.stats[p.stats_stride + ch] = b;
+                            }
+                            __threadfence();
+                            asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                        }
                         bn_tail_run(p.tail, tid, 128);
                     }
                     asm volatile("bar.sync 2, 128;\n" ::: "memory");

@@ -30,11 +30,26 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
+// Deterministic mode: the pixel-split CTA blockIdx.x stores its accumulators to its own copy of dw (det = true) and
+// wgrad_reduce_kernel adds the copies in index order; otherwise vector fp32 reductions straight into dw.
+__device__ __forceinline__ void acc_out_v4(bool det, float* p, float a, float b, float c, float d) {
+    if (det) *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    else red_add_v4(p, a, b, c, d);
+}
+// dw[i] += part[0][i] + part[1][i] + ... (fixed order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, size_t n, float* __restrict__ dw) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nparts; ++k) s += part[(size_t)k * n + i];
+        dw[i] += s;
+    }
+}
 
 template <typename T, int SPLIT>
 __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ rd_wgrad_params p,
                                                                       const __grid_constant__ CUtensorMap g_map,
-                                                                      const __grid_constant__ CUtensorMap x_map, const int tma_mode) {
+                                                                      const __grid_constant__ CUtensorMap x_map, const int tma_mode,
+                                                                      float* const det_part) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* full = bars;
@@ -167,7 +182,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             if (x_bn && !(p.dbg_flags & 2)) {
                 // fused BatchNorm + activation of the source tile, in place (zero padding stays zero)
                 const int xitems = x_chunks * XPS;               // XPS = x_plane_rows * Wl in this mode
-                const FastDiv fd_xps((uint32_t)XPS), fd_wl((uint32_t)p.Wl);
+                const FastDivS fd_xps((uint32_t)XPS), fd_wl((uint32_t)p.Wl);
                 uint4* xb = reinterpret_cast<uint4*>(sbase + p.g_bytes);
                 for (int it = widx * 32 + lane; it < xitems; it += nworkers * 32) {
                     const int j = (int)fd_xps.div((uint32_t)it), sl = it - j * XPS;
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
                 const int jc = p.Wl - p.Wt;
                 const int items = p.Ht * jc * g_chunks * g_planes;       // planes and chunk planes are all KS slots apart
-                const FastDiv fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
+                const FastDivS fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
                 for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
                     const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
                     const int j = (int)fd_ht.div((uint32_t)q), r = q - j * p.Ht;
@@ -283,6 +298,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tc_fence_after();
         const int row = warp * 32 + lane;                 // output channel within the block
         const bool valid = has_work && row < p.Mc && (co0 + row) < p.Cout;
+        const bool det = det_part != nullptr;
+        float* const dwo = det ? det_part + (size_t)blockIdx.x * ((size_t)p.ntaps * p.Cout * p.Cin) : p.dw;
         if ((SPLIT == 1) && p.fold_len > 0) {
             // folded accumulators: job (row, chunk jx) holds columns [tap-in-row][8 channels of chunk jx]
             const int njobs = p.fold_rows * x_chunks;
@@ -296,9 +313,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                         for (int h = 0; h < 2; ++h) {
                             const int tx = cc * 2 + h;
                             if (tx < p.fold_len) {
-                                float* out = p.dw + ((size_t)(rowi * p.fold_len + tx) * p.Cout + (co0 + row)) * p.Cin + ci0 + jx * 8;
-                                red_add_v4(out, v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
-                                red_add_v4(out + 4, v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
+                                float* out = dwo + ((size_t)(rowi * p.fold_len + tx) * p.Cout + (co0 + row)) * p.Cin + ci0 + jx * 8;
+                                acc_out_v4(det, out, v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
+                                acc_out_v4(det, out + 4, v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
                             }
                         }
                     }
@@ -306,13 +323,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             }
         } else
         for (int tl = 0; tl < T_n; ++tl) {
-            float* out = p.dw + ((size_t)(t0 + tl) * p.Cout + (co0 + row)) * p.Cin + ci0;
+            float* out = dwo + ((size_t)(t0 + tl) * p.Cout + (co0 + row)) * p.Cin + ci0;
             for (int cc = 0; cc < (p.Nc >> 4); ++cc) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * p.Nc + cc * 16), v);
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) red_add_v4(out + cc * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 16; i += 4) acc_out_v4(det, out + cc * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
             }
         }

@@ -10,7 +10,10 @@ namespace rd {
 
 // Ticket + fused BatchNorm finalisation for the channel-reducing kernels: call after the block's statistics atomics
 // with ALL threads of the block.
-__device__ __forceinline__ void block_bn_tail(const rd_bn_tail& t) {
+// Deterministic mode (det_part != nullptr): the blocks have stored their partial sums to det_part[block][na][C]
+// (block_channel_reduce); the last block adds them in block order into outs[a][c] before finalising.
+__device__ __forceinline__ void block_bn_tail(const rd_bn_tail& t, const float* det_part = nullptr, int na = 0, int C = 0,
+                                              double* const* outs = nullptr) {
     if (t.counter == nullptr) return;
     __shared__ unsigned int s_last;
     __threadfence();
@@ -19,11 +22,35 @@ __device__ __forceinline__ void block_bn_tail(const rd_bn_tail& t) {
     __syncthreads();
     if (s_last) {
         __threadfence();
+        if (det_part) {
+            const int n = na * C;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double s = 0.0;
+                for (unsigned b = 0; b < gridDim.x; ++b) s += (double)__ldcg(det_part + (size_t)b * n + i);
+                const int a = i / C;
+                outs[a][i - a * C] = s;
+            }
+            __threadfence();
+            __syncthreads();
+        }
         bn_tail_run(t, (int)threadIdx.x, (int)blockDim.x);
     }
 }
 
 struct VView { void* ptr; int pitch; int coff; };   // same as rd_view, device-side
+
+// Deterministic mode helper: out[j] (+)= part[0][j] + part[1][j] + ... + part[nparts-1][j], part[k][j] at part[k*stride + j].
+// One warp per output: lane l adds the parts l, l+32, ... in order, then a fixed shuffle tree -- the result depends only
+// on the values, never on scheduling.  Launch with grid = nout, block = 32.
+template <typename TI, typename TO>
+__global__ void ordered_sum_kernel(const TI* __restrict__ part, int nparts, int stride, TO* __restrict__ out, int accumulate) {
+    const int j = blockIdx.x, lane = threadIdx.x;
+    double s = 0.0;
+    for (int k = lane; k < nparts; k += 32) s += (double)part[(size_t)k * stride + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[j] = accumulate ? (TO)((double)out[j] + s) : (TO)s;
+}
 
 template <typename T>
 __device__ __forceinline__ const T* vptr(const VView& v, size_t pix, int c) {
@@ -145,7 +172,25 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
 // NA accumulators per channel; smem partials then one fp64 atomic per channel per block.
 template <int NA>
 __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, int C, float* red_s, double* const* outs,
-                                                     const rd_bn_tail& tail) {
+                                                     const rd_bn_tail& tail, float* det_part = nullptr) {
+    if (det_part) {
+        // deterministic: every thread parks its accumulators in shared memory ([thread][NA][8]); channel c is then added
+        // over the threads that own its group (thread = pl * groups + cg) in pl order and stored as this block's partial
+        const int groups_ = C >> 3, ppb = blockDim.x / groups_;
+        float* mine = red_s + (size_t)threadIdx.x * NA * 8;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mine[a * 8 + k] = acc[a][k];
+        __syncthreads();
+        for (int i = threadIdx.x; i < NA * C; i += blockDim.x) {
+            const int a = i / C, c = i - a * C, cgi = c >> 3, k = c & 7;
+            float s = 0.f;
+            for (int pl = 0; pl < ppb; ++pl) s += red_s[((size_t)(pl * groups_ + cgi) * NA + a) * 8 + k];
+            det_part[(size_t)blockIdx.x * NA * C + i] = s;
+        }
+        return;
+    }
     // red_s: [copies][NA][C] floats (zeroed here).  With fewer than 32 channel groups many threads of a warp own the
     // same group: lanes are first combined with shuffles (power-of-two group counts) and every warp gets a private
     // copy, so that at most a handful of shared-memory atomics ever collide on one address.
@@ -252,7 +297,8 @@ __global__ void __launch_bounds__(256) bn_add_act_kernel(VView z, const float* _
 // Writes g (may alias dout).  Autograd of the residual join + ReLU.
 template <typename T>
 __global__ void __launch_bounds__(256, 3) join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
-                                double* sum_g, double* sum_gz, double* sum_gzid, const __grid_constant__ rd_bn_tail tail) {
+                                double* sum_g, double* sum_gz, double* sum_gzid, const __grid_constant__ rd_bn_tail tail,
+                                float* det_part) {
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -305,9 +351,9 @@ __global__ void __launch_bounds__(256, 3) join_bwd_kernel(VView dout, VView outv
         }
     }
     double* outs[3] = {sum_g, sum_gz, sum_gzid};
-    if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs, tail);
-    else block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
-    block_bn_tail(tail);
+    if (zid.ptr) block_channel_reduce<3>(acc, cg, C, red_s, outs, tail, det_part);
+    else block_channel_reduce<2>(acc, cg, C, red_s, outs, tail, det_part);
+    block_bn_tail(tail, det_part, zid.ptr ? 3 : 2, C, outs);
 }
 
 // bn_bwd_apply: dz = A*g + Bz*z + Cc (per channel).  dz may alias g.
@@ -515,7 +561,7 @@ template <typename T>
 __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restrict__ amax, VView z,
                                    const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
                                    int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
-                                   double* sum_gz, const __grid_constant__ rd_bn_tail tail) {
+                                   double* sum_gz, const __grid_constant__ rd_bn_tail tail, float* det_part) {
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -575,8 +621,8 @@ __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restri
         }
     }
     double* outs[2] = {sum_g, sum_gz};
-    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
-    block_bn_tail(tail);
+    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail, det_part);
+    block_bn_tail(tail, det_part, 2, C, outs);
 }
 
 // Tiled bf16 fast path of maxpool_bwd: persistent blocks walk 4 x 32 input-pixel tiles.  A window sends its gradient to
@@ -589,7 +635,7 @@ constexpr int kMbTileH = 4, kMbTileW = 32, kMbWinH = kMbTileH / 2 + 1, kMbWinW =
 __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VView dpb, const uint8_t* __restrict__ amax, VView z,
                                         const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
                                         int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
-                                        double* sum_gz, const __grid_constant__ rd_bn_tail tail) {
+                                        double* sum_gz, const __grid_constant__ rd_bn_tail tail, float* det_part) {
     extern __shared__ __align__(16) uint8_t mb_smem[];
     const int G = C >> 3;
     float* accum = reinterpret_cast<float*>(mb_smem);                                // [kMbTileH*kMbTileW][C] fp32, zero between tiles
@@ -687,8 +733,8 @@ __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VVi
         __syncthreads();
     }
     double* outs[2] = {sum_g, sum_gz};
-    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail);
-    block_bn_tail(tail);
+    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail, det_part);
+    block_bn_tail(tail, det_part, 2, C, outs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -744,9 +790,10 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(VView x, const float
 // out of the register cliff (it is a pure bandwidth kernel: 16 B in, 16 B out per thread and iteration).
 template <typename T>
 __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w,
-                                                             int B, int H, int W, VView dx, float* dw /*[144]*/) {
+                                                             int B, int H, int W, VView dx, float* dw /*[144]*/, float* det_part) {
     __shared__ __align__(16) float ws[144];            // [half][tap][8]: a tap's 8 weights of one half = two LDS.128
     __shared__ float dws[144];
+    __shared__ float dws_w[8][144];                    // deterministic mode: one copy per warp, added in warp order
     for (int i = threadIdx.x; i < 144; i += blockDim.x) {
         const int c = i / 9, t = i - c * 9;
         ws[(c >> 3) * 72 + t * 8 + (c & 7)] = w[i];
@@ -799,9 +846,21 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __re
             float s = wacc[t][c];
 #pragma unroll
             for (int o = 16; o >= 2; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((threadIdx.x & 31) < 2) atomicAdd(&dws[(half * 8 + c) * 9 + t], s);
+            if ((threadIdx.x & 31) < 2) {
+                if (det_part) dws_w[threadIdx.x >> 5][(half * 8 + c) * 9 + t] = s;
+                else atomicAdd(&dws[(half * 8 + c) * 9 + t], s);
+            }
         }
     __syncthreads();
+    if (det_part) {
+        // the block's partial goes to det_part[block][144]; ordered_sum_kernel adds the blocks in index order into dw
+        for (int i = threadIdx.x; i < 144; i += blockDim.x) {
+            float v = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += dws_w[w][i];
+            det_part[(size_t)blockIdx.x * 144 + i] = v;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < 144; i += blockDim.x) atomicAdd(&dw[i], dws[i]);
 }
 
@@ -918,7 +977,8 @@ __global__ void depth_metrics_kernel(const float* __restrict__ output, const flo
 // ------------------------------------------------------------------------------------------------
 // MaskedL1Loss (criteria_new.py:44-54): mean |target - pred| over target > 0.  No boolean gather, no host sync:
 // acc[0] += sum, acc[1] += count (fp64), then a 1-thread finalize writes the fp32 scalar.
-__global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* acc) {
+__global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* acc,
+                              double* det_part /* deterministic mode: [block][2] partials instead of atomics */) {
     float s = 0.f, cnt = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float t = target[i];
@@ -936,7 +996,10 @@ __global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __res
         cnt = l < nw ? sc_[l] : 0.f;
         s = warp_sum(s);
         cnt = warp_sum(cnt);
-        if (l == 0) { atomicAdd(&acc[0], (double)s); atomicAdd(&acc[1], (double)cnt); }
+        if (l == 0) {
+            if (det_part) { det_part[2 * blockIdx.x] = (double)s; det_part[2 * blockIdx.x + 1] = (double)cnt; }
+            else { atomicAdd(&acc[0], (double)s); atomicAdd(&acc[1], (double)cnt); }
+        }
     }
 }
 __global__ void l1_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] / acc[1]); }   // 0/0 -> NaN like the reference
@@ -1011,7 +1074,8 @@ __global__ void sid_filter_kernel(const float* __restrict__ radar, const float* 
 // SmoothnessLoss (criteria_new.py:8-28): d^ = d / (mean_HW(d) + 1e-7);
 //   loss = mean(|dx d^| * exp(-mean_c |dx I|)) + mean(|dy d^| * exp(-mean_c |dy I|)).
 // The reference calls it with the full 4-channel network input as "image" (main.py:422), so C is a parameter.
-__global__ void image_sum_kernel(const float* __restrict__ d, int B, size_t hw, double* sums /*[B]*/) {
+__global__ void image_sum_kernel(const float* __restrict__ d, int B, size_t hw, double* sums /*[B]*/,
+                                 double* det_part /* deterministic mode: [blockIdx.x][B] partials */) {
     const int b = blockIdx.y;
     float s = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += d[b * hw + i];
@@ -1023,7 +1087,10 @@ __global__ void image_sum_kernel(const float* __restrict__ d, int B, size_t hw, 
     if (w == 0) {
         s = l < (int)(blockDim.x >> 5) ? ss[l] : 0.f;
         s = warp_sum(s);
-        if (l == 0) atomicAdd(&sums[b], (double)s);
+        if (l == 0) {
+            if (det_part) det_part[(size_t)blockIdx.x * B + b] = (double)s;
+            else atomicAdd(&sums[b], (double)s);
+        }
     }
 }
 
@@ -1034,28 +1101,47 @@ __device__ __forceinline__ float edge_weight(const float* __restrict__ img, int 
 }
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
+// Block-wide sum of one double per thread (blockDim.x a multiple of 32, <= 1024); the result is valid in thread 0.
+__device__ __forceinline__ double block_sum_f64(double v, double* red /*[32] shared*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();                                   // red may still be read from a previous call
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    v = (w == 0 && l < (int)(blockDim.x >> 5)) ? red[l] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+// One image per blockIdx.y, pixels grid-strided over blockIdx.x; every sum is reduced inside the block (fp64) and leaves
+// it as ONE atomic per block and address (the per-pixel / per-warp fp64 atomics of the first version put 3.4 M
+// same-address atomics into every backward at b=8).
 // mode 0: acc[0] += sum_x terms, acc[1] += sum_y terms (forward).
 // mode 1: gd[b] += sum_p G[p] * d[p]  where G = d loss / d d^ (first backward pass).
 // mode 2: grad[p] (+)= gout * (G[p] * r_b - r_b^2 * gd[b] / (H*W))   (second backward pass).
 __global__ void smoothness_kernel(const float* __restrict__ d, const float* __restrict__ img, int B, int C, int H, int W,
                                   const double* __restrict__ sums, int mode, double* acc, double* gd,
-                                  const float* __restrict__ gout, float* __restrict__ grad, int accumulate) {
+                                  const float* __restrict__ gout, float* __restrict__ grad, int accumulate,
+                                  double* det_part /* deterministic mode: mode 0 [block y*gx+x][2], mode 1 [blockIdx.x][B] */) {
+    __shared__ double red[32];
     const size_t hw = (size_t)H * W;
-    const size_t total = (size_t)B * hw;
+    const int b = blockIdx.y;
     const float inv_nx = 1.f / (float)((size_t)B * H * (W - 1));
     const float inv_ny = 1.f / (float)((size_t)B * (H - 1) * W);
-    float a0 = 0.f, a1 = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / hw);
-        const size_t p = i - (size_t)b * hw;
+    const float r = 1.f / ((float)(sums[b] / (double)hw) + 1e-7f);
+    const float* db = d + (size_t)b * hw;
+    const float* ib = img + (size_t)b * C * hw;
+    double a0 = 0.0, a1 = 0.0, gs = 0.0;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-        const float r = 1.f / ((float)(sums[b] / (double)hw) + 1e-7f);
-        const float* db = d + (size_t)b * hw;
-        const float* ib = img + (size_t)b * C * hw;
         const float dc = db[p] * r;
         if (mode == 0) {
-            if (x + 1 < W) a0 += fabsf(dc - db[p + 1] * r) * edge_weight(ib, C, hw, p, p + 1);
-            if (y + 1 < H) a1 += fabsf(dc - db[p + W] * r) * edge_weight(ib, C, hw, p, p + W);
+            if (x + 1 < W) a0 += (double)(fabsf(dc - db[p + 1] * r) * edge_weight(ib, C, hw, p, p + 1));
+            if (y + 1 < H) a1 += (double)(fabsf(dc - db[p + W] * r) * edge_weight(ib, C, hw, p, p + W));
         } else {
             float G = 0.f;
             if (x + 1 < W) G += edge_weight(ib, C, hw, p, p + 1) * sgn(dc - db[p + 1] * r) * inv_nx;
@@ -1063,17 +1149,30 @@ __global__ void smoothness_kernel(const float* __restrict__ d, const float* __re
             if (y + 1 < H) G += edge_weight(ib, C, hw, p, p + W) * sgn(dc - db[p + W] * r) * inv_ny;
             if (y > 0) G -= edge_weight(ib, C, hw, p - W, p) * sgn(db[p - W] * r - dc) * inv_ny;
             if (mode == 1) {
-                atomicAdd(&gd[b], (double)(G * db[p]));      // few hundred thousand pixels per image; fp64 REDG
+                gs += (double)(G * db[p]);
             } else {
+                const size_t i = (size_t)b * hw + p;
                 const float g = (*gout) * (G * r - r * r * (float)(gd[b] / (double)hw));
                 grad[i] = accumulate ? grad[i] + g : g;
             }
         }
     }
     if (mode == 0) {
-        a0 = warp_sum(a0);
-        a1 = warp_sum(a1);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], (double)a0 * inv_nx); atomicAdd(&acc[1], (double)a1 * inv_ny); }
+        a0 = block_sum_f64(a0, red);
+        a1 = block_sum_f64(a1, red);
+        if (threadIdx.x == 0) {
+            if (det_part) {
+                const size_t k = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+                det_part[2 * k] = a0 * (double)inv_nx;
+                det_part[2 * k + 1] = a1 * (double)inv_ny;
+            } else { atomicAdd(&acc[0], a0 * (double)inv_nx); atomicAdd(&acc[1], a1 * (double)inv_ny); }
+        }
+    } else if (mode == 1) {
+        gs = block_sum_f64(gs, red);
+        if (threadIdx.x == 0) {
+            if (det_part) det_part[(size_t)blockIdx.x * B + b] = gs;
+            else atomicAdd(&gd[b], gs);
+        }
     }
 }
 __global__ void smoothness_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] + acc[1]); }

@@ -25,8 +25,8 @@ struct TileSrc {
     const float* sc;        // shared-memory copies of the fused BN scale/shift (indexed by channel), or nullptr
     const float* sh;
     float slope;
-    FastDiv fd_slots, fd_wl;   // divisions by plane_slots / Wl (filled by prepare())
-    __device__ __forceinline__ void prepare() { fd_slots = FastDiv((uint32_t)plane_slots); fd_wl = FastDiv((uint32_t)Wl); }
+    FastDivS fd_slots, fd_wl;   // divisions by plane_slots / Wl (filled by prepare())
+    __device__ __forceinline__ void prepare() { fd_slots = FastDivS((uint32_t)plane_slots); fd_wl = FastDivS((uint32_t)Wl); }
 };
 
 // Raw 16-byte-granular loads of 8 consecutive channels (kept as raw registers so that a batch of independent loads
@@ -70,7 +70,7 @@ __device__ __forceinline__ void stage_tile(const TileSrc& t, uint8_t* dst, int c
     const int sh_s = t.S >> 1;                         // S is 1 or 2
     const T* src = reinterpret_cast<const T*>(t.ptr);
     const int row_items = t.Wl * nchunks;
-    const FastDiv fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
+    const FastDivS fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
     const bool raw_copy = (SPLIT == 1) && (sizeof(T) == 2) && (t.sc == nullptr);
     const int nrows = planes * t.plane_rows;
     const int my_rows = nrows > warp_idx ? (nrows - warp_idx + nwarps - 1) / nwarps : 0;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void stage_tile_async(const TileSrc& t, uint8_t* dst,
     const int sh_s = t.S >> 1;
     const T* src = reinterpret_cast<const T*>(t.ptr);
     const int row_items = t.Wl * nchunks;
-    const FastDiv fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
+    const FastDivS fd_ch((uint32_t)nchunks), fd_row((uint32_t)row_items), fd_pr((uint32_t)t.plane_rows);
     const int nrows = planes * t.plane_rows;
     const int my_rows = nrows > warp_idx ? (nrows - warp_idx + nwarps - 1) / nwarps : 0;
     const int my_items = my_rows * row_items;

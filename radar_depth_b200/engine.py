@@ -28,7 +28,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import _lib, convplan as cp
+from . import _lib, convplan as cp, determinism
 from ._lib import RD_BF16, RD_F32, View
 
 # copies of every statistics array (rd_bn_tail.slots spreads same-address fp64 atomics).  Measured on B200 (same box,
@@ -65,10 +65,12 @@ class BNGroup:
 
 
 class Launch:
-    __slots__ = ("fn", "args", "name")
+    """One pre-bound C-ABI call.  ``meta`` = algorithmic work of the launch for the roofline report of bench.py:
+    {"flops": 2*MAC without structural zeros, "bytes": tensors read + written once}."""
+    __slots__ = ("fn", "args", "name", "meta")
 
-    def __init__(self, name, fn, args):
-        self.name, self.fn, self.args = name, fn, args
+    def __init__(self, name, fn, args, meta=None):
+        self.name, self.fn, self.args, self.meta = name, fn, args, meta
 
 
 class LatefusionEngine:
@@ -92,6 +94,11 @@ class LatefusionEngine:
         self._keep = []                    # keeps ctypes structs referenced by launches alive
         self._buffers = []                 # keeps every device buffer referenced by raw pointer alive
         self.use_graphs = os.environ.get("RADAR_DEPTH_B200_GRAPHS", "1") != "0"
+        # fixed-order reductions (determinism.py): default on in the fp32 parity mode, off in the bf16 throughput mode
+        self.det = determinism.engine_default(act_dtype)
+        self.det_scratch = None
+        # tile shapes: measured table (tuned_tiles.json) or, with use_tuned = False, the analytic cost model only
+        self.use_tuned = os.environ.get("RD_USE_TUNED", "1") != "0"
         self._graphs = {}
 
     # ------------------------------------------------------------------ parameter arena
@@ -206,26 +213,40 @@ class LatefusionEngine:
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         H4, W4 = (H2 + 1) // 2, (W2 + 1) // 2
 
+        # deterministic mode: the conv kernels keep per-warp statistic arrays behind their rings (8 warps x [2][N] floats)
+        det_reserve = 8 * 2 * 256 * 4 if self.det else 0
+        det_bytes = [8 << 20]
+
         # -------- helpers that register a conv and emit launches
         def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True):
-            fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act)
+            fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned)
             f_off = self._wpk_total
             self._wpk_tables.append(fplan.pack_idx)
             self._wpk_total += fplan.wpk_elems
             dplan, d_off = None, None
             if need_dgrad:
-                dplan = cp.plan_fprop(g.transposed(), B, dst_hw, src_hw, act)
+                dplan = cp.plan_fprop(g.transposed(), B, dst_hw, src_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned)
                 d_off = self._wpk_total
                 self._wpk_tables.append(dplan.pack_idx)
                 self._wpk_total += dplan.wpk_elems
             wplan, w_off = None, None
             if need_wgrad:
-                wplan = cp.plan_wgrad(g, B, src_hw, dst_hw, act)
+                wplan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, use_tuned=self.use_tuned)
                 w_off = self._dw_total
                 self._scatter_p.append(wplan.scatter[0])
                 self._scatter_d.append(wplan.scatter[1] + w_off)
                 self._dw_total += wplan.dw_elems
-            rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off)
+                det_bytes.append(int(wplan.params.max_ctas) * wplan.dw_elems * 4)
+            nnz = int(sum(int((t.widx >= 0).sum()) for t in g.taps))
+            es = 2 if act == RD_BF16 else 4
+            sH, sW = src_hw
+            dH, dW = dst_hw
+            in_b, out_b = B * sH * sW * g.Cx * es, B * dH * dW * g.N * es
+            fpp, dpp = fplan.params, (dplan.params if dplan is not None else None)
+            work = dict(f=dict(flops=2.0 * B * fpp.Hb * fpp.Wb * nnz, bytes=in_b + out_b + 2 * nnz),
+                        d=dict(flops=2.0 * B * dpp.Hb * dpp.Wb * nnz, bytes=in_b + out_b + 2 * nnz) if dpp is not None else None,
+                        w=dict(flops=2.0 * B * fpp.Hb * fpp.Wb * nnz, bytes=in_b + out_b + 4 * nnz))
+            rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off, work=work)
             self.convs.append(rec)
             return rec
 
@@ -252,7 +273,12 @@ class LatefusionEngine:
                 p.tail = tail
             self._pending.append((p, "wpk", rec["f_off"] if which == "f" else rec["d_off"]))
             self._keep.append(p)
-            prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),)))
+            meta = dict(rec["work"][which])
+            extra = (1 if addend is not None else 0) + (1 if zsrc is not None else 0)       # tensors of the output's size
+            if extra:
+                es_ = 2 if act == RD_BF16 else 4
+                meta["bytes"] += extra * B * p.dstH * p.dstW * p.N * p.nblk * es_
+            prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),), meta))
             return p
 
         def emit_wgrad(prog, rec, gy: View, x: View, ld=None):
@@ -265,7 +291,7 @@ class LatefusionEngine:
                 p.ld_scale, p.ld_shift, p.ld_slope = None, None, 1.0
             self._pending.append((p, "dw", rec["w_off"]))
             self._keep.append(p)
-            prog.append(Launch(f"wgrad:{rec['name']}", lib.rd_conv_wgrad, (C.byref(p),)))
+            prog.append(Launch(f"wgrad:{rec['name']}", lib.rd_conv_wgrad, (C.byref(p),), dict(rec["work"]["w"])))
 
         def bn_buffers(name):
             m = self.module.get_submodule(name)
@@ -335,7 +361,9 @@ class LatefusionEngine:
         # ============================== buffers + forward program ==============================
         self.x_in = torch.zeros(B, self.in_channels, H, W, dtype=torch.float32, device=self.device)
         xs = self.act(B, H2, W2, 4 * Cs)
-        both(Launch("input_pack", lib.rd_input_pack, (_p(self.x_in), _p(xs), B, self.in_channels, H, W, Cs, act)))
+        es = 2 if act == RD_BF16 else 4                 # bytes per stored activation element (Launch.meta["bytes"])
+        both(Launch("input_pack", lib.rd_input_pack, (_p(self.x_in), _p(xs), B, self.in_channels, H, W, Cs, act),
+                    dict(bytes=self.x_in.numel() * 4 + xs.numel() * es)))
 
         # ---- stem
         stem = reg("stem", cp.gconv_stem(o["conv1.weight"], o["conv1_depth.weight"], cin_d), (H2, W2), (H2, W2),
@@ -348,7 +376,7 @@ class LatefusionEngine:
         amax = self.hold(torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device))
         both(Launch("maxpool", lib.rd_maxpool_fwd,
                     (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0, 0.2, _v(p_rgb), _v(p_d),
-                     _p(amax), H4, W4, act)))
+                     _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + (p_rgb.numel() + p_d.numel()) * es + amax.numel())))
 
         # ---- encoders
         enc_specs = [("", (64, 128, 256, 512), 64, p_rgb, 0), ("_depth", (16, 32, 64, 128), 16, p_d, 512)]
@@ -393,7 +421,8 @@ class LatefusionEngine:
                     idv = _v(zd) if zd is not None else (_v(x_cur) if isinstance(x_cur, torch.Tensor) else x_cur)
                     both(Launch("join:" + pfx, lib.rd_bn_add_act,
                                 (_v(z2), _p(b2.scale), _p(b2.shift), idv, _p(bd.scale) if bd else None,
-                                 _p(bd.shift) if bd else None, out_v, int(B * ho * wo), cw, 0.0, act)))
+                                 _p(bd.shift) if bd else None, out_v, int(B * ho * wo), cw, 0.0, act),
+                                dict(bytes=3 * B * ho * wo * cw * es)))
                     blks.append(dict(pfx=pfx, c1=c1, c2=c2, ds=ds, b1=b1, b2=b2, bd=bd, z1=z1, z2=z2, zd=zd, x_in=x_cur,
                                      out_v=out_v, hw_in=(h, w), hw=(ho, wo), cw=cw, ci=ci, n=n, last=last, cat_off=cat_off))
                     x_cur, h, w = out_t, ho, wo
@@ -434,7 +463,7 @@ class LatefusionEngine:
             emit_conv_fwd(c3, _v(zcat, 0), _v(zu2), (gcat.scale, gcat.shift, 0.0), bu2, n)
             both(Launch("join:" + pfx, lib.rd_bn_add_act,
                         (_v(zu2), _p(bu2.scale), _p(bu2.shift), _v(zcat, co), _p(gcat.scale, co), _p(gcat.shift, co),
-                         _v(out_t), int(B * ho * wo), co, 0.0, act)))
+                         _v(out_t), int(B * ho * wo), co, 0.0, act), dict(bytes=3 * B * ho * wo * co * es)))
             dec.append(dict(pfx=pfx, up=up, c3=c3, zcat=zcat, zu2=zu2, out=out_t, gcat=gcat, bu2=bu2, co=co, cin=cin,
                             x_in=d_in_t, x_ld=d_in_ld, hw_in=(h, w), hw=(ho, wo), n=n))
             d_in_t, d_in_ld = out_t, None
@@ -447,17 +476,21 @@ class LatefusionEngine:
         c3map = self.hold(torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device))
         self.pred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
         w3 = _p(self.flat, o["conv3.weight"])
-        both(Launch("head_conv", lib.rd_head_conv_fwd, (_v(d_in_t), w3, B, Hd, Wd, _p(c3map), act)))
-        both(Launch("bilinear", lib.rd_bilinear_fwd, (_p(c3map), B, Hd, Wd, _p(self.pred), OH, OW)))
+        both(Launch("head_conv", lib.rd_head_conv_fwd, (_v(d_in_t), w3, B, Hd, Wd, _p(c3map), act),
+                    dict(bytes=d_in_t.numel() * es + c3map.numel() * 4, flops=2.0 * B * Hd * Wd * 144)))
+        both(Launch("bilinear", lib.rd_bilinear_fwd, (_p(c3map), B, Hd, Wd, _p(self.pred), OH, OW),
+                    dict(bytes=(c3map.numel() + self.pred.numel()) * 4)))
 
         # ============================== backward program ==============================
         bw = self.bwd
         self.dpred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
         dc3 = self.hold(torch.zeros(B, Hd, Wd, dtype=torch.float32, device=self.device))
-        bw.append(Launch("bilinear_bwd", lib.rd_bilinear_bwd, (_p(self.dpred), B, Hd, Wd, _p(dc3), OH, OW)))
+        bw.append(Launch("bilinear_bwd", lib.rd_bilinear_bwd, (_p(self.dpred), B, Hd, Wd, _p(dc3), OH, OW),
+                         dict(bytes=(self.dpred.numel() + dc3.numel()) * 4)))
         d_out = self.act(B, Hd, Wd, dec[-1]["co"])
         bw.append(Launch("head_conv_bwd", lib.rd_head_conv_bwd,
-                         (_p(dc3), _v(dec[-1]["out"]), w3, B, Hd, Wd, _v(d_out), _p(self.gflat, o["conv3.weight"]), act)))
+                         (_p(dc3), _v(dec[-1]["out"]), w3, B, Hd, Wd, _v(d_out), _p(self.gflat, o["conv3.weight"]), act),
+                         dict(bytes=dc3.numel() * 4 + 2 * d_out.numel() * es, flops=4.0 * B * Hd * Wd * 144)))
         for li in range(3, -1, -1):
             L = dec[li]
             co, (ho, wo), n = L["co"], L["hw"], L["n"]
@@ -470,16 +503,20 @@ class LatefusionEngine:
                            bwd_job(gcat, 1, _p(bu2.bstats[0]), _p(bu2.bstats[2]), n)], 3, bu2.C)
             bw.append(Launch("join_bwd:" + L["pfx"], lib.rd_join_bwd,
                              (_v(d_out), _v(L["out"]), _v(L["zu2"]), _v(L["zcat"], co), _v(g_t), npix, co, 0.0,
-                              _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), C.byref(tj), act)))
+                              _p(bu2.bstats[0]), _p(bu2.bstats[1]), _p(bu2.bstats[2]), C.byref(tj), act),
+                             dict(bytes=5 * npix * co * es)))
             bw.append(Launch("bn_bwd_apply:bottom", lib.rd_bn_bwd_apply,
-                             (_v(g_t), _v(L["zcat"], co), _v(dzcat, co), _p(gcat.cA, co), _p(gcat.cB, co), _p(gcat.cC, co), npix, co, act)))
+                             (_v(g_t), _v(L["zcat"], co), _v(dzcat, co), _p(gcat.cA, co), _p(gcat.cB, co), _p(gcat.cC, co), npix, co, act),
+                             dict(bytes=3 * npix * co * es)))
             bw.append(Launch("bn_bwd_apply:u2", lib.rd_bn_bwd_apply,
-                             (_v(g_t), _v(L["zu2"]), _v(dzu2), _p(bu2.cA), _p(bu2.cB), _p(bu2.cC), npix, co, act)))
+                             (_v(g_t), _v(L["zu2"]), _v(dzu2), _p(bu2.cA), _p(bu2.cB), _p(bu2.cC), npix, co, act),
+                             dict(bytes=3 * npix * co * es)))
             emit_wgrad(bw, L["c3"], _v(dzu2), _v(L["zcat"], 0), ld=(gcat.scale, gcat.shift, 0.0))
             emit_conv(bw, L["c3"], "d", _v(dzu2), _v(dzcat, 0), epi=1, zsrc=_v(L["zcat"], 0), ep=(gcat.scale, gcat.shift, 0.0),
                       stats=gcat.bstats[:2], tail=new_tail([bwd_job(gcat, 0, _p(gcat.bstats[0]), _p(gcat.bstats[1]), n)], 3, gcat.C))
             bw.append(Launch("bn_bwd_apply:u1", lib.rd_bn_bwd_apply,
-                             (_v(dzcat, 0), _v(L["zcat"], 0), _v(dzcat, 0), _p(gcat.cA), _p(gcat.cB), _p(gcat.cC), npix, co, act)))
+                             (_v(dzcat, 0), _v(L["zcat"], 0), _v(dzcat, 0), _p(gcat.cA), _p(gcat.cB), _p(gcat.cC), npix, co, act),
+                             dict(bytes=3 * npix * co * es)))
             emit_wgrad(bw, L["up"], _v(dzcat), _v(L["x_in"]), ld=L["x_ld"])
             if li > 0:
                 hin, win = L["hw_in"]
@@ -493,13 +530,13 @@ class LatefusionEngine:
                 split_b = len(bw)          # g_c2 = d(loss)/d(bn2 output) here (slope 1: the activation mask is the identity)
         npf = int(B * h32 * w32)
         bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
-                         (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act)))
+                         (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act), dict(bytes=3 * npf * 256 * es)))
         emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
         g_f = self.act(B, h32, w32, 512)
         emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2],
                   tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)], 3, bf.C))
         bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
-                         (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act)))
+                         (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act), dict(bytes=3 * npf * 512 * es)))
         emit_wgrad(bw, cf, _v(g_f), _v(concat))
         emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
 
@@ -517,19 +554,23 @@ class LatefusionEngine:
                 tj = new_tail(jobs, 3, b2.C)
                 bw.append(Launch("join_bwd:" + Bk["pfx"], lib.rd_join_bwd,
                                  (d_out_v, Bk["out_v"], _v(Bk["z2"]), _v(Bk["zd"]) if bd else NULLV, _v(g_t), npix, cw, 0.0,
-                                  _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), C.byref(tj), act)))
+                                  _p(b2.bstats[0]), _p(b2.bstats[1]), _p(b2.bstats[2]), C.byref(tj), act),
+                                 dict(bytes=(5 if bd else 4) * npix * cw * es)))
                 bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
-                                 (_v(g_t), _v(Bk["z2"]), _v(dz2), _p(b2.cA), _p(b2.cB), _p(b2.cC), npix, cw, act)))
+                                 (_v(g_t), _v(Bk["z2"]), _v(dz2), _p(b2.cA), _p(b2.cB), _p(b2.cC), npix, cw, act),
+                                 dict(bytes=3 * npix * cw * es)))
                 dzd = None
                 if bd:
                     dzd = self.act(B, ho, wo, cw)
                     bw.append(Launch("bn_bwd_apply:ds", lib.rd_bn_bwd_apply,
-                                     (_v(g_t), _v(Bk["zd"]), _v(dzd), _p(bd.cA), _p(bd.cB), _p(bd.cC), npix, cw, act)))
+                                     (_v(g_t), _v(Bk["zd"]), _v(dzd), _p(bd.cA), _p(bd.cB), _p(bd.cC), npix, cw, act),
+                                     dict(bytes=3 * npix * cw * es)))
                 emit_wgrad(bw, Bk["c2"], _v(dz2), _v(Bk["z1"]), ld=(b1.scale, b1.shift, 0.0))
                 emit_conv(bw, Bk["c2"], "d", _v(dz2), _v(g1), epi=1, zsrc=_v(Bk["z1"]), ep=(b1.scale, b1.shift, 0.0),
                           stats=b1.bstats[:2], tail=new_tail([bwd_job(b1, 0, _p(b1.bstats[0]), _p(b1.bstats[1]), n)], 3, b1.C))
                 bw.append(Launch("bn_bwd_apply:bn1", lib.rd_bn_bwd_apply,
-                                 (_v(g1), _v(Bk["z1"]), _v(g1), _p(b1.cA), _p(b1.cB), _p(b1.cC), npix, cw, act)))
+                                 (_v(g1), _v(Bk["z1"]), _v(g1), _p(b1.cA), _p(b1.cB), _p(b1.cC), npix, cw, act),
+                                 dict(bytes=3 * npix * cw * es)))
                 x_in_v = _v(Bk["x_in"])
                 emit_wgrad(bw, Bk["c1"], _v(g1), x_in_v)
                 dx = self.act(B, hi, wi, Bk["ci"])
@@ -548,9 +589,11 @@ class LatefusionEngine:
                        bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)], 3, g_stem.C)
         bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
                          (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
-                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act)))
+                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
+                         dict(bytes=(p_rgb.numel() + p_d.numel()) * es + amax.numel() + 2 * z_stem.numel() * es)))
         bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
-                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act)))
+                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act),
+                         dict(bytes=3 * z_stem.numel() * es)))
         emit_wgrad(bw, stem, _v(gz_stem), _v(xs))
         self.dxs = None
         if self.in_channels > 4:
@@ -558,6 +601,7 @@ class LatefusionEngine:
             emit_conv(bw, stem, "d", _v(gz_stem), _v(self.dxs))
 
         # ============================== arenas that depend on the totals ==============================
+        self.det_scratch = torch.zeros(max(det_bytes), dtype=torch.uint8, device=self.device) if self.det else None
         self.wpk = torch.zeros(self._wpk_total, dtype=torch.bfloat16, device=self.device)
         self.dw = torch.zeros(max(self._dw_total, 1), dtype=torch.float32, device=self.device)
         self.pack_idx = torch.from_numpy(np.concatenate(self._wpk_tables)).to(self.device)
@@ -571,13 +615,15 @@ class LatefusionEngine:
                 p.dw = _p(self.dw, off)
         self._pending = []
         self._wpk_tables = []
-        pack = Launch("pack_weights", lib.rd_pack_weights, (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel()))
+        pack = Launch("pack_weights", lib.rd_pack_weights, (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel()),
+                      dict(bytes=self.pack_idx.numel() * (4 + 4 + 2)))
         self.fwd.insert(0, pack)
         self.fwd_eval.insert(0, pack)
         self.bn_eval_table = self.hold(torch.tensor(self._bn_eval_rows, dtype=torch.int64, device=self.device))
         self.fwd_eval.insert(1, Launch("bn_fin_eval_all", lib.rd_bn_finalize_eval_multi,
                                        (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
-        bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams)))
+        bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams),
+                         dict(bytes=self.nparams * (4 + 4 + 8))))
         self.stats_used = self.stats[:self._stats_used]
         # programs of the graph cut (pack_weights / bn_fin_eval_all were inserted at the heads above)
         exp = Launch("feature_export", lib.rd_feature_export,
@@ -611,10 +657,11 @@ class LatefusionEngine:
         # full-grid kernels with ~200 KB of shared memory per CTA do not overlap; the program stays single-stream.)
         st = torch.cuda.current_stream().cuda_stream
         lib = self.lib
-        for L in prog:
-            rc = L.fn(*L.args, st)
-            if rc != 0:
-                raise _lib.RdError(f"{L.name} failed ({rc}): {lib.rd_last_error().decode()}")
+        with determinism.mode(self.det_scratch if self.det else None):
+            for L in prog:
+                rc = L.fn(*L.args, st)
+                if rc != 0:
+                    raise _lib.RdError(f"{L.name} failed ({rc}): {lib.rd_last_error().decode()}")
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         B, Cc, H, W = x.shape

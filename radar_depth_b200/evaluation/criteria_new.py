@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, determinism
 from ..ops import ptr, stream_ptr
 
 
@@ -20,7 +20,8 @@ class _MaskedL1Fn(torch.autograd.Function):
         tgt_c = target.detach().float().contiguous()
         acc = torch.empty(2, dtype=torch.float64, device=pred.device)
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        _lib.call("rd_l1_fwd", ptr(pred_c), ptr(tgt_c), pred_c.numel(), ptr(acc), ptr(loss), stream_ptr())
+        with determinism.mode(determinism.loss_scratch(pred.device)):     # fixed-order loss sums: reproducible run to run
+            _lib.call("rd_l1_fwd", ptr(pred_c), ptr(tgt_c), pred_c.numel(), ptr(acc), ptr(loss), stream_ptr())
         ctx.save_for_backward(pred_c, tgt_c, acc)
         return loss
 
@@ -53,7 +54,8 @@ class _SmoothnessFn(torch.autograd.Function):
         B, _, H, W = pred_c.shape
         scratch = torch.empty(2 * B + 2, dtype=torch.float64, device=pred.device)
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        _lib.call("rd_smoothness_fwd", ptr(pred_c), ptr(img_c), B, img_c.shape[1], H, W, ptr(scratch), ptr(loss), stream_ptr())
+        with determinism.mode(determinism.loss_scratch(pred.device)):
+            _lib.call("rd_smoothness_fwd", ptr(pred_c), ptr(img_c), B, img_c.shape[1], H, W, ptr(scratch), ptr(loss), stream_ptr())
         ctx.save_for_backward(pred_c, img_c, scratch)
         return loss
 
@@ -63,8 +65,9 @@ class _SmoothnessFn(torch.autograd.Function):
         B, _, H, W = pred_c.shape
         gpred = torch.empty_like(pred_c)
         g = gout.detach().float().contiguous()
-        _lib.call("rd_smoothness_bwd", ptr(pred_c), ptr(img_c), B, img_c.shape[1], H, W, ptr(scratch), ptr(g), ptr(gpred), 0,
-                  stream_ptr())
+        with determinism.mode(determinism.loss_scratch(pred_c.device)):
+            _lib.call("rd_smoothness_bwd", ptr(pred_c), ptr(img_c), B, img_c.shape[1], H, W, ptr(scratch), ptr(g), ptr(gpred), 0,
+                      stream_ptr())
         return gpred, None
 
 

@@ -269,7 +269,8 @@ class ResNet_latefusion(nn.Module):
                 self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
             return _LatefusionFn.apply(x, self._anchor, self)
         eng = self._get_engine()
-        return eng.forward(x, self.training).clone()
+        self._fwd_serial += 1                        # the saved activations of an earlier grad-enabled forward are gone:
+        return eng.forward(x, self.training).clone()  # its backward() must raise, not differentiate the wrong pass
 
     # API surface of models.py:669-707 (PnP-Depth refinement); main.py never calls them.  front = encoder
     # + fusion 1x1s up to bn2's output, rear = decoder + head + bilinear.  rear(front(x)) == forward(x).  The usual PnP

@@ -226,6 +226,45 @@ def test_head_conv_and_bilinear_vs_autograd(name, act, td):
     torch.testing.assert_close(dw.view(1, 16, 3, 3), wr.grad, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("B,Hi,Wi,Ho,Wo", [(16, 176, 608, 352, 1216), (17, 225, 400, 450, 800)])
+def test_bilinear_at_benchmark_batch_matches_interpolate(B, Hi, Wi, Ho, Wo):
+    """Flat output indices of the headline configuration exceed the range in which a multiply-high division without a
+    correction step is exact (n * d >= 2^32: the last column of the last ~114 rows of image 15 landed one row down).
+    Forward and backward at B=16 352x1216 (and a W=800 output at B=17) against F.interpolate / autograd."""
+    torch.manual_seed(7)
+    c3 = torch.randn(B, 1, Hi, Wi, device="cuda").requires_grad_(True)
+    ref = F.interpolate(c3, size=(Ho, Wo), mode="bilinear", align_corners=True)
+    dpred = torch.randn(B, 1, Ho, Wo, device="cuda")
+    ref.backward(dpred)
+    pred = torch.full((B, 1, Ho, Wo), float("nan"), device="cuda")
+    call("rd_bilinear_fwd", ptr(c3.detach()), B, Hi, Wi, ptr(pred), Ho, Wo, stream_ptr())
+    torch.testing.assert_close(pred, ref.detach(), rtol=1e-4, atol=1e-4)
+    assert torch.equal(pred[-1, 0, -3:, -1], pred[-1, 0, -3:, -1]) and not torch.isnan(pred).any()
+    dc3 = torch.empty(B, Hi, Wi, device="cuda")
+    call("rd_bilinear_bwd", ptr(dpred), B, Hi, Wi, ptr(dc3), Ho, Wo, stream_ptr())
+    torch.testing.assert_close(dc3.view_as(c3), c3.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_loss_sums_are_deterministic():
+    """MaskedL1 / Smoothness reduce in a fixed order (determinism.py): identical bits on repeated calls at full size."""
+    from radar_depth_b200.evaluation.criteria_new import MaskedL1Loss, SmoothnessLoss
+    torch.manual_seed(11)
+    pred = torch.rand(8, 1, 352, 1216, device="cuda") * 60 + 0.5
+    tgt = torch.rand(8, 1, 352, 1216, device="cuda") * 80
+    tgt[torch.rand_like(tgt) < 0.95] = 0
+    img = torch.rand(8, 4, 352, 1216, device="cuda")
+    vals = []
+    for _ in range(3):
+        p = pred.clone().requires_grad_(True)
+        l1, sm = MaskedL1Loss()(p, tgt), SmoothnessLoss()(p, img)
+        (l1 + 0.1 * sm).backward()
+        vals.append((float(l1), float(sm), p.grad.clone()))
+    for v in vals[1:]:
+        assert v[0] == vals[0][0] and v[1] == vals[0][1] and torch.equal(v[2], vals[0][2])
+    d = (tgt - pred)[tgt > 0].abs().double().mean()
+    assert abs(vals[0][0] - float(d)) <= 1e-6 * float(d)
+
+
 def test_masked_l1_forward_backward_vs_reference_formula():
     torch.manual_seed(3)
     pred = (torch.rand(2, 1, 24, 40, device="cuda") * 30).requires_grad_(True)

@@ -86,3 +86,67 @@ def test_multistage_fixs_train_step_fp32_mode(h, w):
     # the stage-2 loss reaches stage 1 through the 5th input channel (depth1 is not detached, multistage_model.py:75)
     for k in ("stage1.conv3.weight", "stage1.decoder.layer4.upper_branch.conv2.weight"):
         assert _rel(named[k].grad, ref["grads"][k]) < 0.15, k
+
+
+def _build_multistage(hw, precision):
+    sd = O.synth_state_dict(O.multistage_entries())
+    m = ResNet_multistage(18, "upproj", hw, pretrained=False)
+    m.register_parameter("w_stage1", torch.nn.Parameter(torch.tensor(1.0)))
+    m.register_parameter("w_stage2", torch.nn.Parameter(torch.tensor(1.0)))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.stage1.precision = m.stage2.precision = precision
+    return m
+
+
+def test_multistage_fixs_full_size_matches_reference_golden_fp32_mode():
+    """352x1216 (the shape of BASELINE.json configs[3]), b=2, against the REAL reference's outputs
+    (tests/golden/multistage_fixs_train_b2_352x1216.npz, oracle/gen_golden.py::run_multistage)."""
+    g = np.load(os.path.join(GOLDEN, "multistage_fixs_train_b2_352x1216.npz"))
+    m = _build_multistage((352, 1216), "fp32")
+    inputs, target = O.synth_batch(2, 352, 1216)
+    x, t = inputs.cuda(), target.cuda()
+    out = m(x)
+    loss, d1, d2, s = _fixs_loss(out, x, t, m.w_stage1, m.w_stage2)
+    loss.backward()
+    assert _rel(out["stage1"][..., ::8, ::8], torch.from_numpy(g["stage1"])) < 1e-3
+    assert _rel(out["stage2"][..., ::8, ::8], torch.from_numpy(g["stage2"])) < 2e-3
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    assert abs(float(d1) - float(g["l1_stage1"])) <= 1e-4 * abs(float(g["l1_stage1"]))
+    assert abs(float(d2) - float(g["l1_stage2"])) <= 2e-4 * abs(float(g["l1_stage2"]))
+    assert abs(float(s) - float(g["smooth"])) <= 1e-3 * abs(float(g["smooth"]))
+    # the SID mask is a threshold on the stage-1 prediction: allow the few points that sit within its fp32 error
+    assert abs(float(out["mask"].sum()) - float(g["mask_sum"])) <= 2.0
+    got = dict(m.named_parameters())
+    bad = []
+    for i, k in enumerate(str(n) for n in g["grad_names"]):          # the reference's own gradient norms
+        rn = float(g["grad_norms"][i])
+        gn = float(got[k].grad.double().norm())
+        if abs(gn - rn) > 8e-2 * rn + 1e-6:
+            bad.append((k, gn, rn))
+    assert not bad, bad[:5]
+
+
+def test_multistage_b8_bf16_as_benchmarked_against_its_own_fp32_mode():
+    """The configuration bench.py --arch multistage times (b=8, 352x1216, bf16, tuned / cost-model tiles for B=8 and the
+    5-channel stage-2 stem) against the fp32 parity mode of the same path, at the level the reference's own bf16 autocast
+    run differs from its fp32 run (see tests/test_model_gpu.py)."""
+    inputs, target = O.synth_batch(8, 352, 1216)
+    x, t = inputs.cuda(), target.cuda()
+    res = {}
+    for precision in ("fp32", "bf16"):
+        m = _build_multistage((352, 1216), precision)
+        out = m(x)
+        loss, d1, d2, s = _fixs_loss(out, x, t, m.w_stage1, m.w_stage2)
+        loss.backward()
+        res[precision] = (out["stage1"].detach().clone(), out["stage2"].detach().clone(), float(loss),
+                          m.stage2.conv3.weight.grad.detach().clone(), float(m.w_stage1.grad))
+        del m, out
+        torch.cuda.empty_cache()
+    a, b = res["bf16"], res["fp32"]
+    r1, r2 = _rel(a[0], b[0]), _rel(a[1], b[1])
+    print(f"[multistage b8 bf16 vs fp32] stage1 {r1:.3e} stage2 {r2:.3e} loss {a[2]:.5f} vs {b[2]:.5f}")
+    assert r1 < 0.2 and r2 < 0.25
+    assert abs(a[2] - b[2]) <= 2e-2 * abs(b[2])
+    assert _rel(a[3], b[3]) < 0.1
+    assert abs(a[4] - b[4]) <= 3e-2 * abs(b[4])

@@ -159,3 +159,46 @@ def test_depth_metrics_match_reference_golden(golden_dir):
         ri = O.depth_metrics(out, tgt, lo, hi)
         np.testing.assert_allclose([ri[k] for k in _METRIC_FIELDS], g["multidist"][i], rtol=1e-6, atol=1e-9, equal_nan=True)
         assert (ri["count"] > 0) == bool(g["valid_label"][i])
+
+
+# ---- oracle/torch_modules.py: the module-level walk that the cuDNN speed bar (tests/tools/cudnn_bar.py) times
+def test_module_walk_matches_reference_golden(golden_dir):
+    from oracle import torch_modules as TM
+    from radar_depth_b200.model.models import ResNet_latefusion
+    g = _load(golden_dir, "latefusion_train_b2_64x96")
+    m = ResNet_latefusion(18, "upproj", (64, 96), 4, pretrained=False)
+    m.load_state_dict(O.synth_state_dict(O.latefusion_entries(4)), strict=True)
+    m.train()
+    inputs, target = O.synth_batch(2, 64, 96)
+    pred = TM.latefusion_forward(m, inputs)
+    loss = TM.masked_l1(pred, target)
+    loss.backward()
+    _close(pred.detach().numpy(), g["pred"], 1e-5)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    names = [str(n) for n in g["grad_names"]]
+    got = dict(m.named_parameters())
+    for i, k in enumerate(names):
+        rn = float(g["grad_norms"][i])
+        assert abs(float(got[k].grad.double().norm()) - rn) <= 1e-2 * max(rn, 1e-6) + 1e-7, k
+    assert int(m.bn1.num_batches_tracked) == int(g["nbt"])
+
+
+def test_module_walk_multistage_matches_reference_golden(golden_dir):
+    from oracle import torch_modules as TM
+    from radar_depth_b200.model.multistage_model import ResNet_multistage
+    g = _load(golden_dir, "multistage_fixs_train_b2_64x96")
+    m = ResNet_multistage(18, "upproj", (64, 96), pretrained=False)
+    m.register_parameter("w_stage1", torch.nn.Parameter(torch.tensor(1.0)))
+    m.register_parameter("w_stage2", torch.nn.Parameter(torch.tensor(1.0)))
+    m.load_state_dict(O.synth_state_dict(O.multistage_entries()), strict=True)
+    m.train()
+    inputs, target = O.synth_batch(2, 64, 96)
+    o = TM.multistage_forward(m, inputs)
+    d1, d2 = TM.masked_l1(o["stage1"], target), TM.masked_l1(o["stage2"], target)
+    s = TM.smoothness(o["stage1"], inputs)
+    loss = torch.exp(-m.w_stage1) * (d1 + 0.1 * s) + torch.exp(-m.w_stage2) * d2 + m.w_stage1 + m.w_stage2
+    _close(o["stage1"].detach().numpy(), g["stage1"], 1e-5)
+    _close(o["stage2"].detach().numpy(), g["stage2"], 1e-4)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert abs(float(s) - float(g["smooth"])) <= 1e-5 * abs(float(g["smooth"]))
+    assert float(o["mask"].sum()) == float(g["mask_sum"])

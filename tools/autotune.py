@@ -77,6 +77,9 @@ for rec in eng.convs:
         out = torch.empty(B, d_hw[0], d_hw[1], gg.N, device="cuda", dtype=torch.bfloat16)
         stats = torch.zeros(2, gg.N, dtype=torch.float64, device="cuda")
         best = None
+        # every candidate's OUTPUT is checked against the slow torch evaluation of the same GConv before its time counts
+        ref = cp.gconv_reference(gg, x.float(), w.bfloat16().float(), d_hw)
+        covered = {t.ph for t in gg.taps}
         for ov in [None] + fprop_candidates(gg, s_hw, d_hw):
             try:
                 plan = cp.plan_fprop(gg, B, s_hw, d_hw, act, tile_override=ov, use_tuned=False)
@@ -86,6 +89,15 @@ for rec in eng.convs:
             try:
                 ms = time_launch(lambda: ops.conv_fprop(plan, ops.view(x), wpk, ops.view(out), stats=(stats, gg.N)))
             except Exception as e:  # noqa
+                continue
+            chk = out.float()
+            for a in range(gg.OS):
+                for b in range(gg.OS):
+                    if (a, b) not in covered:
+                        chk[:, a::gg.OS, b::gg.OS] = 0
+            rel = float((chk - ref).norm() / (ref.norm() + 1e-20))
+            if not rel < 8e-3:
+                print(f"  REJECTED {key} {ov}: rel-L2 {rel:.3e}", flush=True)
                 continue
             geo = plan.info["geo"]
             if best is None or ms < best[0]:
@@ -102,6 +114,8 @@ for rec in eng.convs:
         x = torch.randn(B, src_hw[0], src_hw[1], g.Cx, device="cuda").bfloat16()
         dy = torch.randn(B, dst_hw[0], dst_hw[1], g.N, device="cuda").bfloat16()
         best, base = None, None
+        npar = int(max(int(t.widx.max()) for t in g.taps)) + 1
+        ref = cp.gconv_wgrad_reference(g, x.float(), dy.float(), npar)
         for nc in (None, 16, 32, 64, 128):
             for ks in (128, 192, 256, 384):
                 if nc is not None and (nc > g.Cx or g.Cx % nc):
@@ -114,6 +128,14 @@ for rec in eng.convs:
                 try:
                     ms = time_launch(lambda: ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw))
                 except Exception:
+                    continue
+                grad = torch.zeros(npar, dtype=torch.float32, device="cuda")
+                dw.zero_()
+                ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw)
+                grad[torch.from_numpy(plan.scatter[0]).cuda()] = dw[torch.from_numpy(plan.scatter[1]).cuda()]
+                rel = float((grad - ref).norm() / (ref.norm() + 1e-20))
+                if not rel < 8e-3:
+                    print(f"  REJECTED {key} nc={nc} ks={ks}: rel-L2 {rel:.3e}", flush=True)
                     continue
                 if nc is None and ks == 256:
                     base = ms
