@@ -235,7 +235,8 @@ class FpropPlan:
     info: dict = field(default_factory=dict)
 
 
-def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16, budget=SMEM_BUDGET):
+def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, parts, wstage_bytes, B_=16, budget=SMEM_BUDGET,
+                       sms=NUM_SMS):
     """Tile search.  The cost model was fitted to per-role cycle counters measured on B200 (tools/bench_fprop.py):
     UMMA ~max(48, N/2) cycles each, epilogue ~40 cycles per 16 columns per 32 rows (overlapped with the next tile
     when two accumulator sets fit in TMEM), ~2.5k cycles of pipeline hand-off per tile, and a strong preference for
@@ -269,7 +270,7 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
                 per_tile = max(stage * ncblk, epi) + 2500.0
             else:
                 per_tile = stage * ncblk + epi + 2500.0
-            ctas = max(1, NUM_SMS // nblk)
+            ctas = max(1, sms // nblk)
             rounds = -(-(ty * tx * B_) // ctas)
             cost = rounds * per_tile
             if best is None or cost < best[0]:
@@ -281,8 +282,11 @@ def _choose_fprop_tile(Hb, Wb, halo_y, halo_x, S, P, N, nblk, ntaps, ncblk, part
 
 
 def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, n_per_cta: Optional[int] = None,
-               tile_override: Optional[dict] = None, use_tuned: bool = True, smem_reserve: int = 0) -> FpropPlan:
-    """smem_reserve: bytes of dynamic shared memory the launcher needs behind the rings (deterministic statistics)."""
+               tile_override: Optional[dict] = None, use_tuned: bool = True, smem_reserve: int = 0,
+               sm_budget: int = NUM_SMS) -> FpropPlan:
+    """smem_reserve: bytes of dynamic shared memory the launcher needs behind the rings (deterministic statistics).
+    sm_budget: SMs (= persistent CTAs) this launch may occupy; less than the whole GPU when the engine runs the RGB and the
+    depth encoder side by side on disjoint sets of SMs (engine.LatefusionEngine, `lane`)."""
     assert g.Cx % 16 == 0 and g.N % 16 == 0, (g.Cx, g.N)
     budget = SMEM_BUDGET - smem_reserve
     parts = 2 if act_dtype == _lib.RD_F32 else 1
@@ -328,7 +332,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
         if FPROP_HEADER + 2 * geo["istage"] + 2 * wstage > budget:
             geo = None                                     # a measured tile that no longer fits (smem_reserve): re-plan
     if geo is None:
-        geo = _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B, budget)
+        geo = _choose_fprop_tile(Hb, Wb, halo_y, halo_x, g.S, P, N, nblk, ntaps, ncblk, parts, wstage, B, budget, sm_budget)
     istage = geo["istage"]
     # ring depths within the shared-memory budget
     avail = budget - FPROP_HEADER
@@ -379,7 +383,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     # convolutions) need just that one
     p.src_planes = 1 if (g.S == 2 and all(t.pl == (0, 0) for t in taps)) else 0
     ntiles = geo["tiles_y"] * geo["tiles_x"] * B
-    p.max_ctas = max(1, NUM_SMS // nblk)
+    p.max_ctas = max(1, sm_budget // nblk)
     # gather table [nblk][ncblk][tap][part][j][n][k]
     Wst = np.stack([t.widx for t in taps], axis=0)                       # [T, Cx, Ntot]
     Wst = Wst.reshape(ntaps, ncblk, 2, 8, nblk, N).transpose(4, 1, 0, 2, 5, 3)   # [nblk, ncblk, T, j, n, k]
@@ -441,7 +445,7 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
 
 
 def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
-               nc: Optional[int] = None, use_tuned: bool = True) -> WgradPlan:
+               nc: Optional[int] = None, use_tuned: bool = True, sm_budget: int = NUM_SMS) -> WgradPlan:
     """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient."""
     assert g.Cx % 16 == 0 and g.N % 8 == 0
     if use_tuned and nc is None:
@@ -516,7 +520,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     ctas_other = ncob * ncib * ntg
     # one resident wave: every extra wave pays the CTA prologue (TMEM alloc, ring zero-fill) and the final fp32
     # reduction of its accumulators again (measured: 1 wave is ~5 % faster than 2 on the layer1 shapes)
-    p.max_ctas = max(1, min(ntiles, NUM_SMS // ctas_other))
+    p.max_ctas = max(1, min(ntiles, sm_budget // ctas_other))
     # scatter table: dw[(t*N + n)*Cx + c]  ->  parameter widx_t[c, n]
     pi, di = [], []
     for ti, t in enumerate(taps):

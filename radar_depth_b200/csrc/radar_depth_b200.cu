@@ -28,6 +28,7 @@ int check_cuda(cudaError_t e, const char* what) {
 #define RD_REQUIRE(cond, msg) do { if (!(cond)) return fail(RD_EINVAL, std::string("rd: ") + (msg) + " [" #cond "]"); } while (0)
 
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in per CTA on sm_100
+constexpr int kMinSmemExclusive = 117 * 1024;   // > (228 KB - 2 x 1 KB reserved) / 2: at most one such CTA per SM
 
 constexpr int kMaxDevices = 64;
 int current_device() {
@@ -193,8 +194,12 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
         RD_REQUIRE((long long)gx * p->nblk * 2 * p->N * 4 <= g_scratch_bytes, "deterministic mode: scratch buffer too small");
         det_part = (float*)g_scratch;
     }
-    const long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes + det_smem;
+    long long smem = (long long)rd::kSmemHeader + (long long)p->IS * p->istage_bytes + (long long)p->WS * p->wstage_bytes + det_smem;
     RD_REQUIRE(smem <= kMaxSmem, "shared memory budget exceeded");
+    // Every CTA allocates all 512 TMEM columns: two convolution CTAs (of concurrent launches on different streams) must
+    // never share an SM, or the second would sit in tcgen05.alloc until the first retires.  More than half of the SM's
+    // shared memory per CTA guarantees that.
+    if (smem < kMinSmemExclusive) smem = kMinSmemExclusive;
     dim3 grid(gx, p->nblk, 1), block(rd::kFpropThreads, 1, 1);
     cudaStream_t st = (cudaStream_t)stream;
     // Raw bf16 stride-1 source tiles go through TMA: one box (8 ch, Wl, plane_rows, 2 chunks) per 16-channel stage.  TMA

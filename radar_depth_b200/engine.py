@@ -67,10 +67,13 @@ class BNGroup:
 class Launch:
     """One pre-bound C-ABI call.  ``meta`` = algorithmic work of the launch for the roofline report of bench.py:
     {"flops": 2*MAC without structural zeros, "bytes": tensors read + written once}."""
-    __slots__ = ("fn", "args", "name", "meta")
+    __slots__ = ("fn", "args", "name", "meta", "lane", "sync")
 
-    def __init__(self, name, fn, args, meta=None):
+    def __init__(self, name, fn, args, meta=None, lane=0, sync=None):
         self.name, self.fn, self.args, self.meta = name, fn, args, meta
+        # lane 1 = the depth encoder's chain, which runs on a side stream next to the RGB encoder's chain (lane 0);
+        # sync = "fork" on the first launch of the two chains, "join" on the first launch after them (see _run)
+        self.lane, self.sync = lane, sync
 
 
 class LatefusionEngine:
@@ -99,6 +102,9 @@ class LatefusionEngine:
         self.det_scratch = None
         # tile shapes: measured table (tuned_tiles.json) or, with use_tuned = False, the analytic cost model only
         self.use_tuned = os.environ.get("RD_USE_TUNED", "1") != "0"
+        # SMs given to the depth encoder while it runs next to the RGB encoder (0 = one stream, every launch owns the GPU)
+        self.depth_sms = int(os.environ.get("RD_DEPTH_SMS", "12"))
+        self._side = None
         self._graphs = {}
 
     # ------------------------------------------------------------------ parameter arena
@@ -218,20 +224,26 @@ class LatefusionEngine:
         det_bytes = [8 << 20]
 
         # -------- helpers that register a conv and emit launches
-        def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True):
-            fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned)
+        par = self.depth_sms > 0 and not self.det          # deterministic mode shares one scratch buffer: one stream
+        self._par = par
+        sm_of = {None: cp.NUM_SMS, 0: cp.NUM_SMS - self.depth_sms if par else cp.NUM_SMS, 1: self.depth_sms if par else cp.NUM_SMS}
+
+        def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True, lane=None):
+            sms = sm_of[lane]
+            fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned, sm_budget=sms)
             f_off = self._wpk_total
             self._wpk_tables.append(fplan.pack_idx)
             self._wpk_total += fplan.wpk_elems
             dplan, d_off = None, None
             if need_dgrad:
-                dplan = cp.plan_fprop(g.transposed(), B, dst_hw, src_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned)
+                dplan = cp.plan_fprop(g.transposed(), B, dst_hw, src_hw, act, smem_reserve=det_reserve, use_tuned=self.use_tuned,
+                                      sm_budget=sms)
                 d_off = self._wpk_total
                 self._wpk_tables.append(dplan.pack_idx)
                 self._wpk_total += dplan.wpk_elems
             wplan, w_off = None, None
             if need_wgrad:
-                wplan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, use_tuned=self.use_tuned)
+                wplan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, use_tuned=self.use_tuned, sm_budget=sms)
                 w_off = self._dw_total
                 self._scatter_p.append(wplan.scatter[0])
                 self._scatter_d.append(wplan.scatter[1] + w_off)
@@ -246,7 +258,8 @@ class LatefusionEngine:
             work = dict(f=dict(flops=2.0 * B * fpp.Hb * fpp.Wb * nnz, bytes=in_b + out_b + 2 * nnz),
                         d=dict(flops=2.0 * B * dpp.Hb * dpp.Wb * nnz, bytes=in_b + out_b + 2 * nnz) if dpp is not None else None,
                         w=dict(flops=2.0 * B * fpp.Hb * fpp.Wb * nnz, bytes=in_b + out_b + 4 * nnz))
-            rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off, work=work)
+            rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off, work=work,
+                       lane=(lane or 0) if par else 0)
             self.convs.append(rec)
             return rec
 
@@ -278,7 +291,7 @@ class LatefusionEngine:
             if extra:
                 es_ = 2 if act == RD_BF16 else 4
                 meta["bytes"] += extra * B * p.dstH * p.dstW * p.N * p.nblk * es_
-            prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),), meta))
+            prog.append(Launch(f"conv_{which}:{rec['name']}{tag}", lib.rd_conv_fprop, (C.byref(p),), meta, lane=rec["lane"]))
             return p
 
         def emit_wgrad(prog, rec, gy: View, x: View, ld=None):
@@ -291,7 +304,7 @@ class LatefusionEngine:
                 p.ld_scale, p.ld_shift, p.ld_slope = None, None, 1.0
             self._pending.append((p, "dw", rec["w_off"]))
             self._keep.append(p)
-            prog.append(Launch(f"wgrad:{rec['name']}", lib.rd_conv_wgrad, (C.byref(p),), dict(rec["work"]["w"])))
+            prog.append(Launch(f"wgrad:{rec['name']}", lib.rd_conv_wgrad, (C.byref(p),), dict(rec["work"]["w"]), lane=rec["lane"]))
 
         def bn_buffers(name):
             m = self.module.get_submodule(name)
@@ -386,21 +399,24 @@ class LatefusionEngine:
         concat = self.act(B, h32, w32, 640)
         d_concat = self.act(B, h32, w32, 640)
         blocks_all = []
-        for suffix, widths, cin0, x0, cat_off in enc_specs:
+        enc_seg = []                        # (lane, first index, end index) of each encoder chain in fwd / fwd_eval
+        for lane, (suffix, widths, cin0, x0, cat_off) in enumerate(enc_specs):
             x_cur, cin = x0, cin0
             h, w = H4, W4
             blks = []
+            seg0 = (len(self.fwd), len(self.fwd_eval))
             for li, cw in enumerate(widths, start=1):
                 for bi in range(2):
                     pfx = f"layer{li}{suffix}.{bi}"
                     stride = 2 if (li > 1 and bi == 0) else 1
                     ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
                     ci = cin if bi == 0 else cw
-                    c1 = reg(pfx + ".conv1", cp.gconv_standard(o[pfx + ".conv1.weight"], cw, ci, 3, stride, 1), (h, w), (ho, wo))
-                    c2 = reg(pfx + ".conv2", cp.gconv_standard(o[pfx + ".conv2.weight"], cw, cw, 3, 1, 1), (ho, wo), (ho, wo))
+                    c1 = reg(pfx + ".conv1", cp.gconv_standard(o[pfx + ".conv1.weight"], cw, ci, 3, stride, 1), (h, w), (ho, wo), lane=lane)
+                    c2 = reg(pfx + ".conv2", cp.gconv_standard(o[pfx + ".conv2.weight"], cw, cw, 3, 1, 1), (ho, wo), (ho, wo), lane=lane)
                     ds = None
                     if stride == 2:
-                        ds = reg(pfx + ".downsample.0", cp.gconv_standard(o[pfx + ".downsample.0.weight"], cw, ci, 1, 2, 0), (h, w), (ho, wo))
+                        ds = reg(pfx + ".downsample.0", cp.gconv_standard(o[pfx + ".downsample.0.weight"], cw, ci, 1, 2, 0), (h, w), (ho, wo),
+                                 lane=lane)
                     n = float(B * ho * wo)
                     z1, z2 = self.act(B, ho, wo, cw), self.act(B, ho, wo, cw)
                     b1 = BNGroup(self, [(pfx + ".bn1", 0, cw)])
@@ -428,6 +444,17 @@ class LatefusionEngine:
                     x_cur, h, w = out_t, ho, wo
                 cin = cw
             blocks_all.append(blks)
+            enc_seg.append((lane, seg0, (len(self.fwd), len(self.fwd_eval))))
+        # The two encoders are independent chains between the shared stem and the fusion convolution: with `par` the depth
+        # chain (3.5 % of the FLOPs, ~45 % of the encoder's launches, every one of them latency-bound) runs on a side stream
+        # on its own `depth_sms` SMs while the RGB chain keeps the rest -- the launches were planned with those SM budgets.
+        if par:
+            for lane, (f0, e0), (f1, e1) in enc_seg:
+                for prog, a, b in ((self.fwd, f0, f1), (self.fwd_eval, e0, e1)):
+                    for L in prog[a:b]:
+                        L.lane = lane
+            self.fwd[enc_seg[0][1][0]].sync = "fork"
+            self.fwd_eval[enc_seg[0][1][1]].sync = "fork"
 
         # ---- fusion 1x1s
         nf = float(B * h32 * w32)
@@ -435,6 +462,9 @@ class LatefusionEngine:
         zf = self.act(B, h32, w32, 512)
         bf = BNGroup(self, [("bn_fusion", 0, 512)])
         emit_conv_fwd(cf, _v(concat), _v(zf), None, bf, nf)
+        if par:
+            self.fwd[-1].sync = "join"
+            self.fwd_eval[-1].sync = "join"
         cc2 = reg("conv2", cp.gconv_standard(o["conv2.weight"], 256, 512, 1, 1, 0), (h32, w32), (h32, w32))
         zc2 = self.act(B, h32, w32, 256)
         bc2 = BNGroup(self, [("bn2", 0, 256)])
@@ -541,7 +571,8 @@ class LatefusionEngine:
         emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
 
         dpool = []
-        for blks in blocks_all:
+        for lane, blks in enumerate(blocks_all):
+            bseg0 = len(bw)
             d_out_v = _v(d_concat, blks[-1]["cat_off"])
             for Bk in reversed(blks):
                 cw, (ho, wo), (hi, wi), n = Bk["cw"], Bk["hw"], Bk["hw_in"], Bk["n"]
@@ -583,6 +614,11 @@ class LatefusionEngine:
                     emit_conv(bw, Bk["c1"], "d", _v(g1), _v(dx), addend=_v(g_t))
                 d_out_v = _v(dx)
             dpool.append(d_out_v)
+            if par:
+                for L in bw[bseg0:]:
+                    L.lane = lane
+                if lane == 0:
+                    bw[bseg0].sync = "fork"
 
         gz_stem = self.act(B, H2, W2, 80)
         tj = new_tail([bwd_job(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem),
@@ -590,7 +626,8 @@ class LatefusionEngine:
         bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
                          (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
                           0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
-                         dict(bytes=(p_rgb.numel() + p_d.numel()) * es + amax.numel() + 2 * z_stem.numel() * es)))
+                         dict(bytes=(p_rgb.numel() + p_d.numel()) * es + amax.numel() + 2 * z_stem.numel() * es),
+                         sync="join" if par else None))
         bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
                          (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act),
                          dict(bytes=3 * z_stem.numel() * es)))
@@ -655,13 +692,32 @@ class LatefusionEngine:
     def _run(self, prog: List[Launch]):
         # (Weight-gradient launches on a second, event-forked stream were tried: 10.91 vs 10.92 ms/step on B200 --
         # full-grid kernels with ~200 KB of shared memory per CTA do not overlap; the program stays single-stream.)
-        st = torch.cuda.current_stream().cuda_stream
+        main = torch.cuda.current_stream()
+        st = main.cuda_stream
         lib = self.lib
+        side = None
         with determinism.mode(self.det_scratch if self.det else None):
             for L in prog:
-                rc = L.fn(*L.args, st)
+                if L.sync == "fork":
+                    # the side stream joins here (under CUDA-graph capture this event edge forks the graph)
+                    if self._side is None or self._side.device != main.device:
+                        self._side = torch.cuda.Stream(device=main.device)
+                    side = self._side
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                elif L.sync == "join" and side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    main.wait_event(ev)
+                    side = None
+                rc = L.fn(*L.args, side.cuda_stream if (L.lane == 1 and side is not None) else st)
                 if rc != 0:
                     raise _lib.RdError(f"{L.name} failed ({rc}): {lib.rd_last_error().decode()}")
+            if side is not None:               # a program slice that ends inside the parallel region (never the case today)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         B, Cc, H, W = x.shape
