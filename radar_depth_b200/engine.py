@@ -102,8 +102,13 @@ class LatefusionEngine:
         self.det_scratch = None
         # tile shapes: measured table (tuned_tiles.json) or, with use_tuned = False, the analytic cost model only
         self.use_tuned = os.environ.get("RD_USE_TUNED", "1") != "0"
-        # SMs given to the depth encoder while it runs next to the RGB encoder (0 = one stream, every launch owns the GPU)
-        self.depth_sms = int(os.environ.get("RD_DEPTH_SMS", "12"))
+        # SMs given to the depth encoder while it runs next to the RGB encoder (0 = one stream, every launch owns the GPU).
+        # Measured on B200 (bench.py, same box): at b=16 the depth chain is throughput-bound on the SMs it gets (a 16-channel
+        # 3x3 conv takes 23 us on 148 SMs, 59 us on 24, 104 us on 12) and the split never pays: 9.24 ms/step with one
+        # stream, 9.39 (24 SMs), 9.44 (16), 10.9 (12), 13.4 (8).  At b=8 (multistage) every launch is half as long, fill and
+        # drain dominate the small layers, and the split wins: 13.81 -> 12.39 ms/step with 24 SMs.  Default: by batch size.
+        env = os.environ.get("RD_DEPTH_SMS")
+        self.depth_sms = int(env) if env not in (None, "") else None       # None = choose in configure()
         self._side = None
         self._graphs = {}
 
@@ -224,9 +229,10 @@ class LatefusionEngine:
         det_bytes = [8 << 20]
 
         # -------- helpers that register a conv and emit launches
-        par = self.depth_sms > 0 and not self.det          # deterministic mode shares one scratch buffer: one stream
-        self._par = par
-        sm_of = {None: cp.NUM_SMS, 0: cp.NUM_SMS - self.depth_sms if par else cp.NUM_SMS, 1: self.depth_sms if par else cp.NUM_SMS}
+        depth_sms = self.depth_sms if self.depth_sms is not None else (24 if B <= 8 else 0)
+        par = depth_sms > 0 and not self.det               # deterministic mode shares one scratch buffer: one stream
+        self._par, self._depth_sms = par, depth_sms
+        sm_of = {None: cp.NUM_SMS, 0: cp.NUM_SMS - depth_sms if par else cp.NUM_SMS, 1: depth_sms if par else cp.NUM_SMS}
 
         def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True, lane=None):
             sms = sm_of[lane]
