@@ -107,6 +107,28 @@ def run_latefusion(ref, b, h, w, seed_sd=7, in_channels=4, training=True, full_p
     return out
 
 
+def run_variant(ref, b, h, w, arch, in_channels, decoder, seed_sd=7):
+    """The other constructors on the same kernels: ResNet (models.py:233-303) and the UpConv / DeConv
+    decoders (models.py:135-176) under either encoder."""
+    from oracle import torch_oracle as O
+    ent = O.resnet_entries(in_channels, decoder) if arch == "resnet" else O.latefusion_entries(in_channels, decoder)
+    sd = O.synth_state_dict(ent, seed=seed_sd)
+    cls = ref.models.ResNet if arch == "resnet" else ref.models.ResNet_latefusion
+    model = cls(18, decoder, (h, w), in_channels, pretrained=False)
+    assert list(model.state_dict().keys()) == list(sd.keys()), "state_dict key order mismatch"
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    inputs, target = O.synth_batch(b, h, w, seed=1234)
+    pred = model(inputs[:, :in_channels])
+    loss = ref.criteria.MaskedL1Loss()(pred, target)
+    loss.backward()
+    names, norms, heads = _grad_summary(model.named_parameters())
+    bufs = {k: v for k, v in model.state_dict().items() if k.endswith("running_mean") or k.endswith("running_var")}
+    return {"loss": np.float64(loss.item()), "b": b, "h": h, "w": w, "pred": _subsample(pred, 2), "grad_names": names,
+            "grad_norms": norms, "grad_heads": heads, "buf_names": np.array(list(bufs.keys())),
+            "buf_values": np.concatenate([v.reshape(-1).numpy() for v in bufs.values()])}
+
+
 def run_pnp(ref, b, h, w, training, seed_sd=7):
     """pnp_forward_front / pnp_forward_rear of the real reference (models.py:669-707) and the gradient of the masked L1
     loss with respect to the bottleneck feature (what a PnP-Depth refinement loop differentiates)."""
@@ -208,6 +230,11 @@ def main():
         "latefusion_train_b2_352x1216": lambda: run_latefusion(ref, 2, 352, 1216, full_pred=False),
         "multistage_fixs_train_b2_64x96": lambda: run_multistage(ref, 2, 64, 96),
         "multistage_fixs_train_b2_352x1216": lambda: run_multistage(ref, 2, 352, 1216, full_pred=False),   # configs[3] shape
+        "resnet_rgbd_upproj_b2_64x96": lambda: run_variant(ref, 2, 64, 96, "resnet", 4, "upproj"),
+        "resnet_rgb_deconv3_b2_64x96": lambda: run_variant(ref, 2, 64, 96, "resnet", 3, "deconv3"),
+        "resnet_rgbd_upconv_b2_64x96": lambda: run_variant(ref, 2, 64, 96, "resnet", 4, "upconv"),
+        "latefusion_deconv2_b2_64x96": lambda: run_variant(ref, 2, 64, 96, "latefusion", 4, "deconv2"),
+        "latefusion_upconv_b2_64x96": lambda: run_variant(ref, 2, 64, 96, "latefusion", 4, "upconv"),
         "pnp_train_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, True),
         "pnp_eval_b2_64x96": lambda: run_pnp(ref, 2, 64, 96, False),
         "losses_filter": lambda: run_losses(ref),

@@ -47,8 +47,44 @@ def _encoder_entries(out, suffix: str, widths, first_in: int) -> None:
         cin = c
 
 
-def latefusion_entries(in_channels: int = 4) -> "OrderedDict[str, Tuple[tuple, str]]":
-    """Names/shapes of ResNet_latefusion(18,'upproj') in registration order (models.py:539-588)."""
+def _decoder_entries(e, decoder: str, c: int = 256) -> None:
+    """choose_decoder (models.py:219-230): UpProj (models.py:178-216), UpConv (models.py:158-176), DeConv (models.py:135-156)."""
+    for li in range(1, 5):
+        p = f"decoder.layer{li}"
+        if decoder == "upproj":
+            e[p + ".upper_branch.conv1.weight"] = ((c // 2, c, 5, 5), "conv")
+            _bn_entries(e, p + ".upper_branch.batchnorm1", c // 2)
+            e[p + ".upper_branch.conv2.weight"] = ((c // 2, c // 2, 3, 3), "conv")
+            _bn_entries(e, p + ".upper_branch.batchnorm2", c // 2)
+            e[p + ".bottom_branch.conv.weight"] = ((c // 2, c, 5, 5), "conv")
+            _bn_entries(e, p + ".bottom_branch.batchnorm", c // 2)
+        elif decoder == "upconv":
+            e[p + ".conv.weight"] = ((c // 2, c, 5, 5), "conv")
+            _bn_entries(e, p + ".batchnorm", c // 2)
+        elif decoder in ("deconv2", "deconv3"):
+            k = int(decoder[6])
+            e[p + f".deconv{k}.weight"] = ((c, c // 2, k, k), "convT")      # nn.ConvTranspose2d: [in, out, k, k]
+            _bn_entries(e, p + ".batchnorm", c // 2)
+        else:
+            raise ValueError(decoder)
+        c //= 2
+
+
+def resnet_entries(in_channels: int = 3, decoder: str = "upproj") -> "OrderedDict[str, Tuple[tuple, str]]":
+    """Names/shapes of ResNet(18, decoder) in registration order (models.py:233-281): one encoder over all input channels."""
+    e: "OrderedDict[str, Tuple[tuple, str]]" = OrderedDict()
+    e["conv1.weight"] = ((64, in_channels, 7, 7), "conv")
+    _bn_entries(e, "bn1", 64)
+    _encoder_entries(e, "", (64, 128, 256, 512), 64)
+    e["conv2.weight"] = ((256, 512, 1, 1), "conv")
+    _bn_entries(e, "bn2", 256)
+    _decoder_entries(e, decoder)
+    e["conv3.weight"] = ((1, 16, 3, 3), "conv")
+    return e
+
+
+def latefusion_entries(in_channels: int = 4, decoder: str = "upproj") -> "OrderedDict[str, Tuple[tuple, str]]":
+    """Names/shapes of ResNet_latefusion(18, decoder) in registration order (models.py:539-588)."""
     assert in_channels > 3                                   # models.py:535
     e: "OrderedDict[str, Tuple[tuple, str]]" = OrderedDict()
     e["conv1.weight"] = ((64, 3, 7, 7), "conv")
@@ -61,16 +97,7 @@ def latefusion_entries(in_channels: int = 4) -> "OrderedDict[str, Tuple[tuple, s
     _bn_entries(e, "bn_fusion", 512)
     e["conv2.weight"] = ((256, 512, 1, 1), "conv")
     _bn_entries(e, "bn2", 256)
-    c = 256
-    for li in range(1, 5):                                   # UpProj, models.py:178-216
-        p = f"decoder.layer{li}"
-        e[p + ".upper_branch.conv1.weight"] = ((c // 2, c, 5, 5), "conv")
-        _bn_entries(e, p + ".upper_branch.batchnorm1", c // 2)
-        e[p + ".upper_branch.conv2.weight"] = ((c // 2, c // 2, 3, 3), "conv")
-        _bn_entries(e, p + ".upper_branch.batchnorm2", c // 2)
-        e[p + ".bottom_branch.conv.weight"] = ((c // 2, c, 5, 5), "conv")
-        _bn_entries(e, p + ".bottom_branch.batchnorm", c // 2)
-        c //= 2
+    _decoder_entries(e, decoder)
     e["conv3.weight"] = ((1, 16, 3, 3), "conv")
     return e
 
@@ -99,6 +126,8 @@ def synth_state_dict(entries, seed: int = 7, dtype=torch.float32) -> "OrderedDic
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif kind == "convT":
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[0] * shape[2] * shape[3] / 4.0))
         elif kind == "bn_weight":
             t = torch.rand(shape, generator=g) * 0.8 + 0.6
         elif kind == "bn_bias":
@@ -195,6 +224,44 @@ def _upproj(x, sd, p, training, nb):
     return F.relu(x1 + x2)
 
 
+def _upconv(x, sd, p, training, nb):
+    """UpConv.upconv_module (models.py:160-169): unpool -> 5x5 conv -> BN -> ReLU."""
+    return F.relu(_bn(_conv(unpool(x), sd, p + ".conv", 1, 2), sd, p + ".batchnorm", training, nb))
+
+
+def _deconv(x, sd, p, k, training, nb):
+    """DeConv.convt (models.py:140-151): ConvTranspose2d(k, stride 2, padding (k-1)//2, output_padding k%2) -> BN -> ReLU."""
+    y = F.conv_transpose2d(x, sd[p + f".deconv{k}.weight"], None, 2, (k - 1) // 2, k % 2)
+    return F.relu(_bn(y, sd, p + ".batchnorm", training, nb))
+
+
+def _decoder(f, sd, decoder, training, nb):
+    for li in range(1, 5):
+        p = f"decoder.layer{li}"
+        if decoder == "upproj":
+            f = _upproj(f, sd, p, training, nb)
+        elif decoder == "upconv":
+            f = _upconv(f, sd, p, training, nb)
+        elif decoder in ("deconv2", "deconv3"):
+            f = _deconv(f, sd, p, int(decoder[6]), training, nb)
+        else:
+            raise ValueError(decoder)
+    return f
+
+
+def resnet_forward(sd, x: Tensor, output_size, training: bool = True, new_buffers: Optional[dict] = None,
+                   decoder: str = "upproj") -> Tensor:
+    """ResNet.forward (models.py:283-303): single encoder over all input channels, conv2/bn2, decoder, head, bilinear."""
+    nb = new_buffers
+    y = F.relu(_bn(_conv(x, sd, "conv1", 2, 3), sd, "bn1", training, nb))
+    y = F.max_pool2d(y, 3, 2, 1)
+    y = _encoder(y, sd, "", training, nb)
+    y = _bn(_conv(y, sd, "conv2"), sd, "bn2", training, nb)
+    y = _decoder(y, sd, decoder, training, nb)
+    y = _conv(y, sd, "conv3", 1, 1)
+    return F.interpolate(y, size=tuple(output_size), mode="bilinear", align_corners=True)
+
+
 def _scoped(sd, new_buffers, prefix):
     if prefix:
         return _PrefixView(sd, prefix), (_PrefixSink(new_buffers, prefix) if new_buffers is not None else None)
@@ -219,21 +286,20 @@ def latefusion_front(sd, x: Tensor, training: bool = True, new_buffers: Optional
 
 
 def latefusion_rear(sd, f: Tensor, output_size, training: bool = True, new_buffers: Optional[dict] = None,
-                    prefix: str = "") -> Tensor:
+                    prefix: str = "", decoder: str = "upproj") -> Tensor:
     """ResNet_latefusion.pnp_forward_rear (models.py:702-707): decoder, 3x3 head, bilinear resize."""
     sd, nb = _scoped(sd, new_buffers, prefix)
-    for li in range(1, 5):
-        f = _upproj(f, sd, f"decoder.layer{li}", training, nb)
+    f = _decoder(f, sd, decoder, training, nb)
     f = _conv(f, sd, "conv3", 1, 1)
     return F.interpolate(f, size=tuple(output_size), mode="bilinear", align_corners=True)
 
 
 def latefusion_forward(sd, x: Tensor, output_size, training: bool = True,
-                       new_buffers: Optional[dict] = None, prefix: str = "") -> Tensor:
+                       new_buffers: Optional[dict] = None, prefix: str = "", decoder: str = "upproj") -> Tensor:
     """ResNet_latefusion.forward (models.py:627-664) / ResNet_latefusion2.forward
     (multistage_model.py:232-276) = rear(front(x))."""
     f = latefusion_front(sd, x, training, new_buffers, prefix)
-    return latefusion_rear(sd, f, output_size, training, new_buffers, prefix)
+    return latefusion_rear(sd, f, output_size, training, new_buffers, prefix, decoder)
 
 
 class _PrefixView:
@@ -317,14 +383,18 @@ def _leaf_params(sd, dtype):
 
 
 def train_step(sd, inputs: Tensor, target: Tensor, arch: str = "latefusion", training: bool = True,
-               dtype=torch.float32):
+               dtype=torch.float32, decoder: str = "upproj"):
     """fwd + loss + bwd.  Returns dict(pred|preds, loss, grads, new_buffers)."""
     params, work = _leaf_params(sd, dtype)
     inputs, target = inputs.to(dtype), target.to(dtype)
     nb: dict = {}
     size = inputs.shape[-2:]
     if arch == "latefusion":
-        pred = latefusion_forward(work, inputs, size, training, nb)
+        pred = latefusion_forward(work, inputs, size, training, nb, decoder=decoder)
+        loss = masked_l1(pred, target)
+        outs = {"pred": pred.detach()}
+    elif arch == "resnet":
+        pred = resnet_forward(work, inputs, size, training, nb, decoder=decoder)
         loss = masked_l1(pred, target)
         outs = {"pred": pred.detach()}
     elif arch == "multistage_fixs":

@@ -134,6 +134,50 @@ def gconv_stem(off_rgb: int, off_depth: int, cin_depth: int, name: str = "stem")
     return GConv(Cx=Cx, N=N, S=1, OS=1, taps=taps, name=name)
 
 
+def gconv_stem_single(off: int, C: int, name: str = "stem") -> GConv:
+    """ResNet.conv1 (C->64, 7x7 s2 p3, models.py:238-245) as a stride-1 4x4-tap convolution over the space-to-depth
+    input of rd_input_pack (channel = parity*4 + c, C <= 4)."""
+    assert 1 <= C <= 4
+    Cs, N = 4, 64
+    taps = []
+    for sy in range(-2, 2):
+        for sx in range(-2, 2):
+            widx = np.full((4 * Cs, N), -1, dtype=np.int32)
+            for py in range(2):
+                for px in range(2):
+                    ky, kx = 2 * sy + py + 3, 2 * sx + px + 3
+                    if not (0 <= ky < 7 and 0 <= kx < 7):
+                        continue
+                    n = np.arange(N)
+                    for c in range(C):
+                        widx[(py * 2 + px) * Cs + c, :] = off + ((n * C + c) * 7 + ky) * 7 + kx
+            taps.append(GTap(ph=(0, 0), pl=(0, 0), s=(sy, sx), widx=widx))
+    return GConv(Cx=4 * Cs, N=N, S=1, OS=1, taps=taps, name=name)
+
+
+def gconv_upconv(off: int, Cin: int, Cout: int, name: str = "") -> GConv:
+    """UpConv's 5x5 p2 conv on Unpool(x) (models.py:160-169) as 4 sub-pixel convolutions on the un-stuffed x."""
+    taps = []
+    for a in range(2):
+        for b in range(2):
+            for ky in range(5):
+                if (a + ky - 2) % 2:
+                    continue
+                for kx in range(5):
+                    if (b + kx - 2) % 2:
+                        continue
+                    taps.append(GTap(ph=(a, b), pl=(0, 0), s=((a + ky - 2) // 2, (b + kx - 2) // 2),
+                                     widx=_oihw_index(off, Cout, Cin, 5, 5, ky, kx)))
+    return GConv(Cx=Cin, N=Cout, S=1, OS=2, taps=taps, name=name)
+
+
+def gconv_deconv(off: int, Cin: int, Cout: int, k: int, name: str = "") -> GConv:
+    """nn.ConvTranspose2d(Cin, Cout, k, stride 2, padding (k-1)//2, output_padding k%2, bias=False) (DeConv, models.py:140-151):
+    the transpose of the stride-2 convolution whose OIHW weight is the ConvTranspose2d weight [Cin, Cout, k, k]."""
+    assert k in (2, 3)
+    return gconv_standard(off, Cin, Cout, k, 2, (k - 1) // 2, name=name).transposed()
+
+
 def gconv_upproj(off_upper: int, off_bottom: int, Cin: int, Cout: int, name: str = "") -> GConv:
     """Both 5x5 p2 convs of an UpProjModule (upper_branch.conv1 | bottom_branch.conv, models.py:191,198) applied to
     Unpool(x) (models.py:13-27), as 4 sub-pixel convolutions on the un-stuffed x with N = 2*Cout."""

@@ -202,3 +202,21 @@ def test_module_walk_multistage_matches_reference_golden(golden_dir):
     assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     assert abs(float(s) - float(g["smooth"])) <= 1e-5 * abs(float(g["smooth"]))
     assert float(o["mask"].sum()) == float(g["mask_sum"])
+
+
+# ---- the other constructors on the same kernels: ResNet and the UpConv / DeConv decoders
+VARIANTS = [("resnet_rgbd_upproj_b2_64x96", "resnet", 4, "upproj"), ("resnet_rgb_deconv3_b2_64x96", "resnet", 3, "deconv3"),
+            ("resnet_rgbd_upconv_b2_64x96", "resnet", 4, "upconv"), ("latefusion_deconv2_b2_64x96", "latefusion", 4, "deconv2"),
+            ("latefusion_upconv_b2_64x96", "latefusion", 4, "upconv")]
+
+
+@pytest.mark.parametrize("name,arch,cin,decoder", VARIANTS)
+def test_variant_constructors_match_reference_golden(golden_dir, name, arch, cin, decoder):
+    g = _load(golden_dir, name)
+    ent = O.resnet_entries(cin, decoder) if arch == "resnet" else O.latefusion_entries(cin, decoder)
+    sd = O.synth_state_dict(ent)
+    inputs, target = O.synth_batch(2, 64, 96)
+    res = O.train_step(sd, inputs[:, :cin], target, arch, decoder=decoder)
+    _close(res["pred"][..., ::2, ::2].numpy(), g["pred"], 2e-5)
+    assert abs(float(res["loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    _check_grads(g, res)

@@ -104,6 +104,9 @@ for rec in eng.convs:
                 best = (ms, dict(Ht=geo["Ht"], Wt=geo["Wt"]), ov is None)
             if ov is None:
                 base = ms
+        if best is None:
+            print(f"{rec['name']:42s} {key:70s} NO VALID CANDIDATE", flush=True)
+            continue
         table[key] = best[1]
         print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
     if rec["wplan"] is not None:
@@ -141,8 +144,11 @@ for rec in eng.convs:
                     base = ms
                 if best is None or ms < best[0]:
                     best = (ms, dict(nc=plan.info["Nc"], ks=ks))
+        if best is None:
+            print(f"{rec['name']:42s} {key:70s} NO VALID CANDIDATE", flush=True)
+            continue
         table[key] = best[1]
-        print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
+        print(f"{rec['name']:42s} {key:70s} model {(base or best[0]) * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/tuned_tiles.json", "w") as f:
     json.dump(table, f, indent=0, sort_keys=True)
