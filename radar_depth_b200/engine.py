@@ -77,7 +77,12 @@ class Launch:
 
 
 class LatefusionEngine:
-    def __init__(self, module: torch.nn.Module, in_channels: int, output_size, act_dtype: int = RD_BF16):
+    def __init__(self, module: torch.nn.Module, in_channels: int, output_size, act_dtype: int = RD_BF16,
+                 arch: str = "latefusion", decoder: str = "upproj"):
+        """arch: "latefusion" (RGB + depth encoders, models.py:519-664) or "resnet" (one encoder over all input channels,
+        models.py:233-303); decoder: "upproj" | "upconv" | "deconv2" | "deconv3" (models.py:135-230)."""
+        assert arch in ("latefusion", "resnet") and decoder in ("upproj", "upconv", "deconv2", "deconv3"), (arch, decoder)
+        self.arch, self.decoder = arch, decoder
         self.module = module
         self.in_channels = in_channels
         self.output_size = tuple(int(v) for v in output_size)
@@ -230,7 +235,8 @@ class LatefusionEngine:
 
         # -------- helpers that register a conv and emit launches
         depth_sms = self.depth_sms if self.depth_sms is not None else (24 if B <= 8 else 0)
-        par = depth_sms > 0 and not self.det               # deterministic mode shares one scratch buffer: one stream
+        single = self.arch == "resnet"                    # one encoder over all input channels (models.py:233-303)
+        par = depth_sms > 0 and not self.det and not single    # deterministic mode shares one scratch buffer: one stream
         self._par, self._depth_sms = par, depth_sms
         sm_of = {None: cp.NUM_SMS, 0: cp.NUM_SMS - depth_sms if par else cp.NUM_SMS, 1: depth_sms if par else cp.NUM_SMS}
 
@@ -388,25 +394,36 @@ class LatefusionEngine:
                     dict(bytes=self.x_in.numel() * 4 + xs.numel() * es)))
 
         # ---- stem
-        stem = reg("stem", cp.gconv_stem(o["conv1.weight"], o["conv1_depth.weight"], cin_d), (H2, W2), (H2, W2),
-                   need_dgrad=(self.in_channels > 4))
-        z_stem = self.act(B, H2, W2, 80)
-        g_stem = BNGroup(self, [("bn1", 0, 64), ("bn1_depth", 64, 16)])
+        if single:
+            stem = reg("stem", cp.gconv_stem_single(o["conv1.weight"], self.in_channels), (H2, W2), (H2, W2), need_dgrad=False)
+            Cst = 64
+            g_stem = BNGroup(self, [("bn1", 0, 64)])
+        else:
+            stem = reg("stem", cp.gconv_stem(o["conv1.weight"], o["conv1_depth.weight"], cin_d), (H2, W2), (H2, W2),
+                       need_dgrad=(self.in_channels > 4))
+            Cst = 80
+            g_stem = BNGroup(self, [("bn1", 0, 64), ("bn1_depth", 64, 16)])
+        z_stem = self.act(B, H2, W2, Cst)
         n_stem = float(B * H2 * W2)
         emit_conv_fwd(stem, _v(xs), _v(z_stem), None, g_stem, n_stem)
-        p_rgb, p_d = self.act(B, H4, W4, 64), self.act(B, H4, W4, 16)
-        amax = self.hold(torch.zeros(B, H4, W4, 80, dtype=torch.uint8, device=self.device))
+        p_rgb = self.act(B, H4, W4, 64)
+        p_d = None if single else self.act(B, H4, W4, 16)
+        amax = self.hold(torch.zeros(B, H4, W4, Cst, dtype=torch.uint8, device=self.device))
+        pool_out = (p_rgb.numel() + (0 if single else p_d.numel())) * es
         both(Launch("maxpool", lib.rd_maxpool_fwd,
-                    (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0, 0.2, _v(p_rgb), _v(p_d),
-                     _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + (p_rgb.numel() + p_d.numel()) * es + amax.numel())))
+                    (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, Cst, 64, 0.0, 0.2, _v(p_rgb),
+                     NULLV if single else _v(p_d), _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + pool_out + amax.numel())))
 
         # ---- encoders
-        enc_specs = [("", (64, 128, 256, 512), 64, p_rgb, 0), ("_depth", (16, 32, 64, 128), 16, p_d, 512)]
+        enc_specs = [("", (64, 128, 256, 512), 64, p_rgb, 0)]
+        if not single:
+            enc_specs.append(("_depth", (16, 32, 64, 128), 16, p_d, 512))
+        Ccat = 512 if single else 640
         h32, w32 = H4, W4
         for _ in range(3):
             h32, w32 = (h32 + 1) // 2, (w32 + 1) // 2
-        concat = self.act(B, h32, w32, 640)
-        d_concat = self.act(B, h32, w32, 640)
+        concat = self.act(B, h32, w32, Ccat)
+        d_concat = self.act(B, h32, w32, Ccat)
         blocks_all = []
         enc_seg = []                        # (lane, first index, end index) of each encoder chain in fwd / fwd_eval
         for lane, (suffix, widths, cin0, x0, cat_off) in enumerate(enc_specs):
@@ -467,17 +484,21 @@ class LatefusionEngine:
 
         # ---- fusion 1x1s
         nf = float(B * h32 * w32)
-        cf = reg("conv_fusion", cp.gconv_standard(o["conv_fusion.weight"], 512, 640, 1, 1, 0), (h32, w32), (h32, w32))
-        zf = self.act(B, h32, w32, 512)
-        bf = BNGroup(self, [("bn_fusion", 0, 512)])
-        emit_conv_fwd(cf, _v(concat), _v(zf), None, bf, nf)
-        if par:
-            self.fwd[-1].sync = "join"
-            self.fwd_eval[-1].sync = "join"
         cc2 = reg("conv2", cp.gconv_standard(o["conv2.weight"], 256, 512, 1, 1, 0), (h32, w32), (h32, w32))
         zc2 = self.act(B, h32, w32, 256)
         bc2 = BNGroup(self, [("bn2", 0, 256)])
-        emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2, nf)
+        if single:
+            cf = zf = bf = None
+            emit_conv_fwd(cc2, _v(concat), _v(zc2), None, bc2, nf)           # layer4's output feeds conv2 directly
+        else:
+            cf = reg("conv_fusion", cp.gconv_standard(o["conv_fusion.weight"], 512, 640, 1, 1, 0), (h32, w32), (h32, w32))
+            zf = self.act(B, h32, w32, 512)
+            bf = BNGroup(self, [("bn_fusion", 0, 512)])
+            emit_conv_fwd(cf, _v(concat), _v(zf), None, bf, nf)
+            if par:
+                self.fwd[-1].sync = "join"
+                self.fwd_eval[-1].sync = "join"
+            emit_conv_fwd(cc2, _v(zf), _v(zc2), (bf.scale, bf.shift, 1.0), bc2, nf)
         # graph cut of pnp_forward_front / pnp_forward_rear (models.py:669-707): everything up to here is the "front"
         split_f, split_fe = len(self.fwd), len(self.fwd_eval)
         self.bneck = self.hold(torch.zeros(B, 256, h32, w32, dtype=torch.float32, device=self.device))
@@ -487,17 +508,34 @@ class LatefusionEngine:
         dec = []
         d_in_t, d_in_ld = zc2, (bc2.scale, bc2.shift, 1.0)
         h, w, cin = h32, w32, 256
+        upproj = self.decoder == "upproj"
         for li in range(1, 5):
             pfx = f"decoder.layer{li}"
             co = cin // 2
             ho, wo = 2 * h, 2 * w
+            n = float(B * ho * wo)
+            if not upproj:
+                # UpConv (unpool -> 5x5 conv -> BN -> ReLU, models.py:160-169) / DeConv (ConvTranspose2d -> BN -> ReLU,
+                # models.py:140-151): ONE 4-phase program per stage; its BN + ReLU are applied by the next stage on load
+                if self.decoder == "upconv":
+                    up = reg(pfx + ".conv", cp.gconv_upconv(o[pfx + ".conv.weight"], cin, co), (h, w), (ho, wo))
+                else:
+                    k = int(self.decoder[6])
+                    up = reg(pfx + f".deconv{k}", cp.gconv_deconv(o[pfx + f".deconv{k}.weight"], cin, co, k), (h, w), (ho, wo))
+                z = self.act(B, ho, wo, co)
+                grp = BNGroup(self, [(pfx + ".batchnorm", 0, co)])
+                emit_conv_fwd(up, _v(d_in_t), _v(z), d_in_ld, grp, n)
+                dec.append(dict(pfx=pfx, up=up, z=z, grp=grp, co=co, cin=cin, x_in=d_in_t, x_ld=d_in_ld, hw_in=(h, w),
+                                hw=(ho, wo), n=n))
+                d_in_t, d_in_ld = z, (grp.scale, grp.shift, 0.0)
+                h, w, cin = ho, wo, co
+                continue
             up = reg(pfx + ".up5x5", cp.gconv_upproj(o[pfx + ".upper_branch.conv1.weight"], o[pfx + ".bottom_branch.conv.weight"], cin, co),
                      (h, w), (ho, wo))
             c3 = reg(pfx + ".upper_branch.conv2", cp.gconv_standard(o[pfx + ".upper_branch.conv2.weight"], co, co, 3, 1, 1), (ho, wo), (ho, wo))
             zcat, zu2, out_t = self.act(B, ho, wo, 2 * co), self.act(B, ho, wo, co), self.act(B, ho, wo, co)
             gcat = BNGroup(self, [(pfx + ".upper_branch.batchnorm1", 0, co), (pfx + ".bottom_branch.batchnorm", co, co)])
             bu2 = BNGroup(self, [(pfx + ".upper_branch.batchnorm2", 0, co)])
-            n = float(B * ho * wo)
             emit_conv_fwd(up, _v(d_in_t), _v(zcat), d_in_ld, gcat, n)
             emit_conv_fwd(c3, _v(zcat, 0), _v(zu2), (gcat.scale, gcat.shift, 0.0), bu2, n)
             both(Launch("join:" + pfx, lib.rd_bn_add_act,
@@ -509,6 +547,14 @@ class LatefusionEngine:
             h, w, cin = ho, wo, co
         Hd, Wd = h, w
         self.Hd, self.Wd = Hd, Wd
+        if not upproj:
+            # the 3x3 head reads a materialised activation: relu(bn(z)) of the last stage
+            L = dec[-1]
+            L["out"] = self.act(B, Hd, Wd, L["co"])
+            both(Launch("bn_act:" + L["pfx"], lib.rd_bn_add_act,
+                        (_v(L["z"]), _p(L["grp"].scale), _p(L["grp"].shift), NULLV, None, None, _v(L["out"]), int(B * Hd * Wd),
+                         L["co"], 0.0, act), dict(bytes=2 * B * Hd * Wd * L["co"] * es)))
+            d_in_t = L["out"]
 
         # ---- head
         OH, OW = self.output_size
@@ -530,10 +576,38 @@ class LatefusionEngine:
         bw.append(Launch("head_conv_bwd", lib.rd_head_conv_bwd,
                          (_p(dc3), _v(dec[-1]["out"]), w3, B, Hd, Wd, _v(d_out), _p(self.gflat, o["conv3.weight"]), act),
                          dict(bytes=dc3.numel() * 4 + 2 * d_out.numel() * es, flops=4.0 * B * Hd * Wd * 144)))
+        g_cur = None                       # non-UpProj decoders: g = d(loss)/d(bn output) masked by the ReLU, per stage
         for li in range(3, -1, -1):
             L = dec[li]
             co, (ho, wo), n = L["co"], L["hw"], L["n"]
             npix = int(B * ho * wo)
+            if not upproj:
+                grp = L["grp"]
+                if li == 3:
+                    g_cur = self.act(B, ho, wo, co)
+                    tj = new_tail([bwd_job(grp, 0, _p(grp.bstats[0]), _p(grp.bstats[1]), n)], 3, grp.C)
+                    bw.append(Launch("join_bwd:" + L["pfx"], lib.rd_join_bwd,
+                                     (_v(d_out), _v(L["out"]), _v(L["z"]), NULLV, _v(g_cur), npix, co, 0.0,
+                                      _p(grp.bstats[0]), _p(grp.bstats[1]), _p(grp.bstats[2]), C.byref(tj), act),
+                                     dict(bytes=4 * npix * co * es)))
+                bw.append(Launch("bn_bwd_apply:dec", lib.rd_bn_bwd_apply,
+                                 (_v(g_cur), _v(L["z"]), _v(g_cur), _p(grp.cA), _p(grp.cB), _p(grp.cC), npix, co, act),
+                                 dict(bytes=3 * npix * co * es)))
+                emit_wgrad(bw, L["up"], _v(g_cur), _v(L["x_in"]), ld=L["x_ld"])
+                hin, win = L["hw_in"]
+                if li > 0:
+                    P = dec[li - 1]
+                    g_prev = self.act(B, hin, win, L["cin"])
+                    emit_conv(bw, L["up"], "d", _v(g_cur), _v(g_prev), epi=1, zsrc=_v(P["z"]), ep=(P["grp"].scale, P["grp"].shift, 0.0),
+                              stats=P["grp"].bstats[:2],
+                              tail=new_tail([bwd_job(P["grp"], 0, _p(P["grp"].bstats[0]), _p(P["grp"].bstats[1]), P["n"])], 3, P["grp"].C))
+                    g_cur = g_prev
+                else:
+                    g_c2 = self.act(B, h32, w32, 256)
+                    emit_conv(bw, L["up"], "d", _v(g_cur), _v(g_c2), epi=1, zsrc=_v(zc2), ep=(bc2.scale, bc2.shift, 1.0),
+                              stats=bc2.bstats[:2], tail=new_tail([bwd_job(bc2, 0, _p(bc2.bstats[0]), _p(bc2.bstats[1]), nf)], 3, bc2.C))
+                    split_b = len(bw)
+                continue
             gcat, bu2 = L["gcat"], L["bu2"]
             g_t = self.act(B, ho, wo, co)
             dzcat = self.act(B, ho, wo, 2 * co)
@@ -570,14 +644,18 @@ class LatefusionEngine:
         npf = int(B * h32 * w32)
         bw.append(Launch("bn_bwd_apply:bn2", lib.rd_bn_bwd_apply,
                          (_v(g_c2), _v(zc2), _v(g_c2), _p(bc2.cA), _p(bc2.cB), _p(bc2.cC), npf, 256, act), dict(bytes=3 * npf * 256 * es)))
-        emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
-        g_f = self.act(B, h32, w32, 512)
-        emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2],
-                  tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)], 3, bf.C))
-        bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
-                         (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act), dict(bytes=3 * npf * 512 * es)))
-        emit_wgrad(bw, cf, _v(g_f), _v(concat))
-        emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
+        if single:
+            emit_wgrad(bw, cc2, _v(g_c2), _v(concat))
+            emit_conv(bw, cc2, "d", _v(g_c2), _v(d_concat))
+        else:
+            emit_wgrad(bw, cc2, _v(g_c2), _v(zf), ld=(bf.scale, bf.shift, 1.0))
+            g_f = self.act(B, h32, w32, 512)
+            emit_conv(bw, cc2, "d", _v(g_c2), _v(g_f), epi=1, zsrc=_v(zf), ep=(bf.scale, bf.shift, 1.0), stats=bf.bstats[:2],
+                      tail=new_tail([bwd_job(bf, 0, _p(bf.bstats[0]), _p(bf.bstats[1]), nf)], 3, bf.C))
+            bw.append(Launch("bn_bwd_apply:bn_fusion", lib.rd_bn_bwd_apply,
+                             (_v(g_f), _v(zf), _v(g_f), _p(bf.cA), _p(bf.cB), _p(bf.cC), npf, 512, act), dict(bytes=3 * npf * 512 * es)))
+            emit_wgrad(bw, cf, _v(g_f), _v(concat))
+            emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
 
         dpool = []
         for lane, blks in enumerate(blocks_all):
@@ -629,16 +707,18 @@ class LatefusionEngine:
                 if lane == 0:
                     bw[bseg0].sync = "fork"
 
-        gz_stem = self.act(B, H2, W2, 80)
-        tj = new_tail([bwd_job(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem),
-                       bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem)], 3, g_stem.C)
+        gz_stem = self.act(B, H2, W2, Cst)
+        stem_jobs = [bwd_job(g_stem, 0, _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), n_stem)]
+        if not single:
+            stem_jobs.append(bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem))
+        tj = new_tail(stem_jobs, 3, g_stem.C)
         bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
-                         (dpool[0], dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, 80, 64, 0.0,
-                          0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
-                         dict(bytes=(p_rgb.numel() + p_d.numel()) * es + amax.numel() + 2 * z_stem.numel() * es),
+                         (dpool[0], NULLV if single else dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2,
+                          Cst, 64, 0.0, 0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
+                         dict(bytes=pool_out + amax.numel() + 2 * z_stem.numel() * es),
                          sync="join" if par else None))
         bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
-                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), 80, act),
+                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), Cst, act),
                          dict(bytes=3 * z_stem.numel() * es)))
         emit_wgrad(bw, stem, _v(gz_stem), _v(xs))
         self.dxs = None

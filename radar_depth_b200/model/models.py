@@ -7,8 +7,9 @@ constructor signature, attribute names, parameter/buffer names, shapes and regis
 ``forward`` is never called.  ``forward(x)`` runs the whole encoder-decoder through the sm_100a kernels
 (radar_depth_b200.engine) as one autograd node; ``loss.backward()`` fills ``.grad`` of every parameter.
 
-Only what north_star names is built: layers=18 and decoder='upproj'.  Other values that the reference accepts
-raise NotImplementedError (after the reference's own argument errors, which are mirrored).
+north_star names layers=18 and decoder='upproj'; the other decoders (`upconv`, `deconv2`, `deconv3`, models.py:135-176) and
+the single-encoder `ResNet` (models.py:233-303) run on the same convolution programs.  Deeper encoders
+(34/50/101/152) raise NotImplementedError after the reference's own argument errors, which are mirrored.
 There is no CPU / PyTorch fallback: without a CUDA device and the built library, forward raises.
 """
 from __future__ import annotations
@@ -140,12 +141,59 @@ class UpProj(Decoder):
         self.layer4 = self.UpProjModule(in_channels // 8)
 
 
+class DeConv(Decoder):
+    """Four ConvTranspose2d(k, stride 2) + BN + ReLU stages (models.py:135-156): on the engine each is the 4-phase
+    data-gradient form of a stride-2 convolution (convplan.gconv_deconv)."""
+
+    def __init__(self, in_channels, kernel_size):
+        assert kernel_size >= 2, "kernel_size out of range: {}".format(kernel_size)
+        super().__init__()
+        if kernel_size not in (2, 3):
+            raise NotImplementedError("only deconv2 / deconv3 (Decoder.names) are built")
+
+        def convt(c):
+            padding = (kernel_size - 1) // 2
+            output_padding = kernel_size % 2
+            assert -2 - 2 * padding + kernel_size + output_padding == 0, "deconv parameters incorrect"
+            return nn.Sequential(collections.OrderedDict([
+                ("deconv{}".format(kernel_size), nn.ConvTranspose2d(c, c // 2, kernel_size, 2, padding, output_padding, bias=False)),
+                ("batchnorm", nn.BatchNorm2d(c // 2)),
+                ("relu", nn.ReLU(inplace=True)),
+            ]))
+        self.layer1 = convt(in_channels)
+        self.layer2 = convt(in_channels // 2)
+        self.layer3 = convt(in_channels // 4)
+        self.layer4 = convt(in_channels // 8)
+
+
+class UpConv(Decoder):
+    """Four unpool -> 5x5 conv -> BN -> ReLU stages (models.py:158-176): 4-phase sub-pixel programs (convplan.gconv_upconv)."""
+
+    def upconv_module(self, in_channels):
+        return nn.Sequential(collections.OrderedDict([
+            ("unpool", Unpool(in_channels)),
+            ("conv", nn.Conv2d(in_channels, in_channels // 2, 5, 1, 2, bias=False)),
+            ("batchnorm", nn.BatchNorm2d(in_channels // 2)),
+            ("relu", nn.ReLU()),
+        ]))
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.layer1 = self.upconv_module(in_channels)
+        self.layer2 = self.upconv_module(in_channels // 2)
+        self.layer3 = self.upconv_module(in_channels // 4)
+        self.layer4 = self.upconv_module(in_channels // 8)
+
+
 def choose_decoder(decoder, in_channels):
-    """models.py:219-230.  Only 'upproj' has a B200 implementation (north_star: --decoder upproj)."""
-    if decoder == "upproj":
+    """models.py:219-230."""
+    if decoder[:6] == "deconv":
+        assert len(decoder) == 7
+        return DeConv(in_channels, int(decoder[6]))
+    elif decoder == "upproj":
         return UpProj(in_channels)
-    if decoder == "upconv" or (decoder[:6] == "deconv" and len(decoder) == 7):
-        raise NotImplementedError(f"decoder '{decoder}' is outside the B200 hot path (only 'upproj' is built)")
+    elif decoder == "upconv":
+        return UpConv(in_channels)
     assert False, "invalid option for decoder: {}".format(decoder)
 
 
@@ -205,6 +253,8 @@ class ResNet_latefusion(nn.Module):
         assert in_channels > 3                       # models.py:535
         self.output_size = output_size
         self.in_channels = in_channels
+        self.decoder_name = decoder
+        self._arch = "latefusion"
         # ---- RGB branch (models.py:539-551)
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
@@ -256,11 +306,13 @@ class ResNet_latefusion(nn.Module):
     def _get_engine(self) -> LatefusionEngine:
         want = _lib.RD_F32 if self.precision in ("fp32", "f32", "parity") else _lib.RD_BF16
         if self._engine is None or self._engine.act_dtype != want or tuple(self._engine.output_size) != tuple(self.output_size):
-            self._engine = LatefusionEngine(self, self.in_channels, self.output_size, want)
+            self._engine = LatefusionEngine(self, self.in_channels, self.output_size, want, arch=self._arch,
+                                            decoder=self.decoder_name)
         return self._engine
 
     def forward(self, x):
-        assert x.shape[1] >= 4                       # multistage_model.py:233
+        if self._arch == "latefusion":
+            assert x.shape[1] >= 4                   # multistage_model.py:233
         if not x.is_cuda:
             raise _lib.RdError("radar_depth_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
         x = x.float().contiguous()
@@ -294,3 +346,52 @@ class ResNet_latefusion(nn.Module):
     def _image_hw(self):
         eng = self._engine
         return (eng.cfg["H"], eng.cfg["W"]) if eng is not None and eng.cfg is not None else None
+
+
+class ResNet(ResNet_latefusion):
+    """models.py:233-303: ONE ResNet-18 encoder over all input channels (rgb: 3, rgbd: 4, d: 1), conv2/bn2, decoder, head.
+    Same engine and kernels as the late-fusion network (no depth branch, no fusion convolution); parameter / buffer names
+    and registration order are the reference's.  The parent class only lends forward() and the engine plumbing."""
+
+    def __init__(self, layers, decoder, output_size, in_channels=3, pretrained=True):
+        if layers not in _LAYER_CHOICES:
+            raise RuntimeError("Only 18, 34, 50, 101, and 152 layer model are defined for ResNet. Got {}".format(layers))
+        nn.Module.__init__(self)
+        if layers != 18:
+            raise NotImplementedError("only the ResNet-18 encoder is built for B200")
+        if not 1 <= in_channels <= 4:
+            raise NotImplementedError("the B200 stem packs at most 4 input channels")
+        self.output_size = output_size
+        self.in_channels = in_channels
+        self.decoder_name = decoder
+        self._arch = "resnet"
+        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        if in_channels != 3:                          # models.py:243-247 (3 channels: torchvision's own conv1 / bn1)
+            weights_init(self.conv1)
+            weights_init(self.bn1)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = _make_layer(64, 64, 2, 1)
+        self.layer2 = _make_layer(64, 128, 2, 2)
+        self.layer3 = _make_layer(128, 256, 2, 2)
+        self.layer4 = _make_layer(256, 512, 2, 2)
+        self.conv2 = nn.Conv2d(512, 256, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(256)
+        self.decoder = choose_decoder(decoder, 256)
+        self.conv3 = nn.Conv2d(16, 1, 3, 1, 1, bias=False)
+        self.bilinear = nn.Upsample(size=self.output_size, mode="bilinear", align_corners=True)
+        self.conv2.apply(weights_init)
+        self.bn2.apply(weights_init)
+        self.decoder.apply(weights_init)
+        self.conv3.apply(weights_init)
+        if pretrained:
+            import torchvision
+            tv = torchvision.models.resnet18(weights=torchvision.models.ResNet18_Weights.IMAGENET1K_V1)
+            names = ("layer1", "layer2", "layer3", "layer4") + (("conv1", "bn1") if in_channels == 3 else ())
+            for name in names:
+                getattr(self, name).load_state_dict(getattr(tv, name).state_dict())
+        self.precision = _precision_from_env()
+        self._engine = None
+        self._anchor = None
+        self._fwd_serial = 0
