@@ -215,6 +215,9 @@ def main():
     model.train()
     ddp.broadcast_parameters(model)
     opt = FusedSGD(model, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    overlap = world > 1 and os.environ.get("RD_DDP_OVERLAP", "1") != "0"
+    if overlap:
+        ddp.enable_overlap(model)          # bucketed all-reduce started from inside the backward pass
 
     h_in, h_tg = synth_host_batch(b, 1234 + rank, p_lidar=0.05)
     h_in, h_tg = h_in.pin_memory(), h_tg.pin_memory()
@@ -227,7 +230,7 @@ def main():
         loss = loss_fn(pred, x, t)
         opt.zero_grad()
         loss.backward()
-        collectives[0] = ddp.allreduce_gradients(model)
+        collectives[0] = ddp.allreduce_gradients(model, opt)
         opt.step()
         return loss
 
@@ -323,7 +326,7 @@ def main():
                        "arch": args.arch, "deterministic": bool(eng.det),
                        "global_batch": world * b, "parallelism": f"dp{world}", "cuda_graphs": bool(eng.use_graphs),
                        "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
-                       "collectives_per_step": collectives[0], "loss_after_warmup": loss0,
+                       "collectives_per_step": collectives[0], "allreduce_overlapped_with_backward": bool(overlap), "loss_after_warmup": loss0,
                        "loss_after_timed_steps": float(last["loss"])},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K},

@@ -290,6 +290,10 @@ int rd_sid_filter(const float* radar, const float* depth, long long n, float* ra
 int rd_pack_weights(const float* src, const int32_t* idx, void* out, long long n, void* stream);
 int rd_unpack_grads(const float* dw, const int32_t* idx, float* grad, long long n, void* stream);
 int rd_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first, void* stream);
+/* Same with the gradient multiplied by grad_scale first: the 1/world of a data-parallel SUM all-reduce folded into
+ * the update instead of a separate pass over the 58.8 MB gradient arena. */
+int rd_sgd_scaled(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first,
+                  float grad_scale, void* stream);
 
 /* Graph cut at the bottleneck: ResNet_latefusion.pnp_forward_front returns bn2's output, pnp_forward_rear consumes it
  * (models.py:669-707).  export: NHWC activation slice -> NCHW fp32 through an optional per-channel affine (sc/sh both

@@ -121,6 +121,7 @@ _PROTOS = {
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),
     "rd_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _I, _P], _I),
+    "rd_sgd_scaled": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
     "rd_feature_export": ([View, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "rd_feature_import": ([_P, View, _I, _I, _I, _I, _I, _P], _I),
 }

@@ -1045,9 +1045,10 @@ __global__ void unpack_grads_kernel(const float* __restrict__ dw, const int* __r
 
 // Fused SGD with momentum + weight decay over the flat parameter arena (torch.optim.SGD as at main.py:285-290).
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, size_t n, float lr,
-                           float momentum, float wd, int first) {
+                           float momentum, float wd, int first, float gscale) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float d = g[i] + wd * p[i];
+        const float gi = gscale == 1.f ? g[i] : g[i] * gscale;      // gscale = 1/world: the all-reduce's averaging, fused
+        const float d = gi + wd * p[i];
         const float b = first ? d : momentum * mom[i] + d;
         mom[i] = b;
         p[i] -= lr * b;

@@ -658,6 +658,7 @@ class LatefusionEngine:
             emit_conv(bw, cf, "d", _v(g_f), _v(d_concat))
 
         dpool = []
+        cut_enc, cut_l4 = len(bw), None     # gradient-bucket boundaries of the backward program (see _grad_buckets)
         for lane, blks in enumerate(blocks_all):
             bseg0 = len(bw)
             d_out_v = _v(d_concat, blks[-1]["cat_off"])
@@ -700,6 +701,8 @@ class LatefusionEngine:
                 else:
                     emit_conv(bw, Bk["c1"], "d", _v(g1), _v(dx), addend=_v(g_t))
                 d_out_v = _v(dx)
+                if lane == 0 and Bk["pfx"] == "layer4.0":
+                    cut_l4 = len(bw)
             dpool.append(d_out_v)
             if par:
                 for L in bw[bseg0:]:
@@ -750,6 +753,7 @@ class LatefusionEngine:
                                        (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams),
                          dict(bytes=self.nparams * (4 + 4 + 8))))
+        self._grad_buckets(cut_enc, cut_l4, single)
         self.stats_used = self.stats[:self._stats_used]
         # programs of the graph cut (pack_weights / bn_fin_eval_all were inserted at the heads above)
         exp = Launch("feature_export", lib.rd_feature_export,
@@ -777,6 +781,31 @@ class LatefusionEngine:
         self.dbg = dict(z_stem=z_stem, gz_stem=gz_stem, p_rgb=p_rgb, p_d=p_d, amax=amax, xs=xs, concat=concat, d_concat=d_concat,
                         zf=zf, zc2=zc2, g_stem=g_stem)
 
+    # ------------------------------------------------------------------ gradient buckets (overlapped all-reduce, ddp.py)
+    def _grad_buckets(self, cut_enc: int, cut_l4: int, single: bool) -> None:
+        """The backward program in three segments whose parameter gradients are FINAL when the segment ends, in the order
+        the backward produces them ("decoder grads are ready first, RGB stem last"):
+          0: head, decoder, conv2, fusion (arena tail)        -- ends where the encoders' backward starts;
+          1: RGB layer4 (8.4 M of the 14.7 M parameters)      -- ends after layer4.0's weight gradients;
+          2: everything else (RGB layers 1-3, depth encoder, stems).
+        Each segment ends with the rd_unpack_grads launches of its own arena ranges, so ddp.py can start the all-reduce of
+        a bucket while the next segment computes.  self.bwd (one segment, one unpack launch) stays the default program."""
+        names = list(self.offs)
+        first_tail = "conv2.weight" if single else "conv_fusion.weight"
+        t0 = self.offs[first_tail][0]
+        l4 = [i for i, n in enumerate(names) if n.startswith("layer4.")]
+        a4 = self.offs[names[l4[0]]][0]
+        b4 = self.offs[names[l4[-1] + 1]][0]
+        rest = [(0, a4)] + ([(b4, t0)] if b4 < t0 else [])
+        self.grad_ranges = [[(t0, self.nparams)], [(a4, b4)], rest]
+        body = self.bwd[:-1]                                   # without the whole-arena unpack launch
+        cuts = [0, cut_enc, cut_l4, len(body)]
+
+        def unpack(a, b):
+            return Launch(f"unpack_grads[{a}:{b}]", self.lib.rd_unpack_grads,
+                          (_p(self.dw), _p(self.unpack_idx, a), _p(self.gflat, a), b - a), dict(bytes=(b - a) * 16))
+        self.bwd_segments = [body[cuts[k]:cuts[k + 1]] + [unpack(a, b) for a, b in self.grad_ranges[k]] for k in range(3)]
+
     # ------------------------------------------------------------------ execution
     def _run(self, prog: List[Launch]):
         # (Weight-gradient launches on a second, event-forked stream were tried: 10.91 vs 10.92 ms/step on B200 --
@@ -785,9 +814,11 @@ class LatefusionEngine:
         st = main.cuda_stream
         lib = self.lib
         side = None
+        # a program slice that starts inside the two-lane region (segmented backward) forks at its first launch
+        fork_first = any(L.lane == 1 for L in prog) and not any(L.sync == "fork" for L in prog)
         with determinism.mode(self.det_scratch if self.det else None):
-            for L in prog:
-                if L.sync == "fork":
+            for i, L in enumerate(prog):
+                if L.sync == "fork" or (fork_first and i == 0):
                     # the side stream joins here (under CUDA-graph capture this event edge forks the graph)
                     if self._side is None or self._side.device != main.device:
                         self._side = torch.cuda.Stream(device=main.device)
@@ -838,6 +869,12 @@ class LatefusionEngine:
         # by its tails), so a second backward over the same forward (retain_graph) accumulates correctly
         self.stats_used.zero_()
         self._run(self.bwd)
+
+    def _bwd_segment(self, k: int):
+        if k == 0:
+            self.dw.zero_()
+            self.stats_used.zero_()
+        self._run(self.bwd_segments[k])
 
     # ------------------------------------------------------------------ graph cut at the bottleneck (models.py:669-707)
     # PnP-Depth refinement runs the front once, then iterates the rear (forward + gradient w.r.t. the bottleneck feature).
@@ -899,6 +936,14 @@ class LatefusionEngine:
         self.dpred.copy_(dpred.reshape(self.dpred.shape))
         if not accumulate:
             self.gflat.zero_()
+        hook = getattr(self.module, "_rd_grad_hook", None)
+        if training and hook is not None and not accumulate:
+            # data-parallel training (ddp.enable_overlap): three segments, each followed by the hook that starts the
+            # all-reduce of the arena ranges that segment completed
+            for k in range(3):
+                self._replay(f"bwd_seg{k}", lambda k=k: self._bwd_segment(k))
+                hook(self, k)
+            return
         if training:
             self._replay("bwd", self._bwd_body)
             return

@@ -37,6 +37,8 @@ class FusedSGD:
         self._engines: List = []
         self._loose_params: List[torch.nn.Parameter] = []
         self._arena_keys = None
+        # set by ddp.allreduce_gradients(model, optimizer): gradients hold the SUM over ranks, 1/world is applied in the update
+        self.grad_scale = 1.0
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self._params:
@@ -70,13 +72,17 @@ class FusedSGD:
             first = key not in self._mom
             if first:
                 self._mom[key] = torch.zeros_like(eng.flat)
-            _lib.call("rd_sgd", ptr(eng.flat), ptr(eng.gflat), ptr(self._mom[key]), eng.flat.numel(), lr, mo, wd,
-                      1 if first else 0, stream_ptr())
+            if self.grad_scale == 1.0:
+                _lib.call("rd_sgd", ptr(eng.flat), ptr(eng.gflat), ptr(self._mom[key]), eng.flat.numel(), lr, mo, wd,
+                          1 if first else 0, stream_ptr())
+            else:
+                _lib.call("rd_sgd_scaled", ptr(eng.flat), ptr(eng.gflat), ptr(self._mom[key]), eng.flat.numel(), lr, mo, wd,
+                          1 if first else 0, float(self.grad_scale), stream_ptr())
         with torch.no_grad():
             for p in self._loose_params:
                 if p.grad is None:
                     continue
-                d = p.grad + wd * p
+                d = p.grad * self.grad_scale + wd * p
                 buf = self._loose.get(id(p))
                 buf = d.clone() if buf is None else buf.mul_(mo).add_(d)
                 self._loose[id(p)] = buf
