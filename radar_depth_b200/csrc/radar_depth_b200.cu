@@ -47,6 +47,32 @@ int set_smem(K kernel, int bytes, bool* done) {
     return rc;
 }
 
+// ---- launches: every kernel goes through rd_launch, which sets the programmatic-stream-serialization attribute (see
+// pdl_enter() in rd_common.cuh) when RD_PDL=1.  Default off: measured neutral under CUDA-graph replay, see rd_common.cuh
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RD_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+void rd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors are read with cudaGetLastError by the caller
+}
+
 // ---- deterministic mode (rd_set_deterministic): thread-local, read by the launchers at launch time
 thread_local int g_det = 0;
 thread_local char* g_scratch = nullptr;
@@ -221,11 +247,11 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     if (p->act_dtype == RD_BF16) {
         static bool done[kMaxDevices] = {false};
         { int rc = set_smem(rd::conv_fprop_kernel<rd::bf16, 1>, kMaxSmem, done); if (rc) return rc; }
-        rd::conv_fprop_kernel<rd::bf16, 1><<<grid, block, (size_t)smem, st>>>(q, map, use_tma, det_part);
+        rd_launch(rd::conv_fprop_kernel<rd::bf16, 1>, dim3(grid), dim3(block), (size_t)((size_t)smem), st, q, map, use_tma, det_part);
     } else if (p->act_dtype == RD_F32) {
         static bool done[kMaxDevices] = {false};
         { int rc = set_smem(rd::conv_fprop_kernel<float, 3>, kMaxSmem, done); if (rc) return rc; }
-        rd::conv_fprop_kernel<float, 3><<<grid, block, (size_t)smem, st>>>(q, map, 0, det_part);
+        rd_launch(rd::conv_fprop_kernel<float, 3>, dim3(grid), dim3(block), (size_t)((size_t)smem), st, q, map, 0, det_part);
     } else {
         return fail(RD_EINVAL, "rd: bad act_dtype");
     }

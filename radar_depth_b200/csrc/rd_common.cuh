@@ -24,6 +24,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// With RD_PDL=1 every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (rd_launch
+// in radar_depth_b200.cu): the next kernel of the stream may be scheduled onto SMs as soon as this kernel's CTAs have
+// all passed pdl_enter() (and SM resources free up), so its launch latency and its prologue (barrier init, shared-memory
+// zero fill, TMEM allocation) overlap the tail of this kernel.  pdl_enter() = wait until the preceding kernel has COMPLETED
+// and its memory is visible (griddepcontrol.wait), then allow the next kernel to start launching: at most one kernel is
+// ever resident ahead of the running one.  Nothing produced by an earlier kernel may be read, and nothing it might still
+// read may be written, before pdl_enter().  Without the launch attribute both instructions are no-ops.
+// Measured on B200 (round 2): eager back-to-back launches have 3.2 us between the last CTA's exit and the next kernel's
+// first CTA (tools/launch_gap.py) and PDL makes the entries overlap by 8 us, but the early CTAs only wait: 59.3 vs 56.9 us
+// per launch; under CUDA-graph replay (gap 1.7 us) the training step is 9.234 (on) vs 9.238 ms (off), multistage 12.96 vs
+// 12.84.  Hence OFF by default; the hooks stay because they cost nothing.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));

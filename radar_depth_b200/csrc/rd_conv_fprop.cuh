@@ -77,6 +77,123 @@ __device__ __forceinline__ int reduce16_owner_channel(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// ---------------------------------------------------------------- UMMA issue loop
+// Measured on B200 (tools/bench_fprop.py, dbg_flags): with loads, stores AND the tcgen05.mma instructions themselves
+// switched off, the layer1-4 forward programs still took 80-90 % of their full time -- the single issuing warp, not the
+// tensor pipe or shared memory, set the pace: ~60 SASS instructions per tap of four UMMAs (the issue predicate passed
+// as an asm operand, so every UTCHMMA carried VOTEU / UMOV pairs; the B descriptor lived in vector registers and crossed
+// to the uniform file with R2UR every tap; a 4-unrolled loop plus remainder branches), i.e. 69-108 cycles per UMMA
+// against a floor of 48 (N = 64) / 64 (N = 128).  Now ONE elected thread runs the whole loop inside the election
+// branch, the accumulator-block loop is unrolled at compile time (MBT = MB for MB <= 4, MBT = 0: run-time loop), and
+// the taps of a channel block are numbered consecutively across the weight groups (no wrap-around bookkeeping):
+// ~9 instructions per UMMA, the UTCHMMAs of a tap back to back.
+// tcgen05.mma issued from inside an `if (elect_one_sync())` branch: in that form ptxas emits one bare UTCHMMA per call
+// (operands in uniform registers, descriptor arithmetic as UIADD3.64); with the election passed as a predicate OPERAND
+// it cannot prove that at most one lane is active and wraps every UTCHMMA in an ELECT / BRA.U.ANY replay loop.
+__device__ __forceinline__ void umma_bf16_elected(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int SPLIT, int MBT>
+__device__ __forceinline__ void fprop_issue(const rd_conv_params& p, uint8_t* smem, uint32_t tmem_base, bool dbuf, int acc_cols,
+                                            int ntiles, int ncblk, int lane, long long t_entry, bool tl_mode) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* in_full = bars;
+    uint64_t* in_empty = bars + kMaxStages;
+    uint64_t* w_full = bars + 2 * kMaxStages;
+    uint64_t* w_empty = bars + 3 * kMaxStages;
+    uint64_t* tmem_full = bars + 4 * kMaxStages;
+    uint64_t* tmem_empty = bars + 4 * kMaxStages + 2;
+    uint8_t* a_ring = smem + kSmemHeader;
+    uint8_t* w_ring = a_ring + (size_t)p.IS * p.istage_bytes;
+    constexpr int PARTS = (SPLIT == 3) ? 2 : 1;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    PipeState si(p.IS), sw(p.WS);
+    const uint32_t N = (uint32_t)p.N;
+    const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+    const uint32_t PS = (uint32_t)p.chunk_stride;                    // chunk stride in slots (= 16-byte units)
+    const uint32_t tap_units = (uint32_t)PARTS * N * 2u;            // [part][2][N][8] bf16 per tap, in 16-byte units
+    const bool do_issue = !(p.dbg_flags & 1);
+    const int MB = MBT > 0 ? MBT : p.MB;
+    const uint32_t mbn = (uint32_t)MB * N;
+    // ONE elected thread runs the whole issue loop (waits, UMMAs, commits): inside the election branch ptxas keeps
+    // descriptors and tap data in uniform registers and emits bare UTCHMMAs back to back.
+    if (elect_one_sync()) {
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
+            const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
+            mbar_wait(&tmem_empty[ab], (use & 1u) ^ 1u, 0x300);
+            tc_fence_after();
+            const uint32_t d_tile = tmem_u + ab * (uint32_t)acc_cols;
+            for (int c = 0; c < ncblk; ++c) {
+                const long long t0_ = p.dbg ? clock64() : 0;
+                mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
+                const long long t1_ = p.dbg ? clock64() : 0;
+                long long tw_ = 0;
+                fence_proxy_async_smem();      // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
+                tc_fence_after();
+                const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), PS * 16u, 128);
+                const uint32_t keep = c == 0 ? 0u : 1u;                  // channel blocks after the first always accumulate
+                int t = 0;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const long long t2_ = p.dbg ? clock64() : 0;
+                    mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
+                    if (p.dbg) tw_ += clock64() - t2_;
+                    tc_fence_after();
+                    const uint64_t db0 = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), N * 16u, 128);
+                    const int gn = p.grp_n[g];
+                    for (int tl = 0; tl < gn; ++tl, ++t) {
+                        const uint64_t db = db0 + (uint32_t)tl * tap_units;
+                        const uint64_t da = da0 + (uint32_t)p.taps[t].a_shift;
+                        const uint32_t d = d_tile + (uint32_t)p.taps[t].phase * mbn;
+                        const uint32_t acc = keep | ((uint32_t)p.taps[t].first ^ 1u);
+                        if (do_issue) {
+                            if (MBT > 0) {
+#pragma unroll
+                                for (int mb = 0; mb < MBT; ++mb) {
+                                    umma_bf16_elected(d + (uint32_t)mb * N, da + (uint32_t)mb * 128u, db, idesc, acc);
+                                    if (SPLIT == 3) {
+                                        umma_bf16_elected(d + (uint32_t)mb * N, da + (uint32_t)mb * 128u, db + 2u * N, idesc, 1u);
+                                        umma_bf16_elected(d + (uint32_t)mb * N, da + (uint32_t)mb * 128u + 2u * PS, db, idesc, 1u);
+                                    }
+                                }
+                            } else {
+                                uint64_t a = da;
+                                uint32_t dd = d;
+#pragma unroll 2
+                                for (int mb = 0; mb < MB; ++mb, a += 128u, dd += N) {
+                                    umma_bf16_elected(dd, a, db, idesc, acc);
+                                    if (SPLIT == 3) {
+                                        umma_bf16_elected(dd, a, db + 2u * N, idesc, 1u);
+                                        umma_bf16_elected(dd, a + 2u * PS, db, idesc, 1u);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(&w_empty[sw.stage]);
+                    sw.advance();
+                }
+                umma_commit(&in_empty[si.stage]);
+                si.advance();
+                if (p.dbg) {
+                    const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+                    if (tl_mode) { if (tile_iter == 0 && c == 0) p.dbg[2 * ncta + cta] = t1_ - t_entry; p.dbg[3 * ncta + cta] = clock64() - t_entry; }
+                    else { p.dbg[2 * ncta + cta] += (t1_ - t0_) + tw_; p.dbg[3 * ncta + cta] += clock64() - t1_ - tw_; }
+                }
+            }
+            umma_commit(&tmem_full[ab]);
+        }
+    }
+}
+
 template <typename T, int SPLIT>
 __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __grid_constant__ rd_conv_params p,
                                                                       const __grid_constant__ CUtensorMap src_map, const int use_tma,
@@ -113,6 +230,14 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // first operand stage consumed, last UMMA committed, first accumulator ready, epilogue done
     const bool tl_mode = p.dbg && (p.dbg_flags & 8);
     const long long t_entry = p.dbg ? clock64() : 0;
+    // dbg_flags & 16 (with 8): rows 0 / 1 of the timeline hold the GLOBAL timer (ns) at CTA entry / exit instead, so that the
+    // host can separate the kernel's own duration from launch gaps (max exit of launch i -> min entry of launch i+1)
+    const bool gt_mode = tl_mode && (p.dbg_flags & 16);
+    if (gt_mode && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = (long long)gt;
+    }
     const int nb = blockIdx.y;                       // N block
     constexpr int PARTS = (SPLIT == 3) ? 2 : 1;
     const int ncblk = p.Cin >> 4;
@@ -147,15 +272,18 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     const int acc_cols = p.P * p.MB * p.N;
     const bool dbuf = 2 * acc_cols <= 512;
     for (int i = tid; i < 512; i += kFpropThreads) stats_s[i] = 0.f;
+    zero_smem(a_ring, (size_t)p.IS * p.istage_bytes, tid, kFpropThreads);   // tile tails / junk rows stay zero forever
+    fence_proxy_async_smem();
+    if (warp == kWarpW) tmem_alloc<512>(tmem_slot);
+    // Everything above depends on the kernel parameters only and overlaps the tail of the preceding kernel; from here on
+    // the kernel touches global memory (the BatchNorm vectors below were written by the producer's rd_bn_tail).
+    pdl_enter();
     if (p.ld_scale) {
         for (int i = tid; i < p.Cin; i += kFpropThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
     }
     if (p.epi == 1) {
         for (int i = tid; i < p.N; i += kFpropThreads) { ep_sc[i] = p.ep_scale[nb * p.N + i]; ep_sh[i] = p.ep_shift[nb * p.N + i]; }
     }
-    zero_smem(a_ring, (size_t)p.IS * p.istage_bytes, tid, kFpropThreads);   // tile tails / junk rows stay zero forever
-    fence_proxy_async_smem();
-    if (warp == kWarpW) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -173,7 +301,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
         ts.prepare();
-        if (tl_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
+        if (tl_mode && !gt_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
         if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
@@ -240,7 +368,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     st.advance();
                     if (p.dbg) {
                         const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                        if (tl_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry;
+                        if (tl_mode) { if (!gt_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry; }
                         else { const long long t1_ = clock64(); p.dbg[0 * ncta + cta] += t1_ - t0_; }
                     }
                     continue;
@@ -262,7 +390,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 st.advance();
                 if (p.dbg && warp == 4 && lane == 0) {
                     const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                    if (tl_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry;
+                    if (tl_mode) { if (!gt_mode) p.dbg[1 * ncta + cta] = clock64() - t_entry; }
                     else { p.dbg[0 * ncta + cta] += t1_ - t0_; p.dbg[1 * ncta + cta] += clock64() - t1_; }
                 }
             }
@@ -292,75 +420,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         __syncwarp();
     } else if (warp == kWarpMma) {
         // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
-        {
-            const bool leader = elect_one_sync();
-            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            PipeState si(p.IS), sw(p.WS);
-            const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
-            const uint32_t PS = (uint32_t)p.chunk_stride;        // chunk stride in slots
-            const uint32_t a_lbo = PS * 16u;
-            const uint32_t b_lbo = (uint32_t)p.N * 16u;
-            const uint32_t tap_bytes = (uint32_t)PARTS * p.N * 32u;
-            const uint32_t a_units = PS;                         // chunk stride in 16-byte units
-            const uint32_t tap_units = tap_bytes >> 4;
-            const uint32_t do_issue = (leader && !(p.dbg_flags & 1)) ? 1u : 0u;
-            const int mbn = p.MB * p.N;
-            uint32_t tile_iter = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
-                const uint32_t ab = dbuf ? (tile_iter & 1u) : 0u;
-                const uint32_t use = dbuf ? (tile_iter >> 1) : tile_iter;
-                mbar_wait(&tmem_empty[ab], (use & 1u) ^ 1u, 0x300);
-                tc_fence_after();
-                const uint32_t d_tile = tmem_u + ab * (uint32_t)acc_cols;
-                for (int c = 0; c < ncblk; ++c) {
-                    const long long t0_ = p.dbg ? clock64() : 0;
-                    mbar_wait(&in_full[si.stage], si.phase, 0x310 + si.stage);
-                    const long long t1_ = p.dbg ? clock64() : 0;
-                    long long tw_ = 0;
-                    fence_proxy_async_smem();      // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
-                    tc_fence_after();
-                    const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), a_lbo, 128);
-                    // Tap data comes from the (uniform) kernel parameter bank; the values of tap t+1 are fetched while
-                    // the UMMAs of tap t are being issued, so the indexed constant loads are off the issue path.
-                    int t = 0;
-                    uint32_t nx_a = (uint32_t)p.taps[0].a_shift, nx_d = (uint32_t)(p.taps[0].phase * mbn), nx_f = (uint32_t)p.taps[0].first;
-                    for (int g = 0; g < p.ngroups; ++g) {
-                        const long long t2_ = p.dbg ? clock64() : 0;
-                        mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
-                        if (p.dbg) tw_ += clock64() - t2_;
-                        tc_fence_after();
-                        uint64_t db = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), b_lbo, 128);
-                        const int gn = p.grp_n[g];
-                        for (int tl = 0; tl < gn; ++tl, db += tap_units) {
-                            uint64_t da = da0 + nx_a;
-                            uint32_t d = d_tile + nx_d;
-                            const uint32_t acc = (c == 0 && nx_f) ? 0u : 1u;
-                            t = (t + 1 < p.ntaps) ? t + 1 : 0;
-                            nx_a = (uint32_t)p.taps[t].a_shift; nx_d = (uint32_t)(p.taps[t].phase * mbn); nx_f = (uint32_t)p.taps[t].first;
-#pragma unroll 4
-                            for (int mb = 0; mb < p.MB; ++mb, da += 128, d += (uint32_t)p.N) {
-                                umma_bf16_if(do_issue, d, da, db, idesc, acc);
-                                if (SPLIT == 3) {
-                                    umma_bf16_if(do_issue, d, da, db + 2u * (uint32_t)p.N, idesc, 1u);
-                                    umma_bf16_if(do_issue, d, da + 2u * a_units, db, idesc, 1u);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (leader) umma_commit(&w_empty[sw.stage]);
-                        sw.advance();
-                    }
-                    if (leader) umma_commit(&in_empty[si.stage]);
-                    si.advance();
-                    if (p.dbg && lane == 0) {
-                        const size_t ncta = (size_t)gridDim.x * gridDim.y, cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-                        if (tl_mode) { if (tile_iter == 0 && c == 0) p.dbg[2 * ncta + cta] = t1_ - t_entry; p.dbg[3 * ncta + cta] = clock64() - t_entry; }
-                        else { p.dbg[2 * ncta + cta] += (t1_ - t0_) + tw_; p.dbg[3 * ncta + cta] += clock64() - t1_ - tw_; }
-                    }
-                }
-                if (leader) umma_commit(&tmem_full[ab]);
-                __syncwarp();
-            }
+        switch (p.MB) {
+            case 1: fprop_issue<SPLIT, 1>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
+            case 2: fprop_issue<SPLIT, 2>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
+            case 3: fprop_issue<SPLIT, 3>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
+            case 4: fprop_issue<SPLIT, 4>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
+            default: fprop_issue<SPLIT, 0>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
         }
         __syncwarp();
     } else {
@@ -515,6 +580,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     if (warp == kWarpW) tmem_dealloc<512>(tmem_base);
+    if (gt_mode && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[1 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = (long long)gt;
+        p.dbg[2 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
+    }
 }
 
 }  // namespace rd

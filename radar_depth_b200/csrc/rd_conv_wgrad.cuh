@@ -38,6 +38,7 @@ __device__ __forceinline__ void acc_out_v4(bool det, float* p, float a, float b,
 }
 // dw[i] += part[0][i] + part[1][i] + ... (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, size_t n, float* __restrict__ dw) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < nparts; ++k) s += part[(size_t)k * n + i];
@@ -104,12 +105,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         tap_g[tid] = p.taps[t0 + tid].g_off;
         tap_x[tid] = p.taps[t0 + tid].x_shift;
     }
-    if (p.ld_scale) {
-        for (int i = tid; i < p.Cin; i += kWgradThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
-    }
     zero_smem(ring, (size_t)p.NS * p.stage_bytes, tid, kWgradThreads);   // tile tails stay zero forever
     fence_proxy_async_smem();
     if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
+    pdl_enter();      // parameter-only setup above overlaps the preceding kernel's tail (rd_common.cuh)
+    if (p.ld_scale) {
+        for (int i = tid; i < p.Cin; i += kWgradThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

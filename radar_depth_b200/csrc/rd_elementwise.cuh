@@ -44,6 +44,7 @@ struct VView { void* ptr; int pitch; int coff; };   // same as rd_view, device-s
 // on the values, never on scheduling.  Launch with grid = nout, block = 32.
 template <typename TI, typename TO>
 __global__ void ordered_sum_kernel(const TI* __restrict__ part, int nparts, int stride, TO* __restrict__ out, int accumulate) {
+    pdl_enter();
     const int j = blockIdx.x, lane = threadIdx.x;
     double s = 0.0;
     for (int k = lane; k < nparts; k += 32) s += (double)part[(size_t)k * stride + j];
@@ -67,6 +68,7 @@ __device__ __forceinline__ T* vptr_w(const VView& v, size_t pix, int c) {
 // single stride-1 4x4-tap convolution over 16 (or 32) channels.
 template <typename T>
 __global__ void input_pack_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cs) {
+    pdl_enter();
     const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
     const uint32_t total = (uint32_t)B * H2 * W2 * 4;      // one thread per (pixel, parity); launcher guarantees < 2^31
     const FastDiv fdw((uint32_t)W2), fdh((uint32_t)H2);
@@ -97,6 +99,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    float* running_mean, float* running_var, long long* nbt, int C, int training,
                                    float momentum, float eps, float* scale, float* shift, float* save_mean,
                                    float* save_invstd) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && training && nbt) *nbt += 1;
     if (c >= C) return;
@@ -123,6 +126,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 
 // eval-mode finalisation of many BatchNorm layers: block b handles row b of the pointer table
 __global__ void bn_finalize_eval_multi_kernel(const long long* __restrict__ table, float eps) {
+    pdl_enter();
     const long long* row = table + (size_t)blockIdx.x * 9;
     const float* gamma = reinterpret_cast<const float*>(row[0]);
     const float* beta = reinterpret_cast<const float*>(row[1]);
@@ -149,6 +153,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
                                        const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                        const float* __restrict__ save_invstd, int C, int training, float* dgamma,
                                        float* dbeta, float* coefA, float* coefB, float* coefC) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double sg = sum_g[c], sgz = sum_gz[c];
@@ -245,6 +250,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_add_act_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, VView idv,
                                                          const float* __restrict__ id_sc, const float* __restrict__ id_sh, VView out,
                                                          size_t npix, int C, float slope) {
+    pdl_enter();
     extern __shared__ __align__(16) float coef_s[];                 // [sc | sh | id_sc | id_sh][C]
     const bool has_id = idv.ptr != nullptr, id_bn = id_sc != nullptr;
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -299,6 +305,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) join_bwd_kernel(VView dout, VView outv, VView z, VView zid, VView g, size_t npix, int C, float slope,
                                 double* sum_g, double* sum_gz, double* sum_gzid, const __grid_constant__ rd_bn_tail tail,
                                 float* det_part) {
+    pdl_enter();
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(256, 3) join_bwd_kernel(VView dout, VView outv
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(VView g, VView z, VView dz, const float* __restrict__ A,
                                                            const float* __restrict__ Bz, const float* __restrict__ Cc, size_t npix, int C) {
+    pdl_enter();
     extern __shared__ __align__(16) float coef_s[];                 // [A | Bz | Cc][C], see bn_add_act_kernel
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         coef_s[i] = A[i];
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(VView g, VView z, VVi
 // BN that follows conv_fusion / conv2 when the gradient arrives from an elementwise producer.
 template <typename T>
 __global__ void grad_stats_kernel(VView g, VView z, size_t npix, int C, double* sum_g, double* sum_gz) {
+    pdl_enter();
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -437,6 +446,7 @@ template <typename T>
 __global__ void maxpool_fwd_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W,
                                    int C, int split, float slope_a, float slope_b, VView outa, VView outb,
                                    uint8_t* __restrict__ amax, int Ho, int Wo) {
+    pdl_enter();
     const int groups = C >> 3;
     const uint32_t total = (uint32_t)B * Ho * Wo * groups;
     const FastDiv fdg((uint32_t)groups), fdw((uint32_t)Wo), fdh((uint32_t)Ho);
@@ -488,6 +498,7 @@ constexpr int kMpTileH = 4, kMpTileW = 16, kMpInH = 2 * kMpTileH + 1, kMpInW = 2
 __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int H, int W, int C,
                                         int split, float slope_a, float slope_b, VView outa, VView outb,
                                         uint8_t* __restrict__ amax, int Ho, int Wo) {
+    pdl_enter();
     extern __shared__ uint4 mp_tile[];                 // [kMpInH][kMpInW][G]
     const int G = C >> 3;
     const int b = blockIdx.z, oy0 = blockIdx.y * kMpTileH, ox0 = blockIdx.x * kMpTileW;
@@ -562,6 +573,7 @@ __global__ void maxpool_bwd_kernel(VView dpa, VView dpb, const uint8_t* __restri
                                    const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
                                    int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
                                    double* sum_gz, const __grid_constant__ rd_bn_tail tail, float* det_part) {
+    pdl_enter();
     extern __shared__ float red_s[];
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups;
@@ -636,6 +648,7 @@ __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VVi
                                         const float* __restrict__ sc, const float* __restrict__ sh, int B, int H, int W, int C,
                                         int split, float slope_a, float slope_b, int Ho, int Wo, VView g, double* sum_g,
                                         double* sum_gz, const __grid_constant__ rd_bn_tail tail, float* det_part) {
+    pdl_enter();
     extern __shared__ __align__(16) uint8_t mb_smem[];
     const int G = C >> 3;
     float* accum = reinterpret_cast<float*>(mb_smem);                                // [kMbTileH*kMbTileW][C] fp32, zero between tiles
@@ -742,6 +755,7 @@ __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VVi
 template <typename T>
 __global__ void __launch_bounds__(256) head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16][3][3] OIHW with O=1*/, int B,
                                                             int H, int W, float* __restrict__ out) {
+    pdl_enter();
     // weights re-laid as [tap][16]: a tap's 16 channel weights are four broadcast LDS.128 (the [c][tap] order cost one
     // LDS per FMA and made the kernel shared-memory-issue bound); four independent accumulator chains
     __shared__ __align__(16) float ws[9 * 16];
@@ -791,6 +805,7 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(VView x, const float
 template <typename T>
 __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __restrict__ dc3, VView x, const float* __restrict__ w,
                                                              int B, int H, int W, VView dx, float* dw /*[144]*/, float* det_part) {
+    pdl_enter();
     __shared__ __align__(16) float ws[144];            // [half][tap][8]: a tap's 8 weights of one half = two LDS.128
     __shared__ float dws[144];
     __shared__ float dws_w[8][144];                    // deterministic mode: one copy per warp, added in warp order
@@ -866,6 +881,7 @@ __global__ void __launch_bounds__(256, 2) head_conv_bwd_kernel(const float* __re
 
 // bilinear, align_corners=True (models.py:588,662): src = dst * (in-1)/(out-1).
 __global__ void bilinear_fwd_kernel(const float* __restrict__ in, int B, int Hi, int Wi, float* __restrict__ out, int Ho, int Wo) {
+    pdl_enter();
     const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
     const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
     const uint32_t total = (uint32_t)B * Ho * Wo;           // launcher guarantees < 2^31
@@ -888,6 +904,7 @@ __global__ void bilinear_fwd_kernel(const float* __restrict__ in, int B, int Hi,
 
 // bilinear_bwd (gather form, deterministic): din[b,iy,ix] = sum over output pixels whose 2x2 footprint holds it.
 __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int Hi, int Wi, float* __restrict__ din, int Ho, int Wo) {
+    pdl_enter();
     const float ry = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
     const float rx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
     const uint32_t total = (uint32_t)B * Hi * Wi;           // launcher guarantees < 2^31
@@ -935,6 +952,7 @@ __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int H
 // the reference, sums in fp64.
 __global__ void depth_metrics_kernel(const float* __restrict__ output, const float* __restrict__ target, size_t n, float lo, float hi,
                                      double* acc) {
+    pdl_enter();
     double s[RD_METRIC_SLOTS];
 #pragma unroll
     for (int i = 0; i < RD_METRIC_SLOTS; ++i) s[i] = 0.0;
@@ -979,6 +997,7 @@ __global__ void depth_metrics_kernel(const float* __restrict__ output, const flo
 // acc[0] += sum, acc[1] += count (fp64), then a 1-thread finalize writes the fp32 scalar.
 __global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* acc,
                               double* det_part /* deterministic mode: [block][2] partials instead of atomics */) {
+    pdl_enter();
     float s = 0.f, cnt = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float t = target[i];
@@ -1002,12 +1021,14 @@ __global__ void l1_fwd_kernel(const float* __restrict__ pred, const float* __res
         }
     }
 }
-__global__ void l1_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] / acc[1]); }   // 0/0 -> NaN like the reference
+__global__ void l1_finalize_kernel(const double* acc, float* loss) {
+    pdl_enter(); *loss = (float)(acc[0] / acc[1]); }   // 0/0 -> NaN like the reference
 
 // grad_pred = gout * (-sign(target - pred)) / count on valid pixels, 0 elsewhere.
 __global__ void l1_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n,
                               const double* __restrict__ acc, const float* __restrict__ gout, float* __restrict__ gpred,
                               int accumulate) {
+    pdl_enter();
     const float k = (*gout) / (float)acc[1];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float t = target[i];
@@ -1024,6 +1045,7 @@ __global__ void l1_bwd_kernel(const float* __restrict__ pred, const float* __res
 // Weight packing: out[i] = bf16(part(src[idx[i]]))  with idx < 0 -> 0; bit 30 of idx selects the lo part of the
 // bf16 hi/lo split (parity mode).  One launch packs every layer (the table is built once on the host).
 __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __restrict__ idx, bf16* __restrict__ out, size_t n) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int e = idx[i];
         float v = 0.f;
@@ -1037,6 +1059,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __
 }
 // Gradient unpacking: grad[i] (+)= dw[idx[i]] (idx < 0: leave untouched).
 __global__ void unpack_grads_kernel(const float* __restrict__ dw, const int* __restrict__ idx, float* __restrict__ grad, size_t n) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int e = idx[i];
         if (e >= 0) grad[i] += dw[e];
@@ -1046,6 +1069,7 @@ __global__ void unpack_grads_kernel(const float* __restrict__ dw, const int* __r
 // Fused SGD with momentum + weight decay over the flat parameter arena (torch.optim.SGD as at main.py:285-290).
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, size_t n, float lr,
                            float momentum, float wd, int first, float gscale) {
+    pdl_enter();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float gi = gscale == 1.f ? g[i] : g[i] * gscale;      // gscale = 1/world: the all-reduce's averaging, fused
         const float d = gi + wd * p[i];
@@ -1059,6 +1083,7 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 // SID radar filter (multistage_model.py:87-119): thr = exp(d*ln(18/5)/100 + ln 5); mask = |d - radar| <= thr.
 __global__ void sid_filter_kernel(const float* __restrict__ radar, const float* __restrict__ depth, size_t n,
                                   float* __restrict__ radar_f, float* __restrict__ mask) {
+    pdl_enter();
     const float k = 0.012809338454620642f;   // ln(18/5)/100
     const float l5 = 1.6094379124341003f;    // ln 5
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1077,6 +1102,7 @@ __global__ void sid_filter_kernel(const float* __restrict__ radar, const float* 
 // The reference calls it with the full 4-channel network input as "image" (main.py:422), so C is a parameter.
 __global__ void image_sum_kernel(const float* __restrict__ d, int B, size_t hw, double* sums /*[B]*/,
                                  double* det_part /* deterministic mode: [blockIdx.x][B] partials */) {
+    pdl_enter();
     const int b = blockIdx.y;
     float s = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += d[b * hw + i];
@@ -1128,6 +1154,7 @@ __global__ void smoothness_kernel(const float* __restrict__ d, const float* __re
                                   const double* __restrict__ sums, int mode, double* acc, double* gd,
                                   const float* __restrict__ gout, float* __restrict__ grad, int accumulate,
                                   double* det_part /* deterministic mode: mode 0 [block y*gx+x][2], mode 1 [blockIdx.x][B] */) {
+    pdl_enter();
     __shared__ double red[32];
     const size_t hw = (size_t)H * W;
     const int b = blockIdx.y;
@@ -1176,7 +1203,8 @@ __global__ void smoothness_kernel(const float* __restrict__ d, const float* __re
         }
     }
 }
-__global__ void smoothness_finalize_kernel(const double* acc, float* loss) { *loss = (float)(acc[0] + acc[1]); }
+__global__ void smoothness_finalize_kernel(const double* acc, float* loss) {
+    pdl_enter(); *loss = (float)(acc[0] + acc[1]); }
 
 // feature_export: NHWC activation slice -> NCHW fp32, optionally through a per-channel affine (the BatchNorm that the
 // next conv would have applied on load).  feature_import: NCHW fp32 -> NHWC activation slice.  Used where the graph is
@@ -1185,6 +1213,7 @@ __global__ void smoothness_finalize_kernel(const double* acc, float* loss) { *lo
 template <typename T>
 __global__ void feature_export_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, float* __restrict__ out,
                                       int B, int HW, int C) {
+    pdl_enter();
     const int groups = C >> 3;
     const uint32_t total = (uint32_t)B * (uint32_t)HW * (uint32_t)groups;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1204,6 +1233,7 @@ __global__ void feature_export_kernel(VView z, const float* __restrict__ sc, con
 }
 template <typename T>
 __global__ void feature_import_kernel(const float* __restrict__ x, VView z, int B, int HW, int C) {
+    pdl_enter();
     const int groups = C >> 3;
     const uint32_t total = (uint32_t)B * (uint32_t)HW * (uint32_t)groups;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
