@@ -215,7 +215,10 @@ def main():
     model.train()
     ddp.broadcast_parameters(model)
     opt = FusedSGD(model, lr=0.01, momentum=0.9, weight_decay=1e-4)
-    overlap = world > 1 and os.environ.get("RD_DDP_OVERLAP", "1") != "0"
+    # Bucketed all-reduce inside the backward pass: measured SLOWER than one exposed collective at N=2 (latefusion 9.52 vs
+    # 9.36 ms/step, multistage 13.47 vs 13.21: NCCL's CTAs displace persistent 148-CTA conv kernels, whose stragglers then
+    # wait for an SM, and the three-segment backward adds two graph launches), so it is opt-in (RD_DDP_OVERLAP=1).
+    overlap = world > 1 and os.environ.get("RD_DDP_OVERLAP", "0") == "1"
     if overlap:
         ddp.enable_overlap(model)          # bucketed all-reduce started from inside the backward pass
 

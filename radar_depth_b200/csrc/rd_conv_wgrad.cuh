@@ -66,6 +66,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWarpMma = 4 + kWgLoaderWarps;
+    // dbg_flags & 8: the four counters become a timeline (cycles since kernel entry): first stage ready, last UMMA issued,
+    // accumulators complete (epilogue starts), epilogue done
+    const bool tl_mode = p.dbg && (p.dbg_flags & 8);
+    const long long t_entry = p.dbg ? clock64() : 0;
+    const size_t dbg_ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+    const size_t dbg_cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
     const int cob = blockIdx.y;
     const int cib = blockIdx.z / p.ntg;
     const int tg = blockIdx.z - cib * p.ntg;
@@ -163,11 +169,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     }
                 }
                 st.advance();
-                if (p.dbg && lane == 0) {
-                    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
-                    const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
-                    p.dbg[0 * ncta + cta] += tw1 - tw0;
-                }
+                if (p.dbg && !tl_mode && lane == 0) p.dbg[0 * dbg_ncta + dbg_cta] += tw1 - tw0;
                 continue;
             }
             // ---- worker warps
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 if (lane == 0) mbar_arrive(&full[st.stage]);
             }
             st.advance();
-            if (p.dbg && !any_tma && warp == 4 && lane == 0) {
+            if (p.dbg && !tl_mode && !any_tma && warp == 4 && lane == 0) {
                 const long long tw2 = clock64();
                 const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
                 const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
@@ -284,10 +286,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 first_tile = false;
                 if (p.dbg && lane == 0) {
                     const long long tm2 = clock64();
-                    const size_t ncta = (size_t)gridDim.x * gridDim.y * gridDim.z;
-                    const size_t cta = blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z);
-                    p.dbg[2 * ncta + cta] += tm1 - tm0;
-                    p.dbg[3 * ncta + cta] += tm2 - tm1;
+                    if (tl_mode) {
+                        if (tile == (int)blockIdx.x) p.dbg[0 * dbg_ncta + dbg_cta] = tm1 - t_entry;
+                        p.dbg[1 * dbg_ncta + dbg_cta] = tm2 - t_entry;
+                    } else {
+                        p.dbg[2 * dbg_ncta + dbg_cta] += tm1 - tm0;
+                        p.dbg[3 * dbg_ncta + dbg_cta] += tm2 - tm1;
+                    }
                 }
             }
             if (leader) umma_commit(tmem_full);
@@ -298,6 +303,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         const bool has_work = (int)blockIdx.x < ntiles;
         mbar_wait(tmem_full, 0, 0x600);
         tc_fence_after();
+        if (tl_mode && tid == 0) p.dbg[2 * dbg_ncta + dbg_cta] = clock64() - t_entry;
         const int row = warp * 32 + lane;                 // output channel within the block
         const bool valid = has_work && row < p.Mc && (co0 + row) < p.Cout;
         const bool det = det_part != nullptr;
@@ -339,6 +345,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
 
     tc_fence_before();
     __syncthreads();
+    if (tl_mode && tid == 0) p.dbg[3 * dbg_ncta + dbg_cta] = clock64() - t_entry;
     if (warp == kWarpMma) tmem_dealloc<512>(tmem_base);
 }
 
