@@ -338,6 +338,10 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     P = len(phases)
     ntaps = len(taps)
     assert ntaps <= _lib.RD_MAX_TAPS
+    if tile_override is None and use_tuned:
+        tile_override = tuned_table().get(tune_key("f", g, B, src_hw, dst_hw, act_dtype))
+    if n_per_cta is None and tile_override and "N" in tile_override:
+        n_per_cta = int(tile_override["N"])            # measured: output channels per CTA (tools/autotune.py)
     if n_per_cta is None:
         n_per_cta = min(g.N, 128)
         while g.N % n_per_cta:
@@ -361,11 +365,9 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     base, rem = divmod(ntaps, ngroups)
     grp_n = [base + (1 if i < rem else 0) for i in range(ngroups)]
     wstage = _round_up(max(grp_n) * tap_bytes, 128)
-    if tile_override is None and use_tuned:
-        tile_override = tuned_table().get(tune_key("f", g, B, src_hw, dst_hw, act_dtype))
     geo = None
     if tile_override:
-        geo = dict(tile_override)
+        geo = {k: v for k, v in tile_override.items() if k != "N"}
         geo.setdefault("Wl", geo["Wt"] + halo_x)
         geo.setdefault("MB", -(-geo["Ht"] * geo["Wl"] // 128))
         M = geo["MB"] * 128
@@ -384,10 +386,10 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     WS = 2
     while True:
         grown = False
-        if WS < 4 and FPROP_HEADER + IS * istage + (WS + 1) * wstage <= budget:
+        if WS < 6 and FPROP_HEADER + IS * istage + (WS + 1) * wstage <= budget:
             WS += 1
             grown = True
-        if IS < 3 and FPROP_HEADER + (IS + 1) * istage + WS * wstage <= budget:
+        if IS < 6 and (IS + 1) * istage <= 98304 and FPROP_HEADER + (IS + 1) * istage + WS * wstage <= budget:
             IS += 1
             grown = True
         if not grown:

@@ -32,12 +32,9 @@ def time_launch(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 
-def fprop_candidates(g, src_hw, dst_hw):
+def fprop_candidates(g, src_hw, dst_hw, N):
     taps, phases = g.sorted_taps()
     P = len(phases)
-    N = min(g.N, 128)
-    while g.N % N:
-        N -= 16
     dH, dW = dst_hw
     Hb, Wb = -(-dH // g.OS), -(-dW // g.OS)
     sx = [t.s[1] for t in taps]
@@ -51,7 +48,21 @@ def fprop_candidates(g, src_hw, dst_hw):
             Ht = min(M // Wl, Hb)
             if Ht < 1 or (MB > 1 and Ht * Wl <= (MB - 1) * 128):
                 continue
-            out.append(dict(Ht=Ht, Wt=Wl - halo_x))
+            out.append(dict(Ht=Ht, Wt=Wl - halo_x, N=N))
+    return out
+
+
+def n_candidates(g):
+    """Output channels per CTA: the default (<= 128) and, for wide layers, 256 (one UMMA then amortises the A operand read
+    over twice the columns) and 64."""
+    P = len(g.sorted_taps()[1])
+    N0 = min(g.N, 128)
+    while g.N % N0:
+        N0 -= 16
+    out = [N0]
+    for n in (256, 64):
+        if n != N0 and g.N % n == 0 and g.N >= n and P * n <= 512 and n not in out:
+            out.append(n)
     return out
 
 
@@ -80,7 +91,10 @@ for rec in eng.convs:
         # every candidate's OUTPUT is checked against the slow torch evaluation of the same GConv before its time counts
         ref = cp.gconv_reference(gg, x.float(), w.bfloat16().float(), d_hw)
         covered = {t.ph for t in gg.taps}
-        for ov in [None] + fprop_candidates(gg, s_hw, d_hw):
+        cands = [None]
+        for n_ in n_candidates(gg):
+            cands += fprop_candidates(gg, s_hw, d_hw, n_)
+        for ov in cands:
             try:
                 plan = cp.plan_fprop(gg, B, s_hw, d_hw, act, tile_override=ov, use_tuned=False)
             except Exception:
@@ -101,7 +115,7 @@ for rec in eng.convs:
                 continue
             geo = plan.info["geo"]
             if best is None or ms < best[0]:
-                best = (ms, dict(Ht=geo["Ht"], Wt=geo["Wt"]), ov is None)
+                best = (ms, dict(Ht=geo["Ht"], Wt=geo["Wt"], N=plan.info["N"]), ov is None)
             if ov is None:
                 base = ms
         if best is None:
