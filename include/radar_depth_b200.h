@@ -41,7 +41,7 @@ extern "C" {
 const char* rd_last_error(void);
 int rd_version(void);
 /* sizeof() of the parameter blocks below, for binding self-checks. */
-int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params, 2: rd_bn_tail */
+int rd_sizeof(int which); /* 0: rd_conv_params, 1: rd_wgrad_params, 2: rd_bn_tail, 3: rd_aug_sample */
 /* reads and clears the device-side error word (0 = none).  Synchronises the stream. */
 int rd_device_error(void* stream);
 
@@ -301,6 +301,37 @@ int rd_sgd_scaled(float* p, const float* g, float* mom, long long n, float lr, f
 int rd_feature_export(rd_view z, const float* sc, const float* sh, float* out_nchw, int B, int H, int W, int C, int act_dtype,
                       void* stream);
 int rd_feature_import(const float* x_nchw, rd_view z, int B, int H, int W, int C, int act_dtype, void* stream);
+
+/* ---- Input pipeline on the GPU: the reference's per-sample CPU transforms for a whole batch of RAW exported
+ * samples resident in device memory -- uint8 image [B][H][W][3], int16 lidar / radar depth [B][H][W] in 1/256 m
+ * (dataset/nuscenes_export.py:24-27).  Replaces dataset/nuscenes_dataset_torch_new.py:190-195 (h5 depth decode), :237-412
+ * (transform_train: transforms.Rotate -> Resize -> Crop -> HorizontalFlip, ColorJitter, /255, depth / scale, the
+ * max_depth filter of the radar channel :373-374, torch.cat :375) and :415-560 (transform_val: CenterCrop, /255).
+ * Bit-exact with scipy.ndimage.rotate(order 0) / PIL Image.resize / PIL ImageEnhance; the random draws and the small
+ * per-sample tables (PIL's resampling coefficients and nearest-index tables for the crop window) are made on the host
+ * (radar_depth_b200/dataset/gpu_pipeline.py). */
+typedef struct rd_aug_sample {
+    double m00, m01, m10, m11, off0, off1; /* scipy.ndimage.rotate: input (y, x) = M * output (y, x) + off */
+    double factor[3];                      /* ColorJitter factors, in the order the operations are applied */
+    float depth_div;                       /* (float) scale factor: depth /= scale (nuscenes_dataset_torch_new.py:311,325) */
+    int32_t identity_rot;                  /* 1 = no rotation at all (validation) */
+    int32_t flip;                          /* HorizontalFlip */
+    int32_t crop_i, crop_j;                /* upper / left corner of the crop (in the resized image; val: in the raw image) */
+    int32_t op[3];                         /* 0 brightness, 1 contrast, 2 saturation ("Color"), in application order */
+    int32_t pad_;
+} rd_aug_sample;
+
+/* rotate -> bytescale (scipy.misc.imresize's toimage) -> PIL bilinear resize -> crop -> flip -> ColorJitter.
+ * bil_tab [B][ch + cw][5] int32: for every output row then column of the crop window {first source index, taps (<= 3),
+ * k0, k1, k2} in PIL's 22-bit fixed point; scratch: >= B * 32 bytes; img8 [B][ch][cw][3] uint8 (the jittered crop). */
+int rd_aug_rgb(const void* images, const rd_aug_sample* samples, const int32_t* bil_tab, void* scratch, int B, int H, int W,
+               int ch, int cw, void* img8, void* stream);
+/* Final assembly into the network's NCHW fp32 input.  mode 0 (train): rgb from img8, depth through flip -> crop -> PIL
+ * nearest (near_tab [B][ch + cw] int32: source row / column in the rotated image) -> rotation; mode 1 (val): centre crop of
+ * the raw data at (samples[b].crop_i, crop_j).  inputs [B][3 + has_radar][ch][cw], labels / radar_out [B][1][ch][cw]. */
+int rd_aug_pack(const void* img8, const void* images, const void* lidar, const void* radar, const rd_aug_sample* samples,
+                const int32_t* near_tab, int B, int H, int W, int ch, int cw, int mode, int has_radar, float max_depth,
+                float* inputs, float* labels, float* radar_out, void* stream);
 
 #ifdef __cplusplus
 }

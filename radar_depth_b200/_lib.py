@@ -86,6 +86,13 @@ class WgradParams(C.Structure):
     ]
 
 
+class AugSample(C.Structure):
+    """rd_aug_sample: per-sample parameters of the GPU input pipeline (radar_depth_b200/dataset/gpu_pipeline.py)."""
+    _fields_ = [("m00", C.c_double), ("m01", C.c_double), ("m10", C.c_double), ("m11", C.c_double), ("off0", C.c_double),
+                ("off1", C.c_double), ("factor", C.c_double * 3), ("depth_div", C.c_float), ("identity_rot", C.c_int32),
+                ("flip", C.c_int32), ("crop_i", C.c_int32), ("crop_j", C.c_int32), ("op", C.c_int32 * 3), ("pad_", C.c_int32)]
+
+
 _lib = None
 
 _I, _F, _D, _P, _LL = C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_longlong
@@ -124,6 +131,8 @@ _PROTOS = {
     "rd_sgd_scaled": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
     "rd_feature_export": ([View, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "rd_feature_import": ([_P, View, _I, _I, _I, _I, _I, _P], _I),
+    "rd_aug_rgb": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "rd_aug_pack": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P], _I),
 }
 EXPORTS = tuple(_PROTOS.keys()) + ("rd_last_error",)
 
@@ -148,6 +157,8 @@ def load():
     if lib.rd_sizeof(0) != C.sizeof(ConvParams) or lib.rd_sizeof(1) != C.sizeof(WgradParams):
         raise RdError("parameter block layout mismatch between _lib.py and the built library: "
                       f"{lib.rd_sizeof(0)} vs {C.sizeof(ConvParams)}, {lib.rd_sizeof(1)} vs {C.sizeof(WgradParams)}")
+    if lib.rd_sizeof(3) != C.sizeof(AugSample):
+        raise RdError(f"rd_aug_sample layout mismatch: {lib.rd_sizeof(3)} vs {C.sizeof(AugSample)}")
     _lib = lib
     return lib
 

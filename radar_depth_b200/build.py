@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libradar_depth_b200.so")
 SOURCES = ["radar_depth_b200.cu"]
-DEPS = ["rd_common.cuh", "rd_tile.cuh", "rd_conv_fprop.cuh", "rd_conv_wgrad.cuh", "rd_elementwise.cuh",
+DEPS = ["rd_common.cuh", "rd_tile.cuh", "rd_conv_fprop.cuh", "rd_conv_wgrad.cuh", "rd_elementwise.cuh", "rd_dataset.cuh",
         "rd_api_rest.inc", os.path.join("..", "..", "include", "radar_depth_b200.h")]
 
 

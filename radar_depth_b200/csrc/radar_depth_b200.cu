@@ -12,6 +12,7 @@
 #include "rd_conv_fprop.cuh"
 #include "rd_conv_wgrad.cuh"
 #include "rd_elementwise.cuh"
+#include "rd_dataset.cuh"
 
 namespace {
 
@@ -154,6 +155,7 @@ int rd_sizeof(int which) {
         case 0: return (int)sizeof(rd_conv_params);
         case 1: return (int)sizeof(rd_wgrad_params);
         case 2: return (int)sizeof(rd_bn_tail);
+        case 3: return (int)sizeof(rd_aug_sample);
         default: return -1;
     }
 }
