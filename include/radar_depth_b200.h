@@ -146,7 +146,8 @@ typedef struct rd_conv_params {
     rd_view dst;
     int32_t dstH, dstW;
     /* epilogue */
-    int32_t epi;             /* 0 store(+addend)+sum/sumsq stats; 1 activation-gradient mask + sum g / sum g*z stats */
+    int32_t epi;             /* 0 store(+addend)+sum/sumsq stats; 1 activation-gradient mask + sum g / sum g*z stats;
+                                2 folded BatchNorm + addend + activation (inference, see ep_split below) */
     rd_view addend;          /* ptr NULL = none; same spatial size as dst */
     rd_view zsrc;            /* epi 1: producer's pre-BN output z, same spatial size as dst */
     const float* ep_scale;   /* epi 1: [nblk*N] BN scale/shift of the layer being differentiated */
@@ -164,6 +165,13 @@ typedef struct rd_conv_params {
     int32_t dbg_flags;       /* diagnostics only: 1 = skip UMMA issue, 2 = skip tile staging, 4 = skip epilogue stores */
     int32_t src_planes;      /* S = 2: number of parity planes the taps actually read, staged from plane 0 on (0 = all four);
                                 a 1x1 stride-2 convolution only ever reads plane (0,0) */
+    /* epi 2 (inference, main.py:584-595 under model.eval() + torch.no_grad()): the BatchNorm that follows the convolution is
+     * a fixed per-channel affine map (running statistics), so it is folded into the epilogue together with the residual
+     * add and the activation: out = act(acc * ep_scale[n] + ep_shift[n] + addend), slope ep_slope for output channels
+     * < ep_split and ep_slope_b from ep_split on (UpProj: ReLU on the upper branch, identity on the bottom branch; stems:
+     * ReLU on the RGB channels, LeakyReLU(0.2) on the depth channels).  No statistics, no separate join kernel. */
+    int32_t ep_split;        /* multiple of 16 */
+    float ep_slope_b;
 } rd_conv_params;
 
 int rd_conv_fprop(const rd_conv_params* p, void* stream);

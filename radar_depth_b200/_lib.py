@@ -62,6 +62,7 @@ class ConvParams(C.Structure):
         ("stats", C.c_void_p), ("stats_stride", C.c_int32), ("tail", BnTail),
         ("IS", C.c_int32), ("WS", C.c_int32), ("istage_bytes", C.c_int32), ("wstage_bytes", C.c_int32),
         ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("src_planes", C.c_int32),
+        ("ep_split", C.c_int32), ("ep_slope_b", C.c_float),
     ]
 
 

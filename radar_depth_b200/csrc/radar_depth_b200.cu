@@ -205,7 +205,9 @@ int rd_conv_fprop(const rd_conv_params* p, void* stream) {
     }
     RD_REQUIRE(covered == p->ntaps, "tap groups must cover all taps");
     RD_REQUIRE(p->wstage_bytes >= max_grp * parts * p->N * 32 && p->wstage_bytes % 128 == 0, "wstage_bytes too small / misaligned");
-    RD_REQUIRE(p->epi == 0 || (p->epi == 1 && p->zsrc.ptr && p->ep_scale && p->ep_shift), "epi 1 needs zsrc / scale / shift");
+    RD_REQUIRE(p->epi == 0 || (p->epi == 1 && p->zsrc.ptr && p->ep_scale && p->ep_shift) ||
+               (p->epi == 2 && p->ep_scale && p->ep_shift && p->ep_split % 16 == 0 && p->stats == nullptr),
+               "epi 1 needs zsrc / scale / shift; epi 2 needs scale / shift, a 16-aligned split and no statistics");
     RD_REQUIRE(p->stats == nullptr || p->stats_stride >= p->nblk * p->N, "stats_stride too small");
     RD_REQUIRE(p->tail.counter == nullptr || p->stats != nullptr, "a fused BatchNorm finalisation needs the statistics epilogue");
     { const char* e = check_tail(p->tail); if (e) return fail(RD_EINVAL, e); }

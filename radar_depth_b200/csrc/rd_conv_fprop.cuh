@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     if (p.ld_scale) {
         for (int i = tid; i < p.Cin; i += kFpropThreads) { ld_sc[i] = p.ld_scale[i]; ld_sh[i] = p.ld_shift[i]; }
     }
-    if (p.epi == 1) {
+    if (p.epi != 0) {
         for (int i = tid; i < p.N; i += kFpropThreads) { ep_sc[i] = p.ep_scale[nb * p.N + i]; ep_sh[i] = p.ep_shift[nb * p.N + i]; }
     }
     tc_fence_before();
@@ -474,6 +474,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                         if (valid && !(p.dbg_flags & 4)) {
                             const size_t pix = ((size_t)img * p.dstH + fy) * p.dstW + fx;
                             const int ch = nb * p.N + cc * 16;
+                            if (p.epi == 2) {        // inference: the following BatchNorm is a fixed affine map
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], ep_sc[cc * 16 + i], ep_sh[cc * 16 + i]);
+                            }
                             if (addend) {
                                 float a[16];
                                 const T* ap = addend + pix * p.addend.pitch + p.addend.coff + ch;
@@ -481,6 +485,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] += a[i];
                             }
+                            if (p.epi == 2) {
+                                const float sl = ch < p.ep_split ? p.ep_slope : p.ep_slope_b;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+                            } else
                             if (p.epi == 1) {
                                 float z[16];
                                 const T* zp = zsrc + pix * p.zsrc.pitch + p.zsrc.coff + ch;

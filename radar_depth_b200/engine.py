@@ -281,7 +281,7 @@ class LatefusionEngine:
         self._pending = []                 # launches whose weight / dw pointers are patched after arenas exist
 
         def emit_conv(prog, rec, which, src: View, dst: View, ld=None, epi=0, addend=None, zsrc=None, ep=None,
-                      stats=None, tag="", tail=None):
+                      stats=None, tag="", tail=None, ep_split=None, ep_slope_b=0.0):
             plan = rec["fplan"] if which == "f" else rec["dplan"]
             p = type(plan.params).from_buffer_copy(plan.params)
             p.src, p.dst = src, dst
@@ -294,6 +294,8 @@ class LatefusionEngine:
             p.zsrc = zsrc if zsrc is not None else NULLV
             if ep is not None:
                 p.ep_scale, p.ep_shift, p.ep_slope = _p(ep[0]), _p(ep[1]), float(ep[2])
+            p.ep_split = int(ep_split) if ep_split is not None else (1 << 30)
+            p.ep_slope_b = float(ep_slope_b)
             if stats is not None:
                 p.stats, p.stats_stride = _p(stats), stats.shape[1]
             if tail is not None:
@@ -566,6 +568,56 @@ class LatefusionEngine:
         both(Launch("bilinear", lib.rd_bilinear_fwd, (_p(c3map), B, Hd, Wd, _p(self.pred), OH, OW),
                     dict(bytes=(c3map.numel() + self.pred.numel()) * 4)))
 
+        # ============================== inference program (model.eval() + torch.no_grad(), main.py:584-595) ==============
+        # with running statistics every BatchNorm is a fixed per-channel affine map, so it moves into the
+        # epilogue of the convolution that feeds it (rd_conv_params.epi = 2) together with the residual add and the
+        # activation: every conv then reads a MATERIALISED activation through the raw-TMA path (two epilogue groups, no
+        # in-place transform hop), and the 12 residual-join launches disappear.  Same buffers as the training program.
+        # (The collapse of conv_fusion o bn_fusion o conv2 o bn2 into one 640->256 1x1 needs a 256x512 @ 512x640 product of
+        # the WEIGHTS before every evaluation pass; both 1x1s together take ~50 us at 11x38, so it is not done.)
+        self.fwd_infer_body: Optional[List[Launch]] = None
+        if upproj:
+            fi: List[Launch] = [self.fwd[0]]                                  # input_pack
+            ones = self.hold(torch.ones(Cst, dtype=torch.float32, device=self.device))
+            zeros = self.hold(torch.zeros(Cst, dtype=torch.float32, device=self.device))
+            emit_conv(fi, stem, "f", _v(xs), _v(z_stem), epi=2, ep=(g_stem.scale, g_stem.shift, 0.0), ep_split=64, ep_slope_b=0.2,
+                      tag="(infer)")
+            fi.append(Launch("maxpool", lib.rd_maxpool_fwd,
+                             (_v(z_stem), _p(ones), _p(zeros), B, H2, W2, Cst, 64, 1.0, 1.0, _v(p_rgb),
+                              NULLV if single else _v(p_d), _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + pool_out + amax.numel())))
+            enc0 = len(fi)
+            for blks in blocks_all:
+                for Bk in blks:
+                    b1, b2, bd = Bk["b1"], Bk["b2"], Bk["bd"]
+                    x_v = _v(Bk["x_in"])
+                    emit_conv(fi, Bk["c1"], "f", x_v, _v(Bk["z1"]), epi=2, ep=(b1.scale, b1.shift, 0.0), tag="(infer)")
+                    if bd is not None:
+                        emit_conv(fi, Bk["ds"], "f", x_v, _v(Bk["zd"]), epi=2, ep=(bd.scale, bd.shift, 1.0), tag="(infer)")
+                        idv = _v(Bk["zd"])
+                    else:
+                        idv = x_v
+                    emit_conv(fi, Bk["c2"], "f", _v(Bk["z1"]), Bk["out_v"], epi=2, ep=(b2.scale, b2.shift, 0.0), addend=idv,
+                              tag="(infer)")
+            if single:
+                emit_conv(fi, cc2, "f", _v(concat), _v(zc2), epi=2, ep=(bc2.scale, bc2.shift, 1.0), tag="(infer)")
+            else:
+                emit_conv(fi, cf, "f", _v(concat), _v(zf), epi=2, ep=(bf.scale, bf.shift, 1.0), tag="(infer)")
+                if par:                    # two-lane encoder: the depth chain (lane 1, set by emit_conv) forks after the
+                    fi[enc0].sync = "fork"  # max-pool and joins before the fusion convolution, as in the training program
+                    fi[-1].sync = "join"
+                emit_conv(fi, cc2, "f", _v(zf), _v(zc2), epi=2, ep=(bc2.scale, bc2.shift, 1.0), tag="(infer)")
+            self._infer_split = len(fi)                                     # graph cut of pnp_forward_front / rear
+            x_t = zc2
+            for L in dec:
+                co_, gcat_, bu2_ = L["co"], L["gcat"], L["bu2"]
+                emit_conv(fi, L["up"], "f", _v(x_t), _v(L["zcat"]), epi=2, ep=(gcat_.scale, gcat_.shift, 0.0), ep_split=co_,
+                          ep_slope_b=1.0, tag="(infer)")
+                emit_conv(fi, L["c3"], "f", _v(L["zcat"], 0), _v(L["out"]), epi=2, ep=(bu2_.scale, bu2_.shift, 0.0),
+                          addend=_v(L["zcat"], co_), tag="(infer)")
+                x_t = L["out"]
+            fi += self.fwd[-2:]                                               # head_conv, bilinear
+            self.fwd_infer_body = fi
+
         # ============================== backward program ==============================
         bw = self.bwd
         self.dpred = torch.zeros(B, 1, OH, OW, dtype=torch.float32, device=self.device)
@@ -751,6 +803,8 @@ class LatefusionEngine:
         self.bn_eval_table = self.hold(torch.tensor(self._bn_eval_rows, dtype=torch.int64, device=self.device))
         self.fwd_eval.insert(1, Launch("bn_fin_eval_all", lib.rd_bn_finalize_eval_multi,
                                        (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
+        # inference program: same two head launches; decoders without the folded program fall back to the eval program
+        self.fwd_infer = (self.fwd_eval[:2] + self.fwd_infer_body) if self.fwd_infer_body is not None else self.fwd_eval
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams),
                          dict(bytes=self.nparams * (4 + 4 + 8))))
         self._grad_buckets(cut_enc, cut_l4, single)
@@ -763,6 +817,12 @@ class LatefusionEngine:
         self.front_eval = self.fwd_eval[:split_fe + 2] + [exp]
         self.rear = [pack, imp] + self.fwd[split_f + 1:]
         self.rear_eval = self.fwd_eval[:2] + [imp] + self.fwd_eval[split_fe + 2:]
+        # the same cut in the inference program (bn2 is already applied by conv2's epilogue: export without the affine map)
+        self.front_infer = self.rear_infer = None
+        if self.fwd_infer_body is not None:
+            exp_raw = Launch("feature_export(infer)", lib.rd_feature_export, (_v(zc2), None, None, _p(self.bneck), B, h32, w32, 256, act))
+            self.front_infer = self.fwd_eval[:2] + self.fwd_infer_body[:self._infer_split] + [exp_raw]
+            self.rear_infer = self.fwd_eval[:2] + [imp] + self.fwd_infer_body[self._infer_split:]
         self.rear_bwd = bw[:split_b] + [Launch("feature_export(grad)", lib.rd_feature_export,
                                                (_v(g_c2), None, None, _p(self.d_bneck), B, h32, w32, 256, act))]
         self.bc2 = bc2
@@ -839,14 +899,22 @@ class LatefusionEngine:
                 ev.record(side)
                 main.wait_event(ev)
 
-    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, training: bool, inference: bool = False) -> torch.Tensor:
+        """inference = the pass will never be differentiated (torch.no_grad()): in eval mode it then runs the program with
+        BatchNorm, residual add and activation folded into the conv epilogues, which overwrites the raw conv outputs the
+        backward program would need."""
         B, Cc, H, W = x.shape
         assert Cc == self.in_channels, (Cc, self.in_channels)
         if not self.params_adopted():
             self.adopt(x.device)
         self.configure(B, H, W)
         self.x_in.copy_(x)
-        self._replay("fwd" if training else "fwd_eval", lambda: self._fwd_body(training))
+        if training:
+            self._replay("fwd", lambda: self._fwd_body(True))
+        elif self._fold(training, inference):
+            self._replay("fwd_infer", lambda: self._run(self.fwd_infer))
+        else:
+            self._replay("fwd_eval", lambda: self._fwd_body(False))
         return self.pred
 
     def _fwd_body(self, training: bool):
@@ -879,7 +947,10 @@ class LatefusionEngine:
     # ------------------------------------------------------------------ graph cut at the bottleneck (models.py:669-707)
     # PnP-Depth refinement runs the front once, then iterates the rear (forward + gradient w.r.t. the bottleneck feature).
     # These run eagerly (no CUDA graph): they are API surface, main.py never calls them.
-    def forward_front(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+    def _fold(self, training: bool, inference: bool) -> bool:
+        return (not training) and inference and self.fwd_infer_body is not None and os.environ.get("RD_INFER_FOLD", "1") != "0"
+
+    def forward_front(self, x: torch.Tensor, training: bool, inference: bool = False) -> torch.Tensor:
         B, Cc, H, W = x.shape
         assert Cc == self.in_channels, (Cc, self.in_channels)
         if not self.params_adopted():
@@ -888,10 +959,13 @@ class LatefusionEngine:
         self.x_in.copy_(x)
         if training:
             self.stats_used.zero_()
-        self._run(self.front if training else self.front_eval)
+        if self._fold(training, inference):
+            self._run(self.front_infer)
+        else:
+            self._run(self.front if training else self.front_eval)
         return self.bneck
 
-    def forward_rear(self, feat: torch.Tensor, training: bool, image_hw=None) -> torch.Tensor:
+    def forward_rear(self, feat: torch.Tensor, training: bool, image_hw=None, inference: bool = False) -> torch.Tensor:
         B, Cc, h, w = feat.shape
         if Cc != 256:
             raise _lib.RdError(f"pnp_forward_rear expects the 256-channel bn2 output, got {Cc} channels")
@@ -904,6 +978,9 @@ class LatefusionEngine:
                 raise _lib.RdError(f"pnp_forward_rear: a {h}x{w} feature does not belong to a {H}x{W} image "
                                    f"(expected {self.cfg['h32']}x{self.cfg['w32']})")
         self.bneck.copy_(feat)
+        if self._fold(training, inference):
+            self._run(self.rear_infer)         # the decoder's first conv reads the imported feature as it is
+            return self.pred
         if training:
             self.stats_used.zero_()
         prog = self.rear if training else self.rear_eval

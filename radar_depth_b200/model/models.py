@@ -322,7 +322,7 @@ class ResNet_latefusion(nn.Module):
             return _LatefusionFn.apply(x, self._anchor, self)
         eng = self._get_engine()
         self._fwd_serial += 1                        # the saved activations of an earlier grad-enabled forward are gone:
-        return eng.forward(x, self.training).clone()  # its backward() must raise, not differentiate the wrong pass
+        return eng.forward(x, self.training, inference=True).clone()  # its backward() must raise, not differentiate the wrong pass
 
     # API surface of models.py:669-707 (PnP-Depth refinement); main.py never calls them.  front = encoder
     # + fusion 1x1s up to bn2's output, rear = decoder + head + bilinear.  rear(front(x)) == forward(x).  The usual PnP
@@ -333,7 +333,8 @@ class ResNet_latefusion(nn.Module):
         if not x.is_cuda:
             raise _lib.RdError("radar_depth_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
         self._fwd_serial += 1                        # the activations of an earlier forward() are overwritten
-        return self._get_engine().forward_front(x.float().contiguous(), self.training).clone()
+        return self._get_engine().forward_front(x.float().contiguous(), self.training,
+                                                inference=not torch.is_grad_enabled()).clone()
 
     def pnp_forward_rear(self, x):
         if not x.is_cuda:
@@ -341,7 +342,8 @@ class ResNet_latefusion(nn.Module):
         if torch.is_grad_enabled() and x.requires_grad:
             return _RearFn.apply(x, self)
         self._fwd_serial += 1
-        return self._get_engine().forward_rear(x.detach().float().contiguous(), self.training, self._image_hw()).clone()
+        return self._get_engine().forward_rear(x.detach().float().contiguous(), self.training, self._image_hw(),
+                                               inference=not torch.is_grad_enabled()).clone()
 
     def _image_hw(self):
         eng = self._engine

@@ -311,3 +311,48 @@ def test_segmented_backward_equals_the_single_program(precision, b):
     assert covered[0][0] == 0 and all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
     for k, g in grads[0].items():
         assert torch.equal(g, grads[1][k]), k
+
+
+def test_inference_program_equals_the_eval_program():
+    """under model.eval() + torch.no_grad() the engine runs the program with BatchNorm, residual add and
+    activation folded into the conv epilogues (rd_conv_params.epi = 2, no join launches); it must agree with the eval
+    program that keeps the raw conv outputs for a possible backward (same arithmetic up to the rounding of one fused
+    multiply-add per element) and with the real reference's golden output."""
+    g = np.load(os.path.join(GOLDEN, "latefusion_eval_b1_64x96.npz"))
+    m, _ = _build(4, (64, 96), "fp32", training=False)
+    inputs, _ = _inputs(1, 64, 96, 4)
+    x = inputs.cuda()
+    eng = m._get_engine()
+    with torch.no_grad():
+        a = m(x).clone()                                            # folded program
+        b = eng.forward(x, False, inference=False).clone()          # eval program (raw z kept)
+        a2 = m(x).clone()                                           # graph replay of the folded program
+    assert len(eng.fwd_infer) < len(eng.fwd_eval) - 10              # the 12 join launches are gone
+    assert not any(L.name.startswith("join") for L in eng.fwd_infer)
+    assert _rel(a, b) < 2e-5
+    assert torch.equal(a, a2)
+    assert _rel(a, torch.from_numpy(g["pred"])) < 1e-3
+    # an eval-mode forward WITH grad still differentiates (it uses the eval program, whose buffers the backward reads)
+    m.zero_grad(set_to_none=True)
+    pred = m(x)
+    pred.sum().backward()
+    assert m.conv3.weight.grad is not None and torch.isfinite(m.conv3.weight.grad).all()
+
+
+def test_inference_program_bf16_full_size_is_as_close_to_fp32_as_the_eval_program():
+    """bf16 throughput mode at 352x1216, b=1 (what validate() runs): the folded program rounds to bf16 once per layer less
+    than the eval program; both are measured against the fp32-mode result of the same weights."""
+    inputs, _ = _inputs(1, 352, 1216, 4)
+    x = inputs.cuda()
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        m, _ = _build(4, (352, 1216), precision, training=False)
+        eng = m._get_engine()
+        with torch.no_grad():
+            outs[precision, "fold"] = m(x).clone()
+            outs[precision, "eval"] = eng.forward(x, False, inference=False).clone()
+    ref = outs["fp32", "eval"]
+    e_fold, e_eval = _rel(outs["bf16", "fold"], ref), _rel(outs["bf16", "eval"], ref)
+    print(f"[bf16 inference vs fp32 mode, 352x1216 b=1] folded {e_fold:.3e}  eval program {e_eval:.3e}")
+    assert _rel(outs["fp32", "fold"], ref) < 2e-5
+    assert e_eval < 0.2 and e_fold < 0.2 and e_fold < 1.5 * e_eval + 1e-3

@@ -24,4 +24,4 @@ with torch.no_grad():
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 eng = m._engine
-print(f"eval b={b} {H}x{W} bf16: {ms:.3f} ms/forward = {b / ms * 1e3:.1f} images/s, {len(eng.fwd_eval)} launches per forward")
+print(f"eval b={b} {H}x{W} bf16: {ms:.3f} ms/forward = {b / ms * 1e3:.1f} images/s, {len(eng.fwd_eval)} launches per forward in the eval program, {len(eng.fwd_infer)} in the inference program (RD_INFER_FOLD)")
