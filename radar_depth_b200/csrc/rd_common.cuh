@@ -353,4 +353,64 @@ template <> struct Act<float> {
     static __device__ __forceinline__ float round(float v) { return v; }
 };
 
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100): 16 bf16 channels of one pixel in ONE request per lane.  The conv
+// epilogue's lanes each own a different pixel (= a different 128-byte line), so every per-lane request is its own L1
+// wavefront on the data path the tensor core's shared-memory operand fetch also uses; two 128-bit halves were two.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 16 consecutive channels; `wide` = the address is 32-byte aligned (checked once per launch by the caller)
+__device__ __forceinline__ void load16(const bf16* p, float* v, bool wide) {
+    if (wide) {
+        uint32_t r[8];
+        ldg256(p, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] = bf16lo(r[i]); v[2 * i + 1] = bf16hi(r[i]); }
+    } else {
+        Act<bf16>::load8(p, v); Act<bf16>::load8(p + 8, v + 8);
+    }
+}
+__device__ __forceinline__ void store16(bf16* p, const float* v, bool wide) {
+    if (wide) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        stg256(p, r);
+    } else {
+        Act<bf16>::store8(p, v); Act<bf16>::store8(p + 8, v + 8);
+    }
+}
+__device__ __forceinline__ void load16(const float* p, float* v, bool wide) {
+    if (wide) {
+        uint32_t r[8];
+        ldg256(p, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+        ldg256(p + 8, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 + i] = __uint_as_float(r[i]);
+    } else {
+        Act<float>::load8(p, v); Act<float>::load8(p + 8, v + 8);
+    }
+}
+__device__ __forceinline__ void store16(float* p, const float* v, bool wide) {
+    if (wide) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+        stg256(p, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[8 + i]);
+        stg256(p + 8, r);
+    } else {
+        Act<float>::store8(p, v); Act<float>::store8(p + 8, v + 8);
+    }
+}
+
+
 }  // namespace rd

@@ -100,7 +100,7 @@ __device__ __forceinline__ void umma_bf16_elected(uint32_t tmem_d, uint64_t desc
         : "memory");
 }
 
-template <int SPLIT, int MBT>
+template <int SPLIT, int MBT, int NT>
 __device__ __forceinline__ void fprop_issue(const rd_conv_params& p, uint8_t* smem, uint32_t tmem_base, bool dbuf, int acc_cols,
                                             int ntiles, int ncblk, int lane, long long t_entry, bool tl_mode) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -142,6 +142,33 @@ __device__ __forceinline__ void fprop_issue(const rd_conv_params& p, uint8_t* sm
                 const uint64_t da0 = make_smem_desc(smem_u32(a_ring + (size_t)si.stage * p.istage_bytes), PS * 16u, 128);
                 const uint32_t keep = c == 0 ? 0u : 1u;                  // channel blocks after the first always accumulate
                 int t = 0;
+                if (NT > 0) {
+                    // NT taps, one weight group, one output phase (every 3x3 / 1x1 forward conv and stride-1 data gradient with
+                    // N <= 128): straight-line code, the tap shifts are immediate-offset reads of the parameter bank
+                    const long long t2_ = p.dbg ? clock64() : 0;
+                    mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
+                    if (p.dbg) tw_ += clock64() - t2_;
+                    tc_fence_after();
+                    const uint64_t db0 = make_smem_desc(smem_u32(w_ring + (size_t)sw.stage * p.wstage_bytes), N * 16u, 128);
+                    if (do_issue) {
+#pragma unroll
+                        for (int tt = 0; tt < NT; ++tt) {
+                            const uint64_t da = da0 + (uint32_t)p.taps[tt].a_shift;
+                            const uint64_t db = db0 + (uint32_t)tt * tap_units;
+                            const uint32_t acc = tt == 0 ? keep : 1u;
+#pragma unroll
+                            for (int mb = 0; mb < MBT; ++mb) {
+                                umma_bf16_elected(d_tile + (uint32_t)mb * N, da + (uint32_t)mb * 128u, db, idesc, acc);
+                                if (SPLIT == 3) {
+                                    umma_bf16_elected(d_tile + (uint32_t)mb * N, da + (uint32_t)mb * 128u, db + 2u * N, idesc, 1u);
+                                    umma_bf16_elected(d_tile + (uint32_t)mb * N, da + (uint32_t)mb * 128u + 2u * PS, db, idesc, 1u);
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(&w_empty[sw.stage]);
+                    sw.advance();
+                } else
                 for (int g = 0; g < p.ngroups; ++g) {
                     const long long t2_ = p.dbg ? clock64() : 0;
                     mbar_wait(&w_full[sw.stage], sw.phase, 0x320 + sw.stage);
@@ -420,12 +447,25 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         __syncwarp();
     } else if (warp == kWarpMma) {
         // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
-        switch (p.MB) {
-            case 1: fprop_issue<SPLIT, 1>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
-            case 2: fprop_issue<SPLIT, 2>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
-            case 3: fprop_issue<SPLIT, 3>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
-            case 4: fprop_issue<SPLIT, 4>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
-            default: fprop_issue<SPLIT, 0>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode); break;
+        {
+            // straight-line tap loops for the two common programs (first tap of phase 0 clears, one weight group)
+            const bool simple = p.P == 1 && p.ngroups == 1 && p.MB <= 4 && p.taps[0].first == 1;
+            const int nt = simple ? (p.ntaps == 9 ? 9 : (p.ntaps == 1 ? 1 : 0)) : 0;
+#define RD_ISSUE(MBV, NTV) fprop_issue<SPLIT, MBV, NTV>(p, smem, tmem_base, dbuf, acc_cols, ntiles, ncblk, lane, t_entry, tl_mode)
+            if (nt == 9) {
+                switch (p.MB) { case 1: RD_ISSUE(1, 9); break; case 2: RD_ISSUE(2, 9); break; case 3: RD_ISSUE(3, 9); break; default: RD_ISSUE(4, 9); break; }
+            } else if (nt == 1) {
+                switch (p.MB) { case 1: RD_ISSUE(1, 1); break; case 2: RD_ISSUE(2, 1); break; case 3: RD_ISSUE(3, 1); break; default: RD_ISSUE(4, 1); break; }
+            } else {
+                switch (p.MB) {
+                    case 1: RD_ISSUE(1, 0); break;
+                    case 2: RD_ISSUE(2, 0); break;
+                    case 3: RD_ISSUE(3, 0); break;
+                    case 4: RD_ISSUE(4, 0); break;
+                    default: RD_ISSUE(0, 0); break;
+                }
+            }
+#undef RD_ISSUE
         }
         __syncwarp();
     } else {
@@ -436,6 +476,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
         const bool want_stats = p.stats != nullptr;
         const FastDivS fd_wl((uint32_t)p.Wl);
+        // 16 channels of a pixel move as one 256-bit request when every address of the view is 32-byte aligned
+        const int al = 32 / (int)sizeof(T);
+        auto wide_ok = [&](const rd_view& v) { return v.ptr == nullptr || ((((uintptr_t)v.ptr) & 31) == 0 && v.pitch % al == 0 && v.coff % al == 0); };
+        const bool wide = wide_ok(p.dst) && wide_ok(p.addend) && wide_ok(p.zsrc) && !(p.dbg_flags & 32);
         float* det_mine = det_part ? det_s + (size_t)(eg * 4 + wq) * 2 * p.N : nullptr;
         if (det_mine) {
             for (int i = lane; i < 2 * p.N; i += 32) det_mine[i] = 0.f;
@@ -481,7 +525,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                             if (addend) {
                                 float a[16];
                                 const T* ap = addend + pix * p.addend.pitch + p.addend.coff + ch;
-                                Act<T>::load8(ap, a); Act<T>::load8(ap + 8, a + 8);
+                                load16(ap, a, wide);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] += a[i];
                             }
@@ -493,7 +537,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                             if (p.epi == 1) {
                                 float z[16];
                                 const T* zp = zsrc + pix * p.zsrc.pitch + p.zsrc.coff + ch;
-                                Act<T>::load8(zp, z); Act<T>::load8(zp + 8, z + 8);
+                                load16(zp, z, wide);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
                                     const float y = fmaf(z[i], ep_sc[cc * 16 + i], ep_sh[cc * 16 + i]);
@@ -507,7 +551,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                                 for (int i = 0; i < 16; ++i) { s1[i] += v[i]; s2[i] += v[i] * v[i]; }
                             }
                             T* dp = dst + pix * p.dst.pitch + p.dst.coff + ch;
-                            Act<T>::store8(dp, v); Act<T>::store8(dp + 8, v + 8);
+                            store16(dp, v, wide);
                         }
                     }
                 }
