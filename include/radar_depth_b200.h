@@ -218,6 +218,19 @@ typedef struct rd_wgrad_params {
      * per 16 pixels instead of ntaps UMMAs of N=16 -- small-N UMMAs cost ~40 cycles whatever N is.  0 = off. */
     int32_t fold_rows, fold_len;
     int32_t pad2_;
+    /* Gradient copies stacked in M (stride-1 convs with Cout <= 64, gradient tile staged by TMA): the M = 128 operand of the
+     * UMMA spans 16 chunk planes of which a Cout-channel gradient tile fills only Cout/8, so `gcopies` copies of the tile,
+     * copy r shifted by (gcopy_dy[r], gcopy_dx[r]) pixels (a second TMA box at shifted coordinates), are laid side by side:
+     * rows [r*Mc, (r+1)*Mc) of accumulator j then hold the tap whose source shift is taps[j].x_shift MINUS copy r's shift.
+     * One UMMA covers up to 128/Mc taps: 9 -> 6 accumulators (one pass instead of two) for 64-channel layers, 9 -> 3 (or, with
+     * tap-row folding, 6 -> 2) for 16/32-channel layers.  The pixel-tile grid starts at (-tile_oy, -tile_ox) so that every
+     * gradient pixel meets every copy exactly once.  njobs accumulators (taps[0..njobs) are their descriptors); job_tap[j][r]
+     * = index into dw of the tap produced by copy r of job j (with tap-row folding: of the first tap of its row), -1 = unused.
+     * gcopies <= 1: off (one accumulator per tap, as above). */
+    int32_t gcopies, njobs;
+    int32_t gcopy_dy[8], gcopy_dx[8];
+    int32_t tile_oy, tile_ox;
+    int8_t job_tap[RD_MAX_TAPS][8];
 } rd_wgrad_params;
 
 int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);

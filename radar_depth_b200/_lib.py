@@ -84,6 +84,8 @@ class WgradParams(C.Structure):
         ("dw", C.c_void_p), ("NS", C.c_int32), ("stage_bytes", C.c_int32), ("g_bytes", C.c_int32),
         ("act_dtype", C.c_int32), ("max_ctas", C.c_int32), ("dbg", C.c_void_p), ("dbg_flags", C.c_int32), ("x_planes", C.c_int32),
         ("fold_rows", C.c_int32), ("fold_len", C.c_int32), ("pad2_", C.c_int32),
+        ("gcopies", C.c_int32), ("njobs", C.c_int32), ("gcopy_dy", C.c_int32 * 8), ("gcopy_dx", C.c_int32 * 8),
+        ("tile_oy", C.c_int32), ("tile_ox", C.c_int32), ("job_tap", (C.c_int8 * 8) * RD_MAX_TAPS),
     ]
 
 

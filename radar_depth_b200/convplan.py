@@ -452,8 +452,9 @@ class WgradPlan:
     info: dict = field(default_factory=dict)
 
 
-def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks_target):
-    """KS slots per plane / tile shape minimising the modelled cycles subject to >= 2 ring stages in shared memory."""
+def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks_target, R=1, tile_oy=0):
+    """KS slots per plane / tile shape minimising the modelled cycles subject to >= 2 ring stages in shared memory.
+    ntaps = number of accumulators (jobs when the gradient tile is staged R times, see plan_wgrad)."""
     tg_cap = max(1, min(16, 512 // Nc))
     ntg = -(-ntaps // tg_cap)
     tg_size = -(-ntaps // ntg)
@@ -469,19 +470,21 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
             # A tile of exactly KS = Ht*Wl slots lets the gradient tile be one dense TMA box (rd_conv_wgrad: TMA writes the
             # chunk planes of a box back to back, so a plane must not have a tail); such tiles are preferred.
             tma_g = parts == 1 and (Ht * Wl) % 16 == 0 and Wl * g.OS <= 256
+            if R > 1 and not tma_g:
+                continue                                   # gradient copies are TMA boxes
             KS = Ht * Wl if tma_g else KS0
             xrows = Ht + halo_y
             xslots = _round_up(KS + halo_y * Wl + halo_x + (4 if g.Cx == 16 else 0), 8)     # + the junk 4th tap of a folded row
             GPS = _chunk_stride(g.OS * g.OS * KS, Mc // 8)
             XPS = _chunk_stride(g.S * g.S * xslots, Nc // 8)
-            g_bytes = _round_up(parts * (Mc // 8) * GPS * 16, 128)
+            g_bytes = _round_up(parts * R * (Mc // 8) * GPS * 16, 128)
             stage = _round_up(g_bytes + parts * (Nc // 8) * XPS * 16, 128)
             # the M=128 operand always spans 16 chunk planes; rows past Mc are junk but must stay inside smem
             pad = max(0, ((parts - 1) * (Mc // 8) + 16) * GPS * 16 - stage)
             if WGRAD_HEADER + 2 * stage + pad > SMEM_BUDGET:
                 continue
-            ty, tx = -(-Hb // Ht), -(-Wb // Wt)
-            load = (Mc // 8) * GPS + (Nc // 8) * XPS
+            ty, tx = -(-(Hb + tile_oy) // Ht), -(-Wb // Wt)
+            load = R * (Mc // 8) * GPS + (Nc // 8) * XPS
             mma = (KS // 16) * tg_size * max(Nc, 32) / 2.0 * (3 if parts == 2 else 1)
             cost = ty * tx * (max(mma, load * 0.35 * parts * (0.6 if tma_g else 1.0)) + 300.0)
             if best is None or cost < best[0]:
@@ -490,14 +493,35 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
     return best
 
 
+def _gcopy_layout(g: GConv, taps, Mc: int, parts: int):
+    """Gradient copies stacked in M (rd_wgrad_params.gcopies): (R, tap rows, tap columns) for stride-1 convolutions with
+    Cout <= 64 whose taps form a full rows x columns grid, else None."""
+    if parts != 1 or g.S != 1 or g.OS != 1 or Mc > 64 or os.environ.get("RD_TMA", "1") == "0" or \
+            os.environ.get("RD_WGRAD_GCOPY", "1") == "0":
+        return None
+    rows = sorted({t.s[0] for t in taps})
+    cols = sorted({t.s[1] for t in taps})
+    if len(rows) < 2 or len(rows) * len(cols) != len(taps) or [t.s for t in taps] != [(r, c) for r in rows for c in cols]:
+        return None
+    if rows != list(range(rows[0], rows[0] + len(rows))) or cols != list(range(cols[0], cols[0] + len(cols))):
+        return None
+    R = min(128 // Mc, len(rows), 8)
+    return (R, rows, cols) if R >= 2 else None
+
+
 def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
-               nc: Optional[int] = None, use_tuned: bool = True, sm_budget: int = NUM_SMS) -> WgradPlan:
-    """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient."""
+               nc: Optional[int] = None, use_tuned: bool = True, sm_budget: int = NUM_SMS, gcopy: Optional[bool] = None) -> WgradPlan:
+    """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient.
+    gcopy: stack shifted copies of the gradient tile in M where the layer allows it (None: measured table, else on)."""
     assert g.Cx % 16 == 0 and g.N % 8 == 0
     if use_tuned and nc is None:
         t = tuned_table().get(tune_key("w", g, B, x_hw, g_hw, act_dtype))
         if t:
             nc, ks_target = t["nc"], t["ks"]
+            if gcopy is None and "gc" in t:
+                gcopy = bool(t["gc"])
+    if gcopy is None:
+        gcopy = True
     parts = 2 if act_dtype == _lib.RD_F32 else 1
     taps, phases = g.sorted_taps()
     ntaps = len(taps)
@@ -509,10 +533,25 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     halo_y, halo_x = max(sy) - sy_min, max(sx) - sx_min
     Mc = min(_round_up(g.N, 8), 128)
     ncob = -(-g.N // Mc)
+    # ---- gradient copies: jobs instead of taps
+    gl = _gcopy_layout(g, taps, Mc, parts) if gcopy else None
+    R, tile_oy = 1, 0
+    jobs = None                                       # [(sy of copy 0, sx or None when the row is N-folded)]
+    fold_n = False
+    if gl is not None:
+        R, rows, cols = gl
+        tile_oy = R - 1
+        job_rows = [rows[-1] - m * R for m in range(-(-len(rows) // R))]
+        fold_n = g.Cx == 16 and (nc in (None, 16)) and 2 <= len(cols) <= 4 and len(job_rows) * 64 <= 512 and \
+            os.environ.get("RD_WGRAD_FOLD", "1") != "0"
+        jobs = [(sy_, None) for sy_ in job_rows] if fold_n else [(sy_, sx_) for sy_ in job_rows for sx_ in cols]
+        if fold_n:
+            nc = 16
+    nacc = len(jobs) if jobs is not None else ntaps
     if nc is None:
         # prefer ONE tap group per CTA (the gradient and source tiles are then staged once per pixel tile instead
         # of once per tap group): the widest Nc (multiple of 16 dividing Cx) with ntaps*Nc <= 512 TMEM columns
-        tpc = min(ntaps, 16)
+        tpc = min(nacc, 16)
         nc = 16
         for cand in range(16, min(g.Cx, 256) + 1, 16):
             if g.Cx % cand == 0 and tpc * cand <= 512:
@@ -520,15 +559,19 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     nc_candidates = [nc] + [c for c in (128, 64, 32, 16) if c < nc and g.Cx % c == 0]
     best = None
     for Nc in nc_candidates:
-        best = _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks_target)
+        best = _search_wgrad_tile(g, Nc, Mc, ncob, nacc, parts, Hb, Wb, halo_y, halo_x, ks_target, R, tile_oy)
         if best is not None:
             break
+    if best is None and R > 1:
+        return plan_wgrad(g, B, x_hw, g_hw, act_dtype, ks_target, nc, use_tuned, sm_budget, gcopy=False)
     if best is None:
         raise ValueError("no feasible wgrad tile")
     ncib = g.Cx // Nc
     tg_cap = max(1, min(16, 512 // Nc))
-    ntg = -(-ntaps // tg_cap)
-    tg_size = -(-ntaps // ntg)
+    if fold_n:
+        tg_cap = 16                                   # folded jobs own 64 columns each (checked above)
+    ntg = -(-nacc // tg_cap)
+    tg_size = -(-nacc // ntg)
     geo = best[1]
     NS = 2
     while NS < 4 and WGRAD_HEADER + (NS + 1) * geo["stage"] + geo["pad"] <= SMEM_BUDGET:
@@ -549,13 +592,30 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
         p.taps[i].g_off = (t.ph[0] * g.OS + t.ph[1]) * geo["KS"]
         q = t.pl[0] * g.S + t.pl[1]
         p.taps[i].x_shift = q * geo["xslots"] + (t.s[0] - sy_min) * geo["Wl"] + (t.s[1] - sx_min)
+    p.gcopies, p.njobs, p.tile_oy, p.tile_ox = (R if jobs is not None else 0), (nacc if jobs is not None else 0), tile_oy, 0
+    if jobs is not None:
+        ncols = len(cols)
+        for r in range(R):
+            p.gcopy_dy[r], p.gcopy_dx[r] = r, 0
+        for j, (sy_, sx_) in enumerate(jobs):
+            # copy r of the gradient tile holds g[p + (r, 0)]: against the source at shift (sy_, sx_) it produces tap (sy_ - r, sx_)
+            p.taps[j].g_off = 0
+            p.taps[j].x_shift = (sy_ - sy_min) * geo["Wl"] + ((sx_ if sx_ is not None else cols[0]) - sx_min)
+            for r in range(8):
+                ky = sy_ - r
+                ok = r < R and ky >= rows[0]
+                p.job_tap[j][r] = ((ky - rows[0]) * ncols + ((sx_ - cols[0]) if sx_ is not None else 0)) if ok else -1
     p.Mc, p.ncob, p.Nc, p.ncib = Mc, ncob, Nc, ncib
     p.NS, p.stage_bytes, p.g_bytes = NS, geo["stage"], geo["g_bytes"]
     p.act_dtype = act_dtype
     p.x_planes = 1 if (g.S == 2 and all(t.pl == (0, 0) for t in taps)) else 0
     # tap-row folding (rd_wgrad_params.fold_rows): 16-channel stride-1 sources whose taps form full rows of <= 4 adjacent taps
     p.fold_rows, p.fold_len = 0, 0
-    if parts == 1 and g.Cx == 16 and Nc == 16 and g.S == 1 and g.OS == 1 and ntg == 1 and os.environ.get("RD_WGRAD_FOLD", "1") != "0":
+    if jobs is not None:
+        if fold_n:
+            assert Nc == 16 and ntg == 1
+            p.fold_rows, p.fold_len = len(jobs), len(cols)
+    elif parts == 1 and g.Cx == 16 and Nc == 16 and g.S == 1 and g.OS == 1 and ntg == 1 and os.environ.get("RD_WGRAD_FOLD", "1") != "0":
         rows = sorted({t.s[0] for t in taps})
         cols = sorted({t.s[1] for t in taps})
         full = len(rows) * len(cols) == ntaps and cols == list(range(cols[0], cols[0] + len(cols))) and \
@@ -575,4 +635,5 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
         di.append(((ti * g.N + n) * g.Cx + c).astype(np.int64))
     scatter = (np.concatenate(pi), np.concatenate(di))
     return WgradPlan(g=g, params=p, dw_elems=ntaps * g.N * g.Cx, scatter=scatter,
-                     info=dict(geo=geo, NS=NS, Mc=Mc, Nc=Nc, tg_size=tg_size, ntg=ntg, ntiles=ntiles))
+                     info=dict(geo=geo, NS=NS, Mc=Mc, Nc=Nc, tg_size=tg_size, ntg=ntg, ntiles=ntiles, gcopies=int(p.gcopies),
+                               njobs=int(p.njobs)))

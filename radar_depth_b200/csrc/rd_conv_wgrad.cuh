@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const int cib = blockIdx.z / p.ntg;
     const int tg = blockIdx.z - cib * p.ntg;
     const int t0 = tg * p.tg_size;
-    const int T_n = min(p.tg_size, p.ntaps - t0);
+    const int R = p.gcopies > 1 ? p.gcopies : 1;               // gradient copies stacked in M (rd_wgrad_params.gcopies)
+    const int T_n = min(p.tg_size, (R > 1 ? p.njobs : p.ntaps) - t0);
     const int co0 = cob * p.Mc, ci0 = cib * p.Nc;
     const int tiles_per_img = p.tiles_y * p.tiles_x;
     const int ntiles = tiles_per_img * p.B;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-            const int y0 = ty * p.Ht, x0 = tx * p.Wt;
+            const int y0 = ty * p.Ht - p.tile_oy, x0 = tx * p.Wt - p.tile_ox;
             const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty[st.stage], st.phase ^ 1, 0x500 + st.stage);
             const long long tw1 = p.dbg ? clock64() : 0;
@@ -157,8 +158,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 if (lane == 0) {
                     uint64_t* bar = hop ? &tma_full[st.stage] : &full[st.stage];
                     if (!(p.dbg_flags & 2)) {
-                        mbar_arrive_expect_tx(bar, (g_tma ? g_tx : 0u) + (x_tma ? x_tx : 0u));
-                        if (g_tma) {
+                        mbar_arrive_expect_tx(bar, (g_tma ? g_tx * (uint32_t)R : 0u) + (x_tma ? x_tx : 0u));
+                        if (g_tma && R > 1) {
+                            for (int r = 0; r < R; ++r)              // copy r: the same box, (dy, dx) pixels further
+                                tma_load_5d(sbase + (size_t)r * g_chunks * p.KS * 16, &g_map, 0, x0 + p.gcopy_dx[r], y0 + p.gcopy_dy[r],
+                                            co0 >> 3, img, bar);
+                        } else if (g_tma) {
                             for (int q = 0; q < g_planes; ++q)       // parity plane (py, px) of a stride-2 gradient: every 2nd pixel
                                 tma_load_5d(sbase + (size_t)q * g_chunks * p.KS * 16, &g_map, 0, x0 * p.Sg + (q & (p.Sg - 1)),
                                             y0 * p.Sg + (q >> (p.Sg >> 1)), co0 >> 3, img, bar);
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             if (g_tma) {
                 // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
                 const int jc = p.Wl - p.Wt;
-                const int items = p.Ht * jc * g_chunks * g_planes;       // planes and chunk planes are all KS slots apart
+                const int items = p.Ht * jc * g_chunks * g_planes * R;   // planes, copies and chunk planes are all KS slots apart
                 const FastDivS fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
                 for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
                     const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 // tap-outer / k-group-inner: inside the inner loop the descriptors only advance by 16 slots, so one
                 // UMMA costs two uniform adds; the tap offsets come from the (uniform) parameter bank once per tap
                 for (int jb = 0; jb < njobs; ++jb) {
-                    const int tl = fold ? (jb >> 1) * p.fold_len : jb;                 // x_chunks == 2 when folding
+                    const int tl = fold ? (R > 1 ? (jb >> 1) : (jb >> 1) * p.fold_len) : jb;   // x_chunks == 2 when folding
                     const uint32_t d = tmem_u + (uint32_t)(fold ? jb * 32 : jb * p.Nc);
                     uint64_t da = da0 + (uint32_t)p.taps[t0 + tl].g_off;
                     uint64_t db = db0 + (uint32_t)p.taps[t0 + tl].x_shift + (uint32_t)(fold ? (jb & 1) * XPS : 0);
@@ -304,24 +309,28 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         mbar_wait(tmem_full, 0, 0x600);
         tc_fence_after();
         if (tl_mode && tid == 0) p.dbg[2 * dbg_ncta + dbg_cta] = clock64() - t_entry;
-        const int row = warp * 32 + lane;                 // output channel within the block
-        const bool valid = has_work && row < p.Mc && (co0 + row) < p.Cout;
+        const int arow = warp * 32 + lane;                // accumulator row: copy * Mc + output channel within the block
+        const int copy = R > 1 ? arow / p.Mc : 0;
+        const int row = arow - copy * p.Mc;
+        const bool valid = has_work && copy < R && row < p.Mc && (co0 + row) < p.Cout;
         const bool det = det_part != nullptr;
         float* const dwo = det ? det_part + (size_t)blockIdx.x * ((size_t)p.ntaps * p.Cout * p.Cin) : p.dw;
         if ((SPLIT == 1) && p.fold_len > 0) {
             // folded accumulators: job (row, chunk jx) holds columns [tap-in-row][8 channels of chunk jx]
             const int njobs = p.fold_rows * x_chunks;
             for (int jb = 0; jb < njobs; ++jb) {
-                const int rowi = jb >> 1, jx = jb & 1;
+                const int jx = jb & 1;
+                // first tap of the tap row this accumulator row belongs to (gradient copies: one job row covers several)
+                const int tap0 = R > 1 ? (copy < R ? (int)p.job_tap[jb >> 1][copy] : -1) : (jb >> 1) * p.fold_len;
                 for (int cc = 0; cc < 2; ++cc) {
                     float v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(jb * 32 + cc * 16), v);
-                    if (valid) {
+                    if (valid && tap0 >= 0) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int tx = cc * 2 + h;
                             if (tx < p.fold_len) {
-                                float* out = dwo + ((size_t)(rowi * p.fold_len + tx) * p.Cout + (co0 + row)) * p.Cin + ci0 + jx * 8;
+                                float* out = dwo + ((size_t)(tap0 + tx) * p.Cout + (co0 + row)) * p.Cin + ci0 + jx * 8;
                                 acc_out_v4(det, out, v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
                                 acc_out_v4(det, out + 4, v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
                             }
@@ -331,11 +340,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             }
         } else
         for (int tl = 0; tl < T_n; ++tl) {
-            float* out = dwo + ((size_t)(t0 + tl) * p.Cout + (co0 + row)) * p.Cin + ci0;
+            const int tap = R > 1 ? (copy < R ? (int)p.job_tap[t0 + tl][copy] : -1) : t0 + tl;
+            float* out = dwo + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + (co0 + row)) * p.Cin + ci0;
             for (int cc = 0; cc < (p.Nc >> 4); ++cc) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * p.Nc + cc * 16), v);
-                if (valid) {
+                if (valid && tap >= 0) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) acc_out_v4(det, out + cc * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }

@@ -125,7 +125,7 @@ def test_wgrad_planner_folds_tap_rows_of_16_channel_sources():
     """rd_wgrad_params.fold_rows/fold_len: 16-channel stride-1 sources whose taps form full rows of <= 4 adjacent taps
     (3x3 convs of the depth branch / decoder layer 4, the fused 4x4 stem) get one N=32 UMMA per tap row and chunk."""
     g = cp.gconv_standard(0, 16, 16, 3, 1, 1)
-    w = cp.plan_wgrad(g, 2, (24, 40), (24, 40))
+    w = cp.plan_wgrad(g, 2, (24, 40), (24, 40), gcopy=False)
     assert (w.params.fold_rows, w.params.fold_len) == (3, 3) and w.params.Nc == 16 and w.params.ntg == 1
     taps = [w.params.taps[i] for i in range(w.params.ntaps)]
     for r in range(3):
@@ -136,10 +136,41 @@ def test_wgrad_planner_folds_tap_rows_of_16_channel_sources():
     s = cp.gconv_stem(0, 10 ** 6, 1)
     ws = cp.plan_wgrad(s, 2, (32, 48), (32, 48))
     assert (ws.params.fold_rows, ws.params.fold_len) == (4, 4)
+    assert ws.params.gcopies == 0                       # 80 output channels: no room for a second copy in M
     # wider sources, strided sources and the fp32 parity mode are not folded
     assert cp.plan_wgrad(cp.gconv_standard(0, 32, 32, 3, 1, 1), 2, (24, 40), (24, 40)).params.fold_len == 0
     assert cp.plan_wgrad(cp.gconv_standard(0, 32, 16, 3, 2, 1), 2, (24, 40), (12, 20)).params.fold_len == 0
     assert cp.plan_wgrad(g, 2, (24, 40), (24, 40), _lib.RD_F32).params.fold_len == 0
+
+
+def test_wgrad_planner_stacks_gradient_copies_in_m():
+    """rd_wgrad_params.gcopies: stride-1 convolutions with Cout <= 64 stage the gradient tile R = min(128/Cout, rows) times,
+    copy r shifted r rows down, so that one UMMA covers R taps; every tap is produced exactly once."""
+    for co, ci, R, njobs, fold in ((64, 64, 2, 6, 0), (32, 32, 3, 3, 0), (16, 16, 3, 1, 3), (16, 32, 3, 3, 0)):
+        w = cp.plan_wgrad(cp.gconv_standard(0, co, ci, 3, 1, 1), 2, (24, 40), (24, 40), use_tuned=False)
+        q = w.params
+        assert (q.gcopies, q.njobs, q.fold_len) == (R, njobs, fold), (co, ci, w.info)
+        assert q.gcopies * q.Mc <= 128 and q.tile_oy == R - 1 and q.tiles_y * q.Ht >= 24 + q.tile_oy
+        assert q.KS == q.Ht * q.Wl                                       # copies are TMA boxes
+        assert q.g_bytes >= R * (q.Mc // 8) * q.KS * 16
+        produced = []
+        for j in range(q.njobs):
+            sy, sx = divmod(q.taps[j].x_shift, q.Wl)                     # source shift of copy 0, relative to (sy_min, sx_min)
+            for r in range(R):
+                t = q.job_tap[j][r]
+                if t < 0:
+                    assert sy - r < 0                                    # only rows above the first tap row are dropped
+                    continue
+                taps_of = [t + i for i in range(fold)] if fold else [t]
+                assert t == (sy - r) * 3 + (0 if fold else sx)           # tap (sy - r, sx): copy r is the tile r rows further down
+                produced += taps_of
+        assert sorted(produced) == list(range(9)), (co, ci, produced)
+    # strided convolutions, 1x1 convolutions, wide layers, the fp32 parity mode and RD_WGRAD_GCOPY=0 keep one accumulator per tap
+    assert cp.plan_wgrad(cp.gconv_standard(0, 32, 16, 3, 2, 1), 2, (24, 40), (12, 20)).params.gcopies == 0
+    assert cp.plan_wgrad(cp.gconv_standard(0, 64, 64, 1, 1, 0), 2, (24, 40), (24, 40)).params.gcopies == 0
+    assert cp.plan_wgrad(cp.gconv_standard(0, 128, 128, 3, 1, 1), 2, (24, 40), (24, 40)).params.gcopies == 0
+    assert cp.plan_wgrad(cp.gconv_standard(0, 64, 64, 3, 1, 1), 2, (24, 40), (24, 40), _lib.RD_F32).params.gcopies == 0
+    assert cp.plan_wgrad(cp.gconv_standard(0, 64, 64, 3, 1, 1), 2, (24, 40), (24, 40), gcopy=False).params.gcopies == 0
 
 
 def test_planner_stages_one_parity_plane_for_1x1_stride2():
