@@ -496,9 +496,15 @@ def _search_wgrad_tile(g, Nc, Mc, ncob, ntaps, parts, Hb, Wb, halo_y, halo_x, ks
 def _gcopy_layout(g: GConv, taps, Mc: int, parts: int):
     """Gradient copies stacked in M (rd_wgrad_params.gcopies): (R, tap rows, tap columns) for stride-1 convolutions with
     Cout <= 64 whose taps form a full rows x columns grid, else None."""
-    if parts != 1 or g.S != 1 or g.OS != 1 or Mc > 64 or os.environ.get("RD_TMA", "1") == "0" or \
+    if parts != 1 or g.S != 1 or g.OS not in (1, 2) or Mc > 64 or os.environ.get("RD_TMA", "1") == "0" or \
             os.environ.get("RD_WGRAD_GCOPY", "1") == "0":
         return None
+    if g.OS == 2:
+        # sub-pixel (UpProj / UpConv / ConvTranspose2d) programs: the four parity planes of the gradient tile are staged side
+        # by side anyway, so R adjacent planes ARE the stacked operand -- taps of those phases that share a source shift
+        # become one accumulator, with no extra load at all
+        R = min(128 // Mc, 4)
+        return (R, None, None) if R >= 2 else None
     rows = sorted({t.s[0] for t in taps})
     cols = sorted({t.s[1] for t in taps})
     if len(rows) < 2 or len(rows) * len(cols) != len(taps) or [t.s for t in taps] != [(r, c) for r in rows for c in cols]:
@@ -538,7 +544,21 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     R, tile_oy = 1, 0
     jobs = None                                       # [(sy of copy 0, sx or None when the row is N-folded)]
     fold_n = False
-    if gl is not None:
+    plane_jobs = None                                 # OS = 2: [(first plane, (sy, sx), [tap index or -1 per stacked plane])]
+    if gl is not None and gl[1] is None:
+        R = gl[0]
+        phases_ = sorted({t.ph for t in taps})
+        assert all(ph in [(a, b) for a in range(2) for b in range(2)] for ph in phases_)
+        by = {}
+        for i, t in enumerate(taps):
+            by[(t.ph[0] * 2 + t.ph[1], t.s)] = i
+        plane_jobs = []
+        for q0 in range(0, 4, R):
+            shifts = sorted({s_ for (q_, s_) in by if q0 <= q_ < q0 + R})
+            for s_ in shifts:
+                plane_jobs.append((q0, s_, [by.get((q0 + r, s_), -1) for r in range(R)]))
+        jobs = plane_jobs
+    elif gl is not None:
         R, rows, cols = gl
         tile_oy = R - 1
         job_rows = [rows[-1] - m * R for m in range(-(-len(rows) // R))]
@@ -593,7 +613,13 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
         q = t.pl[0] * g.S + t.pl[1]
         p.taps[i].x_shift = q * geo["xslots"] + (t.s[0] - sy_min) * geo["Wl"] + (t.s[1] - sx_min)
     p.gcopies, p.njobs, p.tile_oy, p.tile_ox = (R if jobs is not None else 0), (nacc if jobs is not None else 0), tile_oy, 0
-    if jobs is not None:
+    if plane_jobs is not None:
+        for j, (q0, s_, tl) in enumerate(plane_jobs):
+            p.taps[j].g_off = q0 * geo["KS"]                     # plane offset (rewritten to the TMA layout by the launcher)
+            p.taps[j].x_shift = (s_[0] - sy_min) * geo["Wl"] + (s_[1] - sx_min)
+            for r in range(8):
+                p.job_tap[j][r] = tl[r] if r < R else -1
+    elif jobs is not None:
         ncols = len(cols)
         for r in range(R):
             p.gcopy_dy[r], p.gcopy_dx[r] = r, 0

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     const int cib = blockIdx.z / p.ntg;
     const int tg = blockIdx.z - cib * p.ntg;
     const int t0 = tg * p.tg_size;
-    const int R = p.gcopies > 1 ? p.gcopies : 1;               // gradient copies stacked in M (rd_wgrad_params.gcopies)
+    const int R = p.gcopies > 1 ? p.gcopies : 1;               // gradient copies / planes stacked in M (rd_wgrad_params.gcopies)
+    const int Rload = (p.Sg == 1) ? R : 1;                     // Sg = 2: the R rows blocks are the parity planes staged anyway
     const int T_n = min(p.tg_size, (R > 1 ? p.njobs : p.ntaps) - t0);
     const int co0 = cob * p.Mc, ci0 = cib * p.Nc;
     const int tiles_per_img = p.tiles_y * p.tiles_x;
@@ -158,9 +159,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 if (lane == 0) {
                     uint64_t* bar = hop ? &tma_full[st.stage] : &full[st.stage];
                     if (!(p.dbg_flags & 2)) {
-                        mbar_arrive_expect_tx(bar, (g_tma ? g_tx * (uint32_t)R : 0u) + (x_tma ? x_tx : 0u));
-                        if (g_tma && R > 1) {
-                            for (int r = 0; r < R; ++r)              // copy r: the same box, (dy, dx) pixels further
+                        mbar_arrive_expect_tx(bar, (g_tma ? g_tx * (uint32_t)Rload : 0u) + (x_tma ? x_tx : 0u));
+                        if (g_tma && Rload > 1) {
+                            for (int r = 0; r < Rload; ++r)          // copy r: the same box, (dy, dx) pixels further
                                 tma_load_5d(sbase + (size_t)r * g_chunks * p.KS * 16, &g_map, 0, x0 + p.gcopy_dx[r], y0 + p.gcopy_dy[r],
                                             co0 >> 3, img, bar);
                         } else if (g_tma) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             if (g_tma) {
                 // clear the junk columns [Wt, Wl) of every row and chunk plane of the gradient tile
                 const int jc = p.Wl - p.Wt;
-                const int items = p.Ht * jc * g_chunks * g_planes * R;   // planes, copies and chunk planes are all KS slots apart
+                const int items = p.Ht * jc * g_chunks * g_planes * Rload;   // planes, copies and chunk planes are all KS slots apart
                 const FastDivS fd_jc((uint32_t)jc), fd_ht((uint32_t)p.Ht);
                 for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
                     const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
