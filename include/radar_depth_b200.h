@@ -269,9 +269,26 @@ int rd_bn_bwd_apply(rd_view g, rd_view z, rd_view dz, const float* coefA, const 
  * mask, e.g. bn_fusion / bn2 of models.py:652-657 when their gradient comes from an elementwise producer). */
 int rd_grad_stats(rd_view g, rd_view z, long long npix, int C, double* sum_g, double* sum_gz, int act_dtype, void* stream);
 
-/* nn.MaxPool2d(3,2,1) over act(bn(z)) (models.py:546-547,564-565), both stems at once; stores the arg-max. */
+/* nn.MaxPool2d(3,2,1) over act(bn(z)) (models.py:546-547,564-565), both stems at once; stores the arg-max.
+ * zarg (optional, bf16 only): [B][Ho][Wo][C] bf16, the PRE-activation value z of every window's winner, for
+ * rd_maxpool_bwd_stats. */
 int rd_maxpool_fwd(rd_view z, const float* sc, const float* sh, int B, int H, int W, int C, int split, float slope_a,
-                   float slope_b, rd_view outa, rd_view outb, uint8_t* amax, int Ho, int Wo, int act_dtype, void* stream);
+                   float slope_b, rd_view outa, rd_view outb, uint8_t* amax, int Ho, int Wo, void* zarg, int act_dtype,
+                   void* stream);
+/* The backward of the same max-pool + activation + (training-mode) BatchNorm in two passes that never materialise the
+ * gradient of the BatchNorm output (bf16 path; replaces rd_maxpool_bwd + rd_bn_bwd_apply, i.e. autograd of
+ * models.py:540-547,560-565):
+ *   rd_maxpool_bwd_stats: sum g and sum g*z over the POOLED elements (a pooled element sends its gradient to exactly one
+ *     input pixel) from the pooled gradient and zarg; `tail` finalises dgamma / dbeta and the coefficients of
+ *     dz = A*g + B*z + C like every other statistics producer;
+ *   rd_maxpool_bwd_apply: dz for every input pixel: gathers the gradients of the <= 4 windows whose arg-max is this pixel,
+ *     applies the activation derivative and the three coefficients, writes dz. */
+int rd_maxpool_bwd_stats(rd_view dpa, rd_view dpb, const void* zarg, const float* sc, const float* sh, int B, int Ho, int Wo,
+                         int C, int split, float slope_a, float slope_b, double* sum_g, double* sum_gz,
+                         const rd_bn_tail* tail /* may be NULL */, void* stream);
+int rd_maxpool_bwd_apply(rd_view dpa, rd_view dpb, const uint8_t* amax, rd_view z, const float* sc, const float* sh,
+                         const float* coefA, const float* coefB, const float* coefC, int B, int H, int W, int C, int split,
+                         float slope_a, float slope_b, int Ho, int Wo, rd_view dz, void* stream);
 int rd_maxpool_bwd(rd_view dpa, rd_view dpb, const uint8_t* amax, rd_view z, const float* sc, const float* sh, int B,
                    int H, int W, int C, int split, float slope_a, float slope_b, int Ho, int Wo, rd_view g,
                    double* sum_g, double* sum_gz, const rd_bn_tail* tail /* may be NULL */, int act_dtype, void* stream);

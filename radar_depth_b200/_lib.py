@@ -116,7 +116,9 @@ _PROTOS = {
     "rd_join_bwd": ([View, View, View, View, View, _LL, _I, _F, _P, _P, _P, C.POINTER(BnTail), _I, _P], _I),
     "rd_bn_bwd_apply": ([View, View, View, _P, _P, _P, _LL, _I, _I, _P], _I),
     "rd_grad_stats": ([View, View, _LL, _I, _P, _P, _I, _P], _I),
-    "rd_maxpool_fwd": ([View, _P, _P, _I, _I, _I, _I, _I, _F, _F, View, View, _P, _I, _I, _I, _P], _I),
+    "rd_maxpool_fwd": ([View, _P, _P, _I, _I, _I, _I, _I, _F, _F, View, View, _P, _I, _I, _P, _I, _P], _I),
+    "rd_maxpool_bwd_stats": ([View, View, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, C.POINTER(BnTail), _P], _I),
+    "rd_maxpool_bwd_apply": ([View, View, _P, View, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, View, _P], _I),
     "rd_maxpool_bwd": ([View, View, _P, View, _P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, View, _P, _P, C.POINTER(BnTail), _I, _P], _I),
     "rd_head_conv_fwd": ([View, _P, _I, _I, _I, _P, _I, _P], _I),
     "rd_head_conv_bwd": ([_P, View, _P, _I, _I, _I, View, _P, _I, _P], _I),

@@ -88,6 +88,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
                  : "memory");
 }
+// 8-byte variant (.ca: the 8-byte form has no .cg), same zero-fill rule
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 // Arrive on `bar` once every cp.async previously issued by this thread has landed (no wait, no pending-count increment:
 // the barrier's expected count must include one arrival per issuing thread).

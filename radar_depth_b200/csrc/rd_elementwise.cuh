@@ -494,13 +494,18 @@ __global__ void maxpool_fwd_kernel(VView z, const float* __restrict__ sc, const 
 // BatchNorm + activation ONCE per input element of the 9 x 33 halo tile (the direct kernel does it 2.25x) and parks the
 // rounded bf16 values in shared memory; phase B takes the 3x3 maxima with packed bf16x2 compares, tracking the arg-max
 // with the same rule (strictly greater or NaN replaces: first maximum in window order wins, out-of-image taps are -inf).
-constexpr int kMpTileH = 4, kMpTileW = 16, kMpInH = 2 * kMpTileH + 1, kMpInW = 2 * kMpTileW + 1;
+constexpr int kMpTileW = 16, kMpInW = 2 * kMpTileW + 1;
+template <int TH>
 __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int H, int W, int C,
                                         int split, float slope_a, float slope_b, VView outa, VView outb,
-                                        uint8_t* __restrict__ amax, int Ho, int Wo) {
+                                        uint8_t* __restrict__ amax, int Ho, int Wo, bf16* __restrict__ zarg) {
     pdl_enter();
-    extern __shared__ uint4 mp_tile[];                 // [kMpInH][kMpInW][G]
+    extern __shared__ uint4 mp_tile[];                 // [kMpInH][kMpInW][G], followed by the raw tile when zarg != nullptr
+    constexpr int kMpTileH = TH, kMpInH = 2 * TH + 1;        // TH output rows per block (2 when the raw tile is staged too)
     const int G = C >> 3;
+    // zarg (training): the PRE-activation value of every window's winner, [B][Ho][Wo][C] -- what the backward needs to form
+    // the BatchNorm-backward sums at pool resolution (maxpool_bwd_stats_kernel) instead of over the 4x larger stem tensor
+    uint4* raw_tile = mp_tile + kMpInH * kMpInW * G;
     const int b = blockIdx.z, oy0 = blockIdx.y * kMpTileH, ox0 = blockIdx.x * kMpTileW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
     const FastDiv fdg((uint32_t)G), fdw((uint32_t)kMpInW);
@@ -510,10 +515,11 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
         const int r = (int)fdw.div((uint32_t)pc), cx = pc - r * kMpInW;
         const int iy = iy0 + r, ix = ix0 + cx;
         uint4 u = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // -inf: never selected
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
             const int c = g * 8;
             const float slope = c < split ? slope_a : slope_b;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(zp + (((size_t)b * H + iy) * W + ix) * z.pitch + z.coff + c));
+            raw = __ldg(reinterpret_cast<const uint4*>(zp + (((size_t)b * H + iy) * W + ix) * z.pitch + z.coff + c));
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
             const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + c)), h1 = __ldg(reinterpret_cast<const float4*>(sh + c + 4));
             float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
@@ -528,6 +534,7 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
             u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
         }
         mp_tile[it] = u;
+        if (zarg) raw_tile[it] = raw;
     }
     __syncthreads();
     const FastDiv fdt((uint32_t)kMpTileW);
@@ -537,12 +544,17 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
         const int oy = oy0 + orow, ox = ox0 + ocol;
         if (oy >= Ho || ox >= Wo) continue;
         uint32_t best[4] = {0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u}, idx[4] = {0u, 0u, 0u, 0u};
+        uint32_t braw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const uint4 u = mp_tile[((2 * orow + dy) * kMpInW + 2 * ocol + dx) * G + g];
+                const int ti = ((2 * orow + dy) * kMpInW + 2 * ocol + dx) * G + g;
+                const uint4 u = mp_tile[ti];
                 const uint32_t y[4] = {u.x, u.y, u.z, u.w};
+                uint4 rw = make_uint4(0u, 0u, 0u, 0u);
+                if (zarg) rw = raw_tile[ti];
+                const uint32_t rr[4] = {rw.x, rw.y, rw.z, rw.w};
                 const uint32_t tapw = (uint32_t)(dy * 3 + dx) * 0x00010001u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -551,6 +563,7 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
                     const uint32_t m = __hgt2_mask(yy, bb) | ~__heq2_mask(yy, yy);     // y > best || isnan(y)
                     best[q] = (best[q] & ~m) | (y[q] & m);
                     idx[q] = (idx[q] & ~m) | (tapw & m);
+                    braw[q] = (braw[q] & ~m) | (rr[q] & m);
                 }
             }
         }
@@ -563,6 +576,7 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
         packed.x = (idx[0] & 0xFFu) | ((idx[0] >> 8) & 0xFF00u) | ((idx[1] & 0xFFu) << 16) | ((idx[1] & 0xFF0000u) << 8);
         packed.y = (idx[2] & 0xFFu) | ((idx[2] >> 8) & 0xFF00u) | ((idx[3] & 0xFFu) << 16) | ((idx[3] & 0xFF0000u) << 8);
         *reinterpret_cast<uint2*>(amax + pix * C + c) = packed;
+        if (zarg) *reinterpret_cast<uint4*>(zarg + pix * C + c) = make_uint4(braw[0], braw[1], braw[2], braw[3]);
     }
 }
 
@@ -752,6 +766,209 @@ __global__ void __launch_bounds__(512, 2) maxpool_bwd_tile_kernel(VView dpa, VVi
 
 // ------------------------------------------------------------------------------------------------
 // Head: conv3 3x3 16->1 (models.py:587,661) as a bandwidth kernel, fp32 output at decoder resolution.
+// ------------------------------------------------------------------------------------------------
+// Max-pool backward in two passes that never materialise the gradient of the BatchNorm OUTPUT (bf16 path, round 2).
+// A pooled element sends its gradient to exactly one stem pixel, so the BatchNorm-backward sums over the stem tensor,
+// sum g and sum g*z with g = act'(bn(z)) * (gradient arriving at the pixel), are sums over the POOLED elements of
+// d * act'(bn(z_arg)) and d * act'(bn(z_arg)) * z_arg, z_arg = the winner's pre-activation value kept by the forward pass:
+// pass 1 reads 2 x 68 MB instead of 650 MB.  Pass 2 then has the coefficients of dz = A*g + B*z + C (rd_bn_tail of pass 1)
+// and writes dz directly: the separate bn_bwd_apply pass over the 274 MB stem tensor (read 2x, written 1x) is gone.
+__global__ void __launch_bounds__(256, 3) maxpool_bwd_stats_kernel(VView dpa, VView dpb, const bf16* __restrict__ zarg,
+                                const float* __restrict__ sc, const float* __restrict__ sh, size_t npool, int C, int split,
+                                float slope_a, float slope_b, double* sum_g, double* sum_gz,
+                                const __grid_constant__ rd_bn_tail tail, float* det_part) {
+    pdl_enter();
+    extern __shared__ float red_s[];
+    const int groups = C >> 3;
+    const int cg = threadIdx.x % groups;
+    const int ppb = blockDim.x / groups;
+    const int pl = threadIdx.x / groups;
+    const int c = cg * 8;
+    const float slope = c < split ? slope_a : slope_b;
+    float acc[2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+    if (pl < ppb) {
+        float scv[8], shv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { scv[k] = sc[c + k]; shv[k] = sh[c + k]; }
+        const size_t step = (size_t)gridDim.x * ppb;
+        for (size_t pix = (size_t)blockIdx.x * ppb + pl; pix < npool; pix += 2 * step) {
+            const size_t pix1 = pix + step;
+            const bool two = pix1 < npool;
+            uint4 d0, z0, d1 = make_uint4(0, 0, 0, 0), z1 = make_uint4(0, 0, 0, 0);
+            d0 = c < split ? __ldg(reinterpret_cast<const uint4*>(vptr<bf16>(dpa, pix, c)))
+                           : __ldg(reinterpret_cast<const uint4*>(vptr<bf16>(dpb, pix, c - split)));
+            z0 = __ldg(reinterpret_cast<const uint4*>(zarg + pix * C + c));
+            if (two) {
+                d1 = c < split ? __ldg(reinterpret_cast<const uint4*>(vptr<bf16>(dpa, pix1, c)))
+                               : __ldg(reinterpret_cast<const uint4*>(vptr<bf16>(dpb, pix1, c - split)));
+                z1 = __ldg(reinterpret_cast<const uint4*>(zarg + pix1 * C + c));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                const uint4 d = u ? d1 : d0, zq = u ? z1 : z0;
+                const float dv[8] = {bf16lo(d.x), bf16hi(d.x), bf16lo(d.y), bf16hi(d.y), bf16lo(d.z), bf16hi(d.z), bf16lo(d.w), bf16hi(d.w)};
+                const float zz[8] = {bf16lo(zq.x), bf16hi(zq.x), bf16lo(zq.y), bf16hi(zq.y), bf16lo(zq.z), bf16hi(zq.z), bf16lo(zq.w), bf16hi(zq.w)};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float y = fmaf(zz[k], scv[k], shv[k]);
+                    const float gv = y > 0.f ? dv[k] : dv[k] * slope;
+                    acc[0][k] += gv;
+                    acc[1][k] += gv * zz[k];
+                }
+            }
+        }
+    }
+    double* outs[2] = {sum_g, sum_gz};
+    block_channel_reduce<2>(acc, cg, C, red_s, outs, tail, det_part);
+    block_bn_tail(tail, det_part, 2, C, outs);
+}
+
+// Pass 2: one thread per (stem pixel, 8-channel group).  A pixel of a 3x3 / stride 2 / pad 1 pooling lies in one window per
+// even coordinate and in two per odd coordinate, at a position (dy, dx) inside each window that depends on the parities only;
+// the window's gradient reaches the pixel where its arg-max byte equals dy*3+dx.  Windows (gradient + arg-max bytes) of a
+// tile are staged in shared memory once; the kernel is persistent over tiles.
+constexpr int kMgTileH = 4, kMgTileW = 32, kMgWinH = kMgTileH / 2 + 1, kMgWinW = kMgTileW / 2 + 1;
+__global__ void __launch_bounds__(512, 2) maxpool_bwd_apply_kernel(VView dpa, VView dpb, const uint8_t* __restrict__ amax, VView z,
+                                const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ cA,
+                                const float* __restrict__ cB, const float* __restrict__ cC, int B, int H, int W, int C, int split,
+                                float slope_a, float slope_b, int Ho, int Wo, VView dz) {
+    pdl_enter();
+    // Two shared-memory buffers per block, filled with cp.async one tile ahead: the z tile, the windows' gradients and
+    // their arg-max bytes.  Register-held loads (one or two 16-byte requests per thread) kept ~25 KB in flight per SM,
+    // half of what HBM needs; the asynchronous copies keep 3 blocks x 30 KB in flight without holding registers.
+    extern __shared__ __align__(16) uint8_t mg_smem[];
+    const int G = C >> 3;
+    const int nwin = kMgWinH * kMgWinW * G, npx = kMgTileH * kMgTileW * G;
+    const size_t buf_bytes = (size_t)nwin * 24 + (size_t)npx * 16;
+    float* coef = reinterpret_cast<float*>(mg_smem + 2 * buf_bytes);                       // [sc | sh | A | B | C][C]
+    const int cg = threadIdx.x % G;                        // fixed per thread: blockDim = 32 * G
+    const int c = cg * 8;
+    const float slope = c < split ? slope_a : slope_b;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        coef[i] = sc[i]; coef[C + i] = sh[i]; coef[2 * C + i] = cA[i]; coef[3 * C + i] = cB[i]; coef[4 * C + i] = cC[i];
+    }
+    const int tiles_x = (W + kMgTileW - 1) / kMgTileW, tiles_y = (H + kMgTileH - 1) / kMgTileH;
+    const int ntiles = tiles_x * tiles_y * B;
+    const FastDiv fdg((uint32_t)G), fdww((uint32_t)kMgWinW), fdtx((uint32_t)tiles_x), fdty((uint32_t)tiles_y);
+    const bf16* zp = reinterpret_cast<const bf16*>(z.ptr);
+    bf16* op = reinterpret_cast<bf16*>(dz.ptr);
+    constexpr int kItems = kMgTileH * kMgTileW / 32;       // (pixel, group) items per thread and tile
+
+    // blockDim = 32 * G and a tile is 32 pixels wide: item k of a thread is ALWAYS pixel (row k, column tid / G), group
+    // tid % G -- no per-item index arithmetic, and the column's windows / positions are fixed for the thread's lifetime
+    const int cxt = threadIdx.x / G;                       // tile column of every pixel this thread owns
+    const int nwx = 1 + (cxt & 1);
+    const int wc0 = cxt >> 1, dx0 = (cxt & 1) ? 2 : 1;     // second window of odd columns: wc0 + 1 at dx = 0
+    // the (at most two) window items this thread stages per tile
+    int w_it[2], w_wr[2], w_wc[2], w_cc[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int it = threadIdx.x + j * blockDim.x;
+        const int pw = (int)fdg.div((uint32_t)it);
+        w_it[j] = it < nwin ? it : -1;
+        w_cc[j] = (it - pw * G) * 8;
+        w_wr[j] = (int)fdww.div((uint32_t)pw);
+        w_wc[j] = pw - w_wr[j] * kMgWinW;
+    }
+
+    auto issue = [&](int tile, int buf) {
+        uint8_t* base = mg_smem + (size_t)buf * buf_bytes;
+        uint4* dwin = reinterpret_cast<uint4*>(base);                                      // [kMgWinH][kMgWinW][G] 8 x bf16
+        uint2* awin = reinterpret_cast<uint2*>(base + (size_t)nwin * 16);                  // [kMgWinH][kMgWinW][G] 8 bytes
+        uint4* ztile = reinterpret_cast<uint4*>(base + (size_t)nwin * 24);                 // [kMgTileH][kMgTileW][G]
+        const int t1 = (int)fdtx.div((uint32_t)tile), tx = tile - t1 * tiles_x;
+        const int b = (int)fdty.div((uint32_t)t1), ty = t1 - b * tiles_y;
+        const int iy0 = ty * kMgTileH, ix0 = tx * kMgTileW;           // even
+        const int oy0 = iy0 >> 1, ox0 = ix0 >> 1;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (w_it[j] < 0) continue;
+            const int oy = oy0 + w_wr[j], ox = ox0 + w_wc[j];
+            const bool ok = oy < Ho && ox < Wo;
+            const size_t opix = ok ? ((size_t)b * Ho + oy) * Wo + ox : 0;
+            const int cc = w_cc[j];
+            // windows outside the pooled map: zero gradient (their arg-max bytes read 0 = a valid code, harmless with d = 0)
+            cp_async8(&awin[w_it[j]], amax + opix * C + cc, ok ? 8u : 0u);
+            cp_async16(&dwin[w_it[j]], cc < split ? (const void*)vptr<bf16>(dpa, opix, cc) : (const void*)vptr<bf16>(dpb, opix, cc - split), ok ? 16u : 0u);
+        }
+        const int ix = ix0 + cxt;
+        const bf16* zrow = zp + (((size_t)b * H + iy0) * W + (ix < W ? ix : 0)) * z.pitch + z.coff + c;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const bool ok = iy0 + k < H && ix < W;
+            cp_async16(&ztile[threadIdx.x + k * blockDim.x], ok ? zrow + (size_t)k * W * z.pitch : zp, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+    };
+
+    float scv[8], shv[8];
+    int buf = 0;
+    if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < ntiles) { issue(next, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();                                   // this tile's copies of every thread have landed (and coef is there)
+        const uint8_t* base = mg_smem + (size_t)buf * buf_bytes;
+        const uint4* dwin = reinterpret_cast<const uint4*>(base);
+        const uint2* awin = reinterpret_cast<const uint2*>(base + (size_t)nwin * 16);
+        const uint4* ztile = reinterpret_cast<const uint4*>(base + (size_t)nwin * 24);
+        const int t1 = (int)fdtx.div((uint32_t)tile), tx = tile - t1 * tiles_x;
+        const int b = (int)fdty.div((uint32_t)t1), ty = t1 - b * tiles_y;
+        const int iy0 = ty * kMgTileH, ix = tx * kMgTileW + cxt;
+        lds8(coef + c, scv); lds8(coef + C + c, shv);
+        bf16* orow = op + (((size_t)b * H + iy0) * W + ix) * dz.pitch + dz.coff + c;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {                  // row k of the tile: even rows lie in one window row, odd rows in two
+            if (iy0 + k >= H || ix >= W) continue;
+            // The gradients are summed as packed bf16 pairs under byte masks: arg-max byte == dy*3+dx selects the channel.
+            __nv_bfloat162 acc2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc2[q] = __nv_bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
+#pragma unroll
+            for (int a_ = 0; a_ < 1 + (k & 1); ++a_) {
+                const int wr = (k >> 1) + a_;
+                const int dy = (k & 1) ? (a_ ? 0 : 2) : 1;
+                for (int b_ = 0; b_ < nwx; ++b_) {
+                    const int dx = b_ ? 0 : dx0;
+                    const uint32_t code4 = (uint32_t)(dy * 3 + dx) * 0x01010101u;
+                    const int wi = (wr * kMgWinW + wc0 + b_) * G + cg;
+                    const uint2 a = awin[wi];
+                    const uint4 d = dwin[wi];
+                    const uint32_t mlo = __vcmpeq4(a.x, code4), mhi = __vcmpeq4(a.y, code4);      // 0xFF per matching byte
+                    const uint32_t w0 = d.x & __byte_perm(mlo, 0u, 0x1100), w1 = d.y & __byte_perm(mlo, 0u, 0x3322);
+                    const uint32_t w2 = d.z & __byte_perm(mhi, 0u, 0x1100), w3 = d.w & __byte_perm(mhi, 0u, 0x3322);
+                    acc2[0] = __hadd2(acc2[0], *reinterpret_cast<const __nv_bfloat162*>(&w0));
+                    acc2[1] = __hadd2(acc2[1], *reinterpret_cast<const __nv_bfloat162*>(&w1));
+                    acc2[2] = __hadd2(acc2[2], *reinterpret_cast<const __nv_bfloat162*>(&w2));
+                    acc2[3] = __hadd2(acc2[3], *reinterpret_cast<const __nv_bfloat162*>(&w3));
+                }
+            }
+            const uint32_t* au = reinterpret_cast<const uint32_t*>(acc2);
+            const float gsum[8] = {bf16lo(au[0]), bf16hi(au[0]), bf16lo(au[1]), bf16hi(au[1]), bf16lo(au[2]), bf16hi(au[2]), bf16lo(au[3]), bf16hi(au[3])};
+            const uint4 zz4 = ztile[threadIdx.x + k * blockDim.x];
+            const float zz[8] = {bf16lo(zz4.x), bf16hi(zz4.x), bf16lo(zz4.y), bf16hi(zz4.y), bf16lo(zz4.z), bf16hi(zz4.z), bf16lo(zz4.w), bf16hi(zz4.w)};
+            float o[8], av[8], bv[8], cv[8];
+            lds8(coef + 2 * C + c, av); lds8(coef + 3 * C + c, bv); lds8(coef + 4 * C + c, cv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(zz[e], scv[e], shv[e]);
+                const float gv = y > 0.f ? gsum[e] : gsum[e] * slope;
+                o[e] = fmaf(av[e], gv, fmaf(bv[e], zz[e], cv[e]));
+            }
+            uint4 ov;
+            ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+            ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(orow + (size_t)k * W * dz.pitch) = ov;
+        }
+        __syncthreads();                                   // everyone is done with this buffer before it is refilled
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) head_conv_fwd_kernel(VView x, const float* __restrict__ w /*[16][3][3] OIHW with O=1*/, int B,
                                                             int H, int W, float* __restrict__ out) {

@@ -416,9 +416,16 @@ class LatefusionEngine:
         p_d = None if single else self.act(B, H4, W4, 16)
         amax = self.hold(torch.zeros(B, H4, W4, Cst, dtype=torch.uint8, device=self.device))
         pool_out = (p_rgb.numel() + (0 if single else p_d.numel())) * es
-        both(Launch("maxpool", lib.rd_maxpool_fwd,
-                    (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, Cst, 64, 0.0, 0.2, _v(p_rgb),
-                     NULLV if single else _v(p_d), _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + pool_out + amax.numel())))
+        # bf16 training: the forward also keeps every window winner's PRE-activation value, so that the backward forms the
+        # stem BatchNorm's sums at pool resolution and writes dz in one pass over the stem tensor (rd_maxpool_bwd_stats/apply)
+        self._stem_bwd2 = act == RD_BF16 and os.environ.get("RD_STEM_BWD2", "1") != "0"
+        zarg = self.hold(torch.zeros(B, H4, W4, Cst, dtype=torch.bfloat16, device=self.device)) if self._stem_bwd2 else None
+        mp_args = lambda za: (_v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2, Cst, 64, 0.0, 0.2, _v(p_rgb),
+                              NULLV if single else _v(p_d), _p(amax), H4, W4, (_p(za) if za is not None else None), act)
+        mp_bytes = z_stem.numel() * es + pool_out + amax.numel()
+        self.fwd.append(Launch("maxpool", lib.rd_maxpool_fwd, mp_args(zarg),
+                               dict(bytes=mp_bytes + (zarg.numel() * 2 if zarg is not None else 0))))
+        self.fwd_eval.append(Launch("maxpool", lib.rd_maxpool_fwd, mp_args(None), dict(bytes=mp_bytes)))
 
         # ---- encoders
         enc_specs = [("", (64, 128, 256, 512), 64, p_rgb, 0)]
@@ -588,7 +595,7 @@ class LatefusionEngine:
                       tag="(infer)")
             fi.append(Launch("maxpool", lib.rd_maxpool_fwd,
                              (_v(z_stem), _p(ones), _p(zeros), B, H2, W2, Cst, 64, 1.0, 1.0, _v(p_rgb),
-                              NULLV if single else _v(p_d), _p(amax), H4, W4, act), dict(bytes=z_stem.numel() * es + pool_out + amax.numel())))
+                              NULLV if single else _v(p_d), _p(amax), H4, W4, None, act), dict(bytes=z_stem.numel() * es + pool_out + amax.numel())))
             enc0 = len(fi)
             for blks in blocks_all:
                 for Bk in blks:
@@ -771,14 +778,25 @@ class LatefusionEngine:
         if not single:
             stem_jobs.append(bwd_job(g_stem, 1, _p(g_stem.bstats[0], 64), _p(g_stem.bstats[1], 64), n_stem))
         tj = new_tail(stem_jobs, 3, g_stem.C)
-        bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
-                         (dpool[0], NULLV if single else dpool[1], _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2,
-                          Cst, 64, 0.0, 0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
-                         dict(bytes=pool_out + amax.numel() + 2 * z_stem.numel() * es),
-                         sync="join" if par else None))
-        bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
-                         (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), Cst, act),
-                         dict(bytes=3 * z_stem.numel() * es)))
+        dp_b = NULLV if single else dpool[1]
+        if self._stem_bwd2:
+            bw.append(Launch("maxpool_bwd_stats", lib.rd_maxpool_bwd_stats,
+                             (dpool[0], dp_b, _p(zarg), _p(g_stem.scale), _p(g_stem.shift), B, H4, W4, Cst, 64, 0.0, 0.2,
+                              _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj)),
+                             dict(bytes=pool_out + zarg.numel() * 2), sync="join" if par else None))
+            bw.append(Launch("maxpool_bwd_apply", lib.rd_maxpool_bwd_apply,
+                             (dpool[0], dp_b, _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), _p(g_stem.cA), _p(g_stem.cB),
+                              _p(g_stem.cC), B, H2, W2, Cst, 64, 0.0, 0.2, H4, W4, _v(gz_stem)),
+                             dict(bytes=pool_out + amax.numel() + 2 * z_stem.numel() * es)))
+        else:
+            bw.append(Launch("maxpool_bwd", lib.rd_maxpool_bwd,
+                             (dpool[0], dp_b, _p(amax), _v(z_stem), _p(g_stem.scale), _p(g_stem.shift), B, H2, W2,
+                              Cst, 64, 0.0, 0.2, H4, W4, _v(gz_stem), _p(g_stem.bstats[0]), _p(g_stem.bstats[1]), C.byref(tj), act),
+                             dict(bytes=pool_out + amax.numel() + 2 * z_stem.numel() * es),
+                             sync="join" if par else None))
+            bw.append(Launch("bn_bwd_apply:stem", lib.rd_bn_bwd_apply,
+                             (_v(gz_stem), _v(z_stem), _v(gz_stem), _p(g_stem.cA), _p(g_stem.cB), _p(g_stem.cC), int(B * H2 * W2), Cst, act),
+                             dict(bytes=3 * z_stem.numel() * es)))
         emit_wgrad(bw, stem, _v(gz_stem), _v(xs))
         self.dxs = None
         if self.in_channels > 4:

@@ -170,7 +170,9 @@ def test_maxpool_forward_backward_vs_autograd(name, act, td, H, W, ties):
     oa = torch.empty(B, Ho, Wo, split, device="cuda", dtype=td)
     ob = torch.empty(B, Ho, Wo, C - split, device="cuda", dtype=td)
     amax = torch.zeros(B, Ho, Wo, C, device="cuda", dtype=torch.uint8)
-    call("rd_maxpool_fwd", view(z), ptr(sc), ptr(sh), B, H, W, C, split, 0.0, 0.2, view(oa), view(ob), ptr(amax), Ho, Wo, act, stream_ptr())
+    zarg = torch.zeros(B, Ho, Wo, C, device="cuda", dtype=torch.bfloat16) if act == _lib.RD_BF16 else None
+    call("rd_maxpool_fwd", view(z), ptr(sc), ptr(sh), B, H, W, C, split, 0.0, 0.2, view(oa), view(ob), ptr(amax), Ho, Wo, ptr(zarg), act,
+         stream_ptr())
     zr = nchw(z.float()).requires_grad_(True)
     y = zr * sc[None, :, None, None] + sh[None, :, None, None]
     y = torch.cat([F.relu(y[:, :split]), F.leaky_relu(y[:, split:], 0.2)], 1)
@@ -198,6 +200,31 @@ def test_maxpool_forward_backward_vs_autograd(name, act, td, H, W, ties):
     st_tol = dict(rtol=1e-3, atol=1e-3) if act == _lib.RD_F32 else dict(rtol=2e-2, atol=8e-2)
     torch.testing.assert_close(st[0].float(), g.float().sum(dim=(0, 1, 2)), **st_tol)
     torch.testing.assert_close(st[1].float(), (g.float() * z.float()).sum(dim=(0, 1, 2)), **st_tol)
+    if act != _lib.RD_BF16:
+        return
+    # ---- the two-pass backward (rd_maxpool_bwd_stats + rd_maxpool_bwd_apply) against the path above
+    # zarg = z at the arg-max position of every window (per channel)
+    code = amax.long()
+    dy, dx = code // 3, code % 3
+    oy = torch.arange(Ho, device="cuda")[None, :, None, None]
+    ox = torch.arange(Wo, device="cuda")[None, None, :, None]
+    iy, ix = (2 * oy - 1 + dy).clamp(0, H - 1), (2 * ox - 1 + dx).clamp(0, W - 1)
+    bi = torch.arange(B, device="cuda")[:, None, None, None].expand_as(iy)
+    ci = torch.arange(C, device="cuda")[None, None, None, :].expand_as(iy)
+    assert torch.equal(zarg, z[bi, iy, ix, ci])
+    st2 = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    call("rd_maxpool_bwd_stats", view(dpa), view(dpb), ptr(zarg), ptr(sc), ptr(sh), B, Ho, Wo, C, split, 0.0, 0.2, ptr(st2[0]), ptr(st2[1]),
+         None, stream_ptr())
+    # same products as the stem-resolution sums, added in another order (and from un-rounded per-window gradients)
+    torch.testing.assert_close(st2.float(), st.float(), rtol=2e-2, atol=8e-2)
+    cA = torch.rand(C, device="cuda") + 0.5
+    cB = torch.randn(C, device="cuda") * 0.1
+    cC = torch.randn(C, device="cuda") * 0.1
+    dz = torch.empty(B, H, W, C, device="cuda", dtype=td)
+    call("rd_maxpool_bwd_apply", view(dpa), view(dpb), ptr(amax), view(z), ptr(sc), ptr(sh), ptr(cA), ptr(cB), ptr(cC), B, H, W, C, split,
+         0.0, 0.2, Ho, Wo, view(dz), stream_ptr())
+    want = cA * gref + cB * z.float() + cC           # gref: exact fp32 gradient w.r.t. the BatchNorm output (CPU autograd)
+    torch.testing.assert_close(dz.float(), want, rtol=2e-2, atol=2e-2)
 
 
 @pytest.mark.parametrize("name,act,td", ACTS)
