@@ -510,21 +510,27 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
     const FastDiv fdg((uint32_t)G), fdw((uint32_t)kMpInW);
     const bf16* zp = reinterpret_cast<const bf16*>(z.ptr);
-    for (int it = threadIdx.x; it < kMpInH * kMpInW * G; it += blockDim.x) {
-        const int pc = (int)fdg.div((uint32_t)it), g = it - pc * G;
-        const int r = (int)fdw.div((uint32_t)pc), cx = pc - r * kMpInW;
+    // blockDim = 32 * G: a thread's items all belong to channel group tid % G (its BatchNorm vectors live in registers) and
+    // to input positions tid / G + 32 j -- row / column of the 33-wide input tile follow without a division
+    const int g = threadIdx.x % G, c = g * 8, pc0 = threadIdx.x / G;
+    const float slope = c < split ? slope_a : slope_b;
+    float scv[8], shv[8];
+    {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + c)), h1 = __ldg(reinterpret_cast<const float4*>(sh + c + 4));
+        scv[0] = s0.x; scv[1] = s0.y; scv[2] = s0.z; scv[3] = s0.w; scv[4] = s1.x; scv[5] = s1.y; scv[6] = s1.z; scv[7] = s1.w;
+        shv[0] = h0.x; shv[1] = h0.y; shv[2] = h0.z; shv[3] = h0.w; shv[4] = h1.x; shv[5] = h1.y; shv[6] = h1.z; shv[7] = h1.w;
+    }
+    int j = 0;
+    for (int it = threadIdx.x; it < kMpInH * kMpInW * G; it += blockDim.x, ++j) {
+        // position 32 j + pc0 = 33 j + (pc0 - j) of the 33-wide tile (j <= 2 TH <= 8 < 32)
+        const int r = pc0 >= j ? j : j - 1, cx = pc0 >= j ? pc0 - j : pc0 - j + kMpInW;
         const int iy = iy0 + r, ix = ix0 + cx;
         uint4 u = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // -inf: never selected
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            const int c = g * 8;
-            const float slope = c < split ? slope_a : slope_b;
             raw = __ldg(reinterpret_cast<const uint4*>(zp + (((size_t)b * H + iy) * W + ix) * z.pitch + z.coff + c));
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + c)), h1 = __ldg(reinterpret_cast<const float4*>(sh + c + 4));
             float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
-            const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float y = fmaf(v[k], scv[k], shv[k]);
@@ -1137,6 +1143,25 @@ __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int H
         else { oy_lo = 0; oy_hi = Ho - 1; }
         if (rx > 0.f) { ox_lo = max(0, (int)floorf((ix - 1) / rx) - 1); ox_hi = min(Wo - 1, (int)ceilf((ix + 1) / rx) + 1); }
         else { ox_lo = 0; ox_hi = Wo - 1; }
+        // column weights once per thread (the candidate window is at most kBlCand wide for scale factors >= 1/3), then
+        // one pass over the candidate rows: the inner loop is loads and FMAs only
+        constexpr int kBlCand = 8;
+        float wxs[kBlCand];
+        const bool narrow = (ox_hi - ox_lo) < kBlCand;
+#pragma unroll
+        for (int k = 0; k < kBlCand; ++k) {
+            const int ox = ox_lo + k;
+            const float sx = rx * ox;
+            const int x0 = (int)sx;
+            const int x1 = min(x0 + 1, Wi - 1);
+            const float lx = sx - x0;
+            float wx = 0.f;
+            if (ox <= ox_hi) {
+                if (x0 == ix) wx += 1.f - lx;
+                if (x1 == ix) wx += lx;
+            }
+            wxs[k] = wx;
+        }
         float acc = 0.f;
         const float* p = dout + (size_t)b * Ho * Wo;
         for (int oy = oy_lo; oy <= oy_hi; ++oy) {
@@ -1148,16 +1173,25 @@ __global__ void bilinear_bwd_kernel(const float* __restrict__ dout, int B, int H
             if (y0 == iy) wy += 1.f - ly;
             if (y1 == iy) wy += ly;
             if (wy == 0.f) continue;
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                const float sx = rx * ox;
-                const int x0 = (int)sx;
-                const int x1 = min(x0 + 1, Wi - 1);
-                const float lx = sx - x0;
-                float wx = 0.f;
-                if (x0 == ix) wx += 1.f - lx;
-                if (x1 == ix) wx += lx;
-                if (wx == 0.f) continue;
-                acc = fmaf(wy * wx, p[(size_t)oy * Wo + ox], acc);
+            const float* prow_ = p + (size_t)oy * Wo;
+            if (narrow) {
+#pragma unroll
+                for (int k = 0; k < kBlCand; ++k) {
+                    const float wx = wxs[k];
+                    if (wx != 0.f) acc = fmaf(wy * wx, prow_[ox_lo + k], acc);
+                }
+            } else {
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                    const float sx = rx * ox;
+                    const int x0 = (int)sx;
+                    const int x1 = min(x0 + 1, Wi - 1);
+                    const float lx = sx - x0;
+                    float wx = 0.f;
+                    if (x0 == ix) wx += 1.f - lx;
+                    if (x1 == ix) wx += lx;
+                    if (wx == 0.f) continue;
+                    acc = fmaf(wy * wx, prow_[ox], acc);
+                }
             }
         }
         din[i] = acc;
