@@ -123,6 +123,20 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// eight consecutive floats of a 16-byte aligned shared-memory vector as two LDS.128
+__device__ __forceinline__ void lds8(const float* p, float* v) {
+    const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {   // one full warp
@@ -183,6 +197,15 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// SWIZZLE_128B MN-major canonical layout (cute: Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements):
+// a k-row is 128 bytes = 64 consecutive M/N indices, 8 k-rows form a 1024-byte swizzle atom, atoms of the next 8 k-rows
+// are SBO apart, the next 64 M/N indices LBO apart.  layout type 2 in bits [61,64); base_offset (bits [49,52)) = the
+// phase of the start address inside the 1024-byte swizzle pattern when the start is not atom-aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_offset) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
 }
 
 // TMEM -> registers: 32 lanes (this warp's quarter) x 16 consecutive fp32 columns.

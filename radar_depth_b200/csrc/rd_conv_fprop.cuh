@@ -334,10 +334,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
         else if (src_tma_bn && warp != 4) {
             // ---- transform workers (warps 5..11)
-            const int widx = warp - 5, nwork = kFpropLoaderWarps - 1;
+            // A worker thread owns ONE of the two 8-channel chunks of every stage and walks the tile's slots with a fixed
+            // stride: the chunk's scale / shift are read once per stage (not per item), row / column follow incrementally
+            const int t = (warp - 5) * 32 + lane, nthr = (kFpropLoaderWarps - 1) * 32;
             const int cs = p.chunk_stride;                 // = plane_rows * Wl in this mode
-            const int items = 2 * p.plane_rows * p.Wl;
-            const FastDivS fd_cs((uint32_t)cs), fd_wl((uint32_t)p.Wl);
+            const int nslots = p.plane_rows * p.Wl;
+            const int j = t & 1, s0 = t >> 1, tpc = nthr >> 1;
+            const int r0 = s0 / p.Wl, c0 = s0 - r0 * p.Wl, dr = tpc / p.Wl, dc = tpc - dr * p.Wl;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int trem = tile - img * tiles_per_img;
@@ -345,27 +348,29 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                 const int yb = ty * p.Ht + p.sy_min, xb = tx * p.Wt + p.sx_min;
                 (void)img;
                 for (int c = 0; c < ncblk; ++c) {
+                    float scv[8], shv[8];
+                    lds8(ld_sc + c * 16 + j * 8, scv);
+                    lds8(ld_sh + c * 16 + j * 8, shv);
                     mbar_wait(&tma_full[st.stage], st.phase, 0x120 + st.stage);
-                    uint8_t* sbase = a_ring + (size_t)st.stage * p.istage_bytes;
+                    uint4* sbase = reinterpret_cast<uint4*>(a_ring + (size_t)st.stage * p.istage_bytes) + j * cs;
                     if (!(p.dbg_flags & 2)) {
-                        for (int it = widx * 32 + lane; it < items; it += nwork * 32) {
-                            const int j = (int)fd_cs.div((uint32_t)it), sl = it - j * cs;
-                            const int r = (int)fd_wl.div((uint32_t)sl), cx = sl - r * p.Wl;
+                        int r = r0, cx = c0;
+                        for (int sl = s0; sl < nslots; sl += tpc) {
                             const int iy = yb + r, ix = xb + cx;
-                            if (iy < 0 || iy >= p.srcH || ix < 0 || ix >= p.srcW) continue;     // zero padding stays zero
-                            uint4* d = reinterpret_cast<uint4*>(sbase) + it;
-                            uint4 u = *d;
-                            const float* sc = ld_sc + c * 16 + j * 8;
-                            const float* sh = ld_sh + c * 16 + j * 8;
-                            float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+                            if (iy >= 0 && iy < p.srcH && ix >= 0 && ix < p.srcW) {          // zero padding stays zero
+                                uint4 u = sbase[sl];
+                                float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float y = fmaf(v[k], sc[k], sh[k]);
-                                v[k] = y > 0.f ? y : y * p.ld_slope;
+                                for (int k = 0; k < 8; ++k) {
+                                    const float y = fmaf(v[k], scv[k], shv[k]);
+                                    v[k] = y > 0.f ? y : y * p.ld_slope;
+                                }
+                                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                                sbase[sl] = u;
                             }
-                            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                            *d = u;
+                            r += dr; cx += dc;
+                            if (cx >= p.Wl) { cx -= p.Wl; ++r; }
                         }
                     }
                     __syncwarp();

@@ -13,6 +13,7 @@
 #pragma once
 #include "rd_common.cuh"
 #include "rd_tile.cuh"
+#include "rd_conv_fprop.cuh"      // umma_bf16_elected
 #include "../../include/radar_depth_b200.h"
 
 namespace rd {
@@ -95,6 +96,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     // tile's pixels and must be cleared before the contraction: the TMA lands on tma_full[stage], the worker warps then
     // zero those columns and arrive on full[stage].
     const bool g_tma = (tma_mode & 1) != 0, x_tma = (tma_mode & 2) != 0, any_tma = g_tma || x_tma;
+    // tma_mode & 4 (with 1 and 2): both tiles land as 128-byte-swizzled [slot][64 channels] blocks -- the TMA box's inner
+    // dimension is a whole 128-byte run of the NHWC pixel instead of a 16-byte granule (4-8x the box rate, no half-used
+    // sectors), and the blocks ARE the SWIZZLE_128B MN-major canonical layout: slot = k-row, a tap is still a start-address
+    // shift (whole 128-byte rows).  Block strides: KS slots (gradient: copies, then 64-channel blocks) and x_plane_slots.
+    const bool sw = (tma_mode & 4) != 0, sw_bo = (tma_mode & 8) != 0;
+    const int g_blocks = p.Mc >> 6, x_blocks = p.Nc >> 6;
+    const uint32_t GB = (uint32_t)p.KS * 128u, XB = (uint32_t)p.x_plane_slots * 128u;
     const bool g_async = (SPLIT == 1) && (sizeof(T) == 2) && !g_tma;
     const bool x_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr) && !x_tma;
     const bool g_reg = !g_tma && !g_async, x_reg = !x_tma && !x_async;
@@ -145,6 +153,23 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         const int widx = any_tma ? warp - 5 : warp - 4;
         const int g_planes = p.Sg * p.Sg;
         const uint32_t g_tx = (uint32_t)(g_planes * p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)(p.Wl * p.x_plane_rows * x_chunks * 16);
+        // in-place BatchNorm transform (x_bn): this thread's chunk, first slot and slot stride
+        int bn_j = -1, bn_s0 = 0, bn_tpc = 1, bn_r0 = 0, bn_c0 = 0, bn_dr = 0, bn_dc = 0;
+        float bn_sc[8], bn_sh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { bn_sc[k] = 1.f; bn_sh[k] = 0.f; }
+        if (x_bn && widx >= 0) {
+            const int t = widx * 32 + lane;
+            bn_tpc = (nworkers * 32) / x_chunks;
+            if (t < bn_tpc * x_chunks) {
+                bn_j = t % x_chunks;
+                bn_s0 = t / x_chunks;
+                bn_r0 = bn_s0 / p.Wl; bn_c0 = bn_s0 - bn_r0 * p.Wl;
+                bn_dr = bn_tpc / p.Wl; bn_dc = bn_tpc - bn_dr * p.Wl;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { bn_sc[k] = ld_sc[ci0 + bn_j * 8 + k]; bn_sh[k] = ld_sh[ci0 + bn_j * 8 + k]; }
+            }
+        }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             const int trem = tile - img * tiles_per_img;
@@ -160,6 +185,14 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     uint64_t* bar = hop ? &tma_full[st.stage] : &full[st.stage];
                     if (!(p.dbg_flags & 2)) {
                         mbar_arrive_expect_tx(bar, (g_tma ? g_tx * (uint32_t)Rload : 0u) + (x_tma ? x_tx : 0u));
+                        if (sw) {
+                            for (int r = 0; r < Rload; ++r)
+                                for (int b = 0; b < g_blocks; ++b)
+                                    tma_load_4d(sbase + (size_t)(r * g_blocks + b) * GB, &g_map, co0 + b * 64,
+                                                x0 + (Rload > 1 ? p.gcopy_dx[r] : 0), y0 + (Rload > 1 ? p.gcopy_dy[r] : 0), img, bar);
+                            for (int b = 0; b < x_blocks; ++b)
+                                tma_load_4d(sbase + p.g_bytes + (size_t)b * XB, &x_map, ci0 + b * 64, x0 + p.sx_min, y0 + p.sy_min, img, bar);
+                        } else
                         if (g_tma && Rload > 1) {
                             for (int r = 0; r < Rload; ++r)          // copy r: the same box, (dy, dx) pixels further
                                 tma_load_5d(sbase + (size_t)r * g_chunks * p.KS * 16, &g_map, 0, x0 + p.gcopy_dx[r], y0 + p.gcopy_dy[r],
@@ -169,7 +202,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                                 tma_load_5d(sbase + (size_t)q * g_chunks * p.KS * 16, &g_map, 0, x0 * p.Sg + (q & (p.Sg - 1)),
                                             y0 * p.Sg + (q >> (p.Sg >> 1)), co0 >> 3, img, bar);
                         }
-                        if (x_tma) tma_load_5d(sbase + p.g_bytes, &x_map, 0, x0 + p.sx_min, y0 + p.sy_min, ci0 >> 3, img, bar);
+                        if (x_tma && !sw) tma_load_5d(sbase + p.g_bytes, &x_map, 0, x0 + p.sx_min, y0 + p.sy_min, ci0 >> 3, img, bar);
                     } else {
                         mbar_arrive(bar);
                     }
@@ -190,27 +223,40 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             }
             if (hop) mbar_wait(&tma_full[st.stage], st.phase, 0x520 + st.stage);
             if (x_bn && !(p.dbg_flags & 2)) {
-                // fused BatchNorm + activation of the source tile, in place (zero padding stays zero)
-                const int xitems = x_chunks * XPS;               // XPS = x_plane_rows * Wl in this mode
-                const FastDivS fd_xps((uint32_t)XPS), fd_wl((uint32_t)p.Wl);
-                uint4* xb = reinterpret_cast<uint4*>(sbase + p.g_bytes);
-                for (int it = widx * 32 + lane; it < xitems; it += nworkers * 32) {
-                    const int j = (int)fd_xps.div((uint32_t)it), sl = it - j * XPS;
-                    const int r = (int)fd_wl.div((uint32_t)sl), cx = sl - r * p.Wl;
-                    const int iy = y0 + p.sy_min + r, ix = x0 + p.sx_min + cx;
-                    if (iy < 0 || iy >= p.xH || ix < 0 || ix >= p.xW) continue;
-                    uint4 u = xb[it];
-                    const float* sc = ld_sc + ci0 + j * 8;
-                    const float* sh = ld_sh + ci0 + j * 8;
-                    float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+                // fused BatchNorm + activation of the source tile, in place (zero padding stays zero).  A worker thread owns
+                // ONE 8-channel chunk for the whole kernel (its scale / shift live in registers) and walks the tile's slots
+                // with a fixed stride: row / column follow incrementally, no per-item division or coefficient load
+                // (the per-item form cost 30 us of 106 on the layer1 shape, tools/check_wgrad_sw128.py bn=1 vs bn=0).
+                if (bn_j >= 0) {
+                    uint8_t* xbase = sbase + p.g_bytes;
+                    const uint32_t xaddr = smem_u32(xbase);
+                    int r = bn_r0, cx = bn_c0;
+                    for (int sl = bn_s0; sl < XPS; sl += bn_tpc) {
+                        const int iy = y0 + p.sy_min + r, ix = x0 + p.sx_min + cx;
+                        if (iy >= 0 && iy < p.xH && ix >= 0 && ix < p.xW) {
+                            uint32_t off;
+                            if (sw) {
+                                // swizzled blocks: unit (j & 7) of a slot sits at unit (j & 7) ^ (address bits [7,10)) of its row
+                                const uint32_t row = (uint32_t)(bn_j >> 3) * XB + (uint32_t)sl * 128u;
+                                off = row + ((((uint32_t)bn_j & 7u) ^ (((xaddr + row) >> 7) & 7u)) << 4);
+                            } else {
+                                off = (uint32_t)(bn_j * XPS + sl) << 4;
+                            }
+                            uint4* xp = reinterpret_cast<uint4*>(xbase + off);
+                            uint4 u = *xp;
+                            float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float y = fmaf(v[k], sc[k], sh[k]);
-                        v[k] = y > 0.f ? y : y * p.ld_slope;
+                            for (int k = 0; k < 8; ++k) {
+                                const float y = fmaf(v[k], bn_sc[k], bn_sh[k]);
+                                v[k] = y > 0.f ? y : y * p.ld_slope;
+                            }
+                            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                            *xp = u;
+                        }
+                        r += bn_dr; cx += bn_dc;
+                        if (cx >= p.Wl) { cx -= p.Wl; ++r; }
                     }
-                    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                    xb[it] = u;
                 }
             }
             if (g_tma) {
@@ -221,7 +267,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 for (int it = widx * 32 + lane; it < items; it += nworkers * 32) {
                     const int q = (int)fd_jc.div((uint32_t)it), c = it - q * jc;
                     const int j = (int)fd_ht.div((uint32_t)q), r = q - j * p.Ht;
-                    *reinterpret_cast<uint4*>(sbase + ((size_t)(j * GPS + r * p.Wl + p.Wt + c) << 4)) = make_uint4(0, 0, 0, 0);
+                    // (swizzled blocks: the 8 units of a junk slot are cleared by the 8 values j & 7 -- any order)
+                    const size_t off = sw ? (size_t)(j >> 3) * GB + (size_t)(r * p.Wl + p.Wt + c) * 128 + (size_t)(j & 7) * 16
+                                          : ((size_t)(j * GPS + r * p.Wl + p.Wt + c) << 4);
+                    *reinterpret_cast<uint4*>(sbase + off) = make_uint4(0, 0, 0, 0);
                 }
             }
             if (warp_arrives) {
@@ -238,9 +287,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             }
         }
     } else if (warp == kWarpMma) {
-        // ================= UMMA issuer: the whole warp walks the loops (uniform values), one elected lane issues
-        {
-            const bool leader = elect_one_sync();
+        // ================= UMMA issuer: ONE elected thread runs the whole loop (waits, UMMAs, commits).  Inside the election
+        // branch ptxas keeps descriptors in uniform registers and emits bare UTCHMMAs (rd_conv_fprop.cuh, fprop_issue); with
+        // the whole warp walking the loops and a per-UMMA `if (leader)` the loop alone cost ~40 cycles per UMMA slot
+        // (tools/bench_wgrad.py, "neither" mode: 67 of 79 us on the layer1 shape with loads AND UMMAs switched off).
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (elect_one_sync()) {
             PipeState st(p.NS);
             // tap-row folding (see rd_wgrad_params.fold_rows): a job = one row of taps x one 8-channel source chunk
             const bool fold = (SPLIT == 1) && p.fold_len > 0;
@@ -248,8 +300,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             const uint32_t idesc = make_idesc_bf16(128, fold ? 32 : p.Nc, 1, 1);
             const uint32_t g_sbo = (uint32_t)GPS * 16u, x_sbo = fold ? 16u : (uint32_t)XPS * 16u;
             const int KG = p.KS >> 4;
-            bool first_tile = true;
-            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const bool do_issue = !(p.dbg_flags & 1);
+            const uint32_t kstep = sw ? 128u : 16u;            // 16 slots in 16-byte units: 128-byte rows when swizzled
+            const uint32_t lo_b = (uint32_t)x_chunks * (uint32_t)XPS, lo_a = (uint32_t)g_chunks * (uint32_t)GPS;   // fp32 split: low parts
+            uint32_t acc0 = 0u;                                // the first tile overwrites the accumulators
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const long long tm0 = p.dbg ? clock64() : 0;
                 mbar_wait(&full[st.stage], st.phase, 0x510 + st.stage);
@@ -257,40 +311,42 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 fence_proxy_async_smem();          // consumer-side: loaders' generic-proxy writes -> async proxy (UMMA)
                 tc_fence_after();
                 const uint32_t g_base = smem_u32(ring + (size_t)st.stage * p.stage_bytes);
-                const uint64_t da0 = make_smem_desc(g_base, 128, g_sbo);
-                const uint64_t db0 = make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
+                const uint64_t da0 = sw ? make_smem_desc_sw128(g_base, GB, 1024u, 0u) : make_smem_desc(g_base, 128, g_sbo);
+                const uint64_t db0 = sw ? make_smem_desc_sw128(g_base + (uint32_t)p.g_bytes, XB, 1024u, 0u)
+                                        : make_smem_desc(g_base + (uint32_t)p.g_bytes, 128, x_sbo);
                 // tap-outer / k-group-inner: inside the inner loop the descriptors only advance by 16 slots, so one
                 // UMMA costs two uniform adds; the tap offsets come from the (uniform) parameter bank once per tap
+                if (do_issue)
                 for (int jb = 0; jb < njobs; ++jb) {
                     const int tl = fold ? (R > 1 ? (jb >> 1) : (jb >> 1) * p.fold_len) : jb;   // x_chunks == 2 when folding
                     const uint32_t d = tmem_u + (uint32_t)(fold ? jb * 32 : jb * p.Nc);
                     uint64_t da = da0 + (uint32_t)p.taps[t0 + tl].g_off;
-                    uint64_t db = db0 + (uint32_t)p.taps[t0 + tl].x_shift + (uint32_t)(fold ? (jb & 1) * XPS : 0);
-                    if (leader && !(p.dbg_flags & 1)) {
-                        umma_bf16(d, da, db, idesc, first_tile ? 0u : 1u);
-                        if (SPLIT == 3) {
-                            umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
-                            umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
-                        }
-                    }
+                    // swizzled blocks: a shift of s slots = s 128-byte rows.  The hardware swizzles on absolute shared-memory
+                    // address bits, so a start address at any row phase of the 1024-byte pattern reads what TMA wrote
+                    // (base_offset stays 0; setting it to the phase, tma_mode & 8, was measured WRONG)
+                    uint64_t db = db0 + (sw ? (uint32_t)p.taps[t0 + tl].x_shift * 8u
+                                            : (uint32_t)p.taps[t0 + tl].x_shift + (uint32_t)(fold ? (jb & 1) * XPS : 0));
+                    if (sw && sw_bo) db |= (uint64_t)(((g_base + (uint32_t)p.g_bytes + (uint32_t)p.taps[t0 + tl].x_shift * 128u) >> 7) & 7u) << 49;
+                    if (SPLIT == 1) {
+                        umma_bf16_elected(d, da, db, idesc, acc0);
 #pragma unroll 4
-                    for (int kg = 1; kg < KG; ++kg) {
-                        da += 16;
-                        db += 16;
-                        if (leader && !(p.dbg_flags & 1)) {
-                            umma_bf16(d, da, db, idesc, 1u);
-                            if (SPLIT == 3) {
-                                umma_bf16(d, da, db + (uint32_t)x_chunks * (uint32_t)XPS, idesc, 1u);
-                                umma_bf16(d, da + (uint32_t)g_chunks * (uint32_t)GPS, db, idesc, 1u);
-                            }
+                        for (int kg = 1; kg < KG; ++kg) {
+                            da += kstep;
+                            db += kstep;
+                            umma_bf16_elected(d, da, db, idesc, 1u);
+                        }
+                    } else {
+                        for (int kg = 0; kg < KG; ++kg, da += 16u, db += 16u) {
+                            umma_bf16_elected(d, da, db, idesc, kg == 0 ? acc0 : 1u);
+                            umma_bf16_elected(d, da, db + lo_b, idesc, 1u);
+                            umma_bf16_elected(d, da + lo_a, db, idesc, 1u);
                         }
                     }
                 }
-                __syncwarp();
-                if (leader) umma_commit(&empty[st.stage]);
+                umma_commit(&empty[st.stage]);
                 st.advance();
-                first_tile = false;
-                if (p.dbg && lane == 0) {
+                acc0 = 1u;
+                if (p.dbg) {
                     const long long tm2 = clock64();
                     if (tl_mode) {
                         if (tile == (int)blockIdx.x) p.dbg[0 * dbg_ncta + dbg_cta] = tm1 - t_entry;
@@ -301,7 +357,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     }
                 }
             }
-            if (leader) umma_commit(tmem_full);
+            umma_commit(tmem_full);
         }
         __syncwarp();
     } else {

@@ -237,11 +237,6 @@ __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int cg, in
 // bn_add_act: out = act( z*sc + sh + identity )   -- the residual join of BasicBlock (models.py:104-110) and
 // UpProjModule (models.py:205-208).  identity is either a materialised activation (id_sc == nullptr) or another
 // raw conv output with its own BN (downsample branch / bottom branch).  With idv.ptr == nullptr: plain BN+act.
-// eight consecutive floats of a 16-byte aligned shared-memory vector as two LDS.128
-__device__ __forceinline__ void lds8(const float* p, float* v) {
-    const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-}
 
 // Per-channel vectors are staged in shared memory once per block (two LDS.128 per vector and item instead of eight
 // L1 loads per vector), and every thread keeps TWO items (four 16-byte loads) in flight per iteration: with one item
