@@ -516,12 +516,16 @@ def _gcopy_layout(g: GConv, taps, Mc: int, parts: int):
 
 
 def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_target: int = 256,
-               nc: Optional[int] = None, use_tuned: bool = True, sm_budget: int = NUM_SMS, gcopy: Optional[bool] = None) -> WgradPlan:
+               nc: Optional[int] = None, use_tuned: bool = True, sm_budget: int = NUM_SMS, gcopy: Optional[bool] = None,
+               bn: bool = False) -> WgradPlan:
     """x_hw: spatial size of the source activation; g_hw: spatial size of the output gradient.
-    gcopy: stack shifted copies of the gradient tile in M where the layer allows it (None: measured table, else on)."""
+    gcopy: stack shifted copies of the gradient tile in M where the layer allows it (None: measured table, else on).
+    bn: the launch applies the producer's BatchNorm + activation to the source tile in shared memory (every tap group
+    repeats that pass, so the measured table may hold a different blocking under key + "|bn")."""
     assert g.Cx % 16 == 0 and g.N % 8 == 0
     if use_tuned and nc is None:
-        t = tuned_table().get(tune_key("w", g, B, x_hw, g_hw, act_dtype))
+        key = tune_key("w", g, B, x_hw, g_hw, act_dtype)
+        t = (tuned_table().get(key + "|bn") if bn else None) or tuned_table().get(key)
         if t:
             nc, ks_target = t["nc"], t["ks"]
             if gcopy is None and "gc" in t:
@@ -583,7 +587,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
         if best is not None:
             break
     if best is None and R > 1:
-        return plan_wgrad(g, B, x_hw, g_hw, act_dtype, ks_target, nc, use_tuned, sm_budget, gcopy=False)
+        return plan_wgrad(g, B, x_hw, g_hw, act_dtype, ks_target, nc, use_tuned, sm_budget, gcopy=False, bn=bn)
     if best is None:
         raise ValueError("no feasible wgrad tile")
     ncib = g.Cx // Nc

@@ -243,6 +243,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// BatchNorm + (leaky) ReLU of 8 packed bf16 channels: fp32 fma, round to bf16, then -- for slope 0 -- the ReLU as a packed
+// bf16x2 max (max commutes with the rounding, so the bits equal the fp32 select except for the sign of a zero; NaN propagates); the
+// leaky form keeps the fp32 select.  `relu` must be warp-uniform.
+__device__ __forceinline__ uint4 bn_act8(uint4 u, const float* sc, const float* sh, float slope, bool relu) {
+    float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+    uint4 o;
+    if (relu) {
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t* w = &o.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 m = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&w[q]), zero);
+            w[q] = *reinterpret_cast<const uint32_t*>(&m);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    }
+    return o;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

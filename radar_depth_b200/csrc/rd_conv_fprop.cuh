@@ -358,16 +358,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                         for (int sl = s0; sl < nslots; sl += tpc) {
                             const int iy = yb + r, ix = xb + cx;
                             if (iy >= 0 && iy < p.srcH && ix >= 0 && ix < p.srcW) {          // zero padding stays zero
-                                uint4 u = sbase[sl];
-                                float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    const float y = fmaf(v[k], scv[k], shv[k]);
-                                    v[k] = y > 0.f ? y : y * p.ld_slope;
-                                }
-                                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                                sbase[sl] = u;
+                                sbase[sl] = bn_act8(sbase[sl], scv, shv, p.ld_slope, p.ld_slope == 0.f);
                             }
                             r += dr; cx += dc;
                             if (cx >= p.Wl) { cx -= p.Wl; ++r; }

@@ -243,16 +243,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                                 off = (uint32_t)(bn_j * XPS + sl) << 4;
                             }
                             uint4* xp = reinterpret_cast<uint4*>(xbase + off);
-                            uint4 u = *xp;
-                            float v[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y), bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float y = fmaf(v[k], bn_sc[k], bn_sh[k]);
-                                v[k] = y > 0.f ? y : y * p.ld_slope;
-                            }
-                            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                            *xp = u;
+                            *xp = bn_act8(*xp, bn_sc, bn_sh, p.ld_slope, p.ld_slope == 0.f);
                         }
                         r += bn_dr; cx += bn_dc;
                         if (cx >= p.Wl) { cx -= p.Wl; ++r; }

@@ -516,16 +516,28 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
         scv[0] = s0.x; scv[1] = s0.y; scv[2] = s0.z; scv[3] = s0.w; scv[4] = s1.x; scv[5] = s1.y; scv[6] = s1.z; scv[7] = s1.w;
         shv[0] = h0.x; shv[1] = h0.y; shv[2] = h0.z; shv[3] = h0.w; shv[4] = h1.x; shv[5] = h1.y; shv[6] = h1.z; shv[7] = h1.w;
     }
-    int j = 0;
-    for (int it = threadIdx.x; it < kMpInH * kMpInW * G; it += blockDim.x, ++j) {
-        // position 32 j + pc0 = 33 j + (pc0 - j) of the 33-wide tile (j <= 2 TH <= 8 < 32)
+    // All loads of the thread are issued before the first is consumed (NIT independent 16-byte requests in flight per
+    // thread): with load -> transform -> store per iteration a block paid one memory latency per item.
+    constexpr int kPos = kMpInH * kMpInW, NIT = (kPos + 31) / 32;
+    uint4 raw[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+        // position 32 j + pc0 = 33 j + (pc0 - j) of the 33-wide tile (j <= 2 TH + 1 < 32)
         const int r = pc0 >= j ? j : j - 1, cx = pc0 >= j ? pc0 - j : pc0 - j + kMpInW;
         const int iy = iy0 + r, ix = ix0 + cx;
+        raw[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (32 * j + pc0 < kPos && iy >= 0 && iy < H && ix >= 0 && ix < W)
+            raw[j] = __ldg(reinterpret_cast<const uint4*>(zp + (((size_t)b * H + iy) * W + ix) * z.pitch + z.coff + c));
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+        if (32 * j + pc0 >= kPos) break;
+        const int r = pc0 >= j ? j : j - 1, cx = pc0 >= j ? pc0 - j : pc0 - j + kMpInW;
+        const int iy = iy0 + r, ix = ix0 + cx;
+        const int it = threadIdx.x + j * blockDim.x;
         uint4 u = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // -inf: never selected
-        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            raw = __ldg(reinterpret_cast<const uint4*>(zp + (((size_t)b * H + iy) * W + ix) * z.pitch + z.coff + c));
-            float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
+            float v[8] = {bf16lo(raw[j].x), bf16hi(raw[j].x), bf16lo(raw[j].y), bf16hi(raw[j].y), bf16lo(raw[j].z), bf16hi(raw[j].z), bf16lo(raw[j].w), bf16hi(raw[j].w)};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float y = fmaf(v[k], scv[k], shv[k]);
@@ -535,7 +547,7 @@ __global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, c
             u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
         }
         mp_tile[it] = u;
-        if (zarg) raw_tile[it] = raw;
+        if (zarg) raw_tile[it] = raw[j];
     }
     __syncthreads();
     const FastDiv fdt((uint32_t)kMpTileW);

@@ -274,7 +274,7 @@ class LatefusionEngine:
                         d=dict(flops=2.0 * B * dpp.Hb * dpp.Wb * nnz, bytes=in_b + out_b + 2 * nnz) if dpp is not None else None,
                         w=dict(flops=2.0 * B * fpp.Hb * fpp.Wb * nnz, bytes=in_b + out_b + 4 * nnz))
             rec = dict(name=name, g=g, fplan=fplan, dplan=dplan, wplan=wplan, f_off=f_off, d_off=d_off, w_off=w_off, work=work,
-                       lane=(lane or 0) if par else 0)
+                       lane=(lane or 0) if par else 0, wargs=(src_hw, dst_hw, tuned, sms))
             self.convs.append(rec)
             return rec
 
@@ -313,6 +313,16 @@ class LatefusionEngine:
 
         def emit_wgrad(prog, rec, gy: View, x: View, ld=None):
             plan = rec["wplan"]
+            if ld is not None and not self.det:
+                # launches that transform the source tile in shared memory may have their own measured blocking (the dw
+                # layout does not depend on it)
+                if "wplan_bn" not in rec:
+                    src_hw, dst_hw, tuned, sms = rec["wargs"]
+                    has = tuned and (cp.tune_key("w", rec["g"], B, src_hw, dst_hw, act) + "|bn") in cp.tuned_table()
+                    rec["wplan_bn"] = cp.plan_wgrad(rec["g"], B, src_hw, dst_hw, act, use_tuned=True, sm_budget=sms, bn=True) if has else None
+                if rec["wplan_bn"] is not None:
+                    plan = rec["wplan_bn"]
+                    assert plan.dw_elems == rec["wplan"].dw_elems
             p = type(plan.params).from_buffer_copy(plan.params)
             p.gy, p.x = gy, x
             if ld is not None:

@@ -87,6 +87,20 @@ def test_every_timed_conv_program_matches_the_torch_evaluation():
             r = _rel(grad, ref)
             worst.append((r, key))
             assert r < 8e-3, (name, key, r)
+            if key + "|bn" in table:
+                # the blocking the engine uses when the launch applies the producer's BatchNorm + ReLU to the source tile
+                plan_bn = cp.plan_wgrad(g, B, s_hw, d_hw, _lib.RD_BF16, use_tuned=True, bn=True)
+                sc = torch.rand(g.Cx, device="cuda", generator=gen) + 0.5
+                sh = torch.randn(g.Cx, device="cuda", generator=gen) * 0.3
+                dw.zero_()
+                ops.conv_wgrad(plan_bn, ops.view(dy), ops.view(x), dw, ld=(sc, sh, 0.0))
+                assert ops.device_error() == 0, key
+                grad.zero_()
+                grad[torch.from_numpy(plan_bn.scatter[0]).cuda()] = dw[torch.from_numpy(plan_bn.scatter[1]).cuda()]
+                ref = cp.gconv_wgrad_reference(g, torch.relu(x.float() * sc + sh).bfloat16().float(), dy.float(), npar)
+                r = _rel(grad, ref)
+                worst.append((r, key + "|bn"))
+                assert r < 8e-3, (name, key + "|bn", r)
             del dy, dw, ref
         del x, w
     worst.sort(reverse=True)

@@ -15,6 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 352
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 1216
 CIN = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+KINDS = os.environ.get("RD_TUNE_KINDS", "fw")       # "w": re-measure the weight-gradient entries only
 act = _lib.RD_BF16
 table = cp.tuned_table().copy()
 cp._TUNED = {}                       # plan from the cost model while tuning
@@ -83,7 +84,7 @@ for rec in eng.convs:
     jobs = [("f", g, src_hw, dst_hw)]
     if rec["dplan"] is not None:
         jobs.append(("f", g.transposed(), dst_hw, src_hw))
-    for kind, gg, s_hw, d_hw in jobs:
+    for kind, gg, s_hw, d_hw in (jobs if "f" in KINDS else []):
         key = cp.tune_key(kind, gg, B, s_hw, d_hw, act)
         if key in seen:
             continue
@@ -128,50 +129,55 @@ for rec in eng.convs:
             continue
         table[key] = best[1]
         print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
-    if rec["wplan"] is not None:
+    if rec["wplan"] is not None and "w" in KINDS:
         key = cp.tune_key("w", g, B, src_hw, dst_hw, act)
         if key in seen:
             continue
         seen.add(key)
         x = torch.randn(B, src_hw[0], src_hw[1], g.Cx, device="cuda").bfloat16()
         dy = torch.randn(B, dst_hw[0], dst_hw[1], g.N, device="cuda").bfloat16()
-        best, base = None, None
         npar = int(max(int(t.widx.max()) for t in g.taps)) + 1
-        ref = cp.gconv_wgrad_reference(g, x.float(), dy.float(), npar)
-        for gc, nc, ks in [(gc_, nc_, ks_) for gc_ in (True, False) for nc_ in (None, 16, 32, 64, 128) for ks_ in (128, 192, 256, 384, 512)]:
-            if True:
-                if nc is not None and (nc > g.Cx or g.Cx % nc):
-                    continue
-                try:
-                    plan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, ks_target=ks, nc=nc, use_tuned=False, gcopy=gc)
-                except Exception:
-                    continue
-                if (not gc) and False:
-                    continue
-                if gc and plan.params.gcopies == 0:
-                    continue                                   # not eligible: the gc=False pass measures it
-                dw = torch.zeros(plan.dw_elems, device="cuda")
-                try:
-                    ms = time_launch(lambda: ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw))
-                except Exception:
-                    continue
-                grad = torch.zeros(npar, dtype=torch.float32, device="cuda")
-                dw.zero_()
-                ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw)
-                grad[torch.from_numpy(plan.scatter[0]).cuda()] = dw[torch.from_numpy(plan.scatter[1]).cuda()]
-                rel = float((grad - ref).norm() / (ref.norm() + 1e-20))
-                if not rel < 8e-3:
-                    print(f"  REJECTED {key} nc={nc} ks={ks}: rel-L2 {rel:.3e}", flush=True)
-                    continue
-                if nc is None and ks == 256:
-                    base = ms
-                if best is None or ms < best[0]:
-                    best = (ms, dict(nc=plan.info["Nc"], ks=ks, gc=int(plan.params.gcopies > 1)))
-        if best is None:
-            print(f"{rec['name']:42s} {key:70s} NO VALID CANDIDATE", flush=True)
-            continue
-        table[key] = best[1]
-        print(f"{rec['name']:42s} {key:70s} model {(base or best[0]) * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
+        # second pass (key + "|bn") for stride-1 sources: the launch transforms the source tile in shared memory, once per tap group
+        sc_ = (torch.rand(g.Cx, device="cuda") + 0.5)
+        sh_ = torch.randn(g.Cx, device="cuda") * 0.3
+        for ld, key in ((None, key), ((sc_, sh_, 0.0), key + "|bn")) if (g.S == 1 and g.Cx >= 32) else ((None, key),):
+            best, base = None, None
+            xr = x.float() if ld is None else torch.relu(x.float() * sc_ + sh_).bfloat16().float()
+            ref = cp.gconv_wgrad_reference(g, xr, dy.float(), npar)
+            for gc, nc, ks in [(gc_, nc_, ks_) for gc_ in (True, False) for nc_ in (None, 16, 32, 64, 128, 256) for ks_ in (128, 192, 256, 384, 512)]:
+                if True:
+                    if nc is not None and (nc > g.Cx or g.Cx % nc):
+                        continue
+                    try:
+                        plan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, ks_target=ks, nc=nc, use_tuned=False, gcopy=gc)
+                    except Exception:
+                        continue
+                    if (not gc) and False:
+                        continue
+                    if gc and plan.params.gcopies == 0:
+                        continue                                   # not eligible: the gc=False pass measures it
+                    dw = torch.zeros(plan.dw_elems, device="cuda")
+                    try:
+                        ms = time_launch(lambda: ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, ld=ld))
+                    except Exception:
+                        continue
+                    grad = torch.zeros(npar, dtype=torch.float32, device="cuda")
+                    dw.zero_()
+                    ops.conv_wgrad(plan, ops.view(dy), ops.view(x), dw, ld=ld)
+                    grad[torch.from_numpy(plan.scatter[0]).cuda()] = dw[torch.from_numpy(plan.scatter[1]).cuda()]
+                    rel = float((grad - ref).norm() / (ref.norm() + 1e-20))
+                    if not rel < 8e-3:
+                        print(f"  REJECTED {key} nc={nc} ks={ks}: rel-L2 {rel:.3e}", flush=True)
+                        continue
+                    if nc is None and ks == 256:
+                        base = ms
+                    if best is None or ms < best[0]:
+                        best = (ms, dict(nc=plan.info["Nc"], ks=ks, gc=int(plan.params.gcopies > 1)))
+            if best is None:
+                print(f"{rec['name']:42s} {key:70s} NO VALID CANDIDATE", flush=True)
+                continue
+            table[key] = best[1]
+            print(f"{rec['name']:42s} {key:70s} model {(base or best[0]) * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/tuned_tiles.json", "w") as f:
     json.dump(table, f, indent=0, sort_keys=True)
