@@ -123,14 +123,14 @@ bool encode_nhwc_map(CUtensorMap* map, const rd_view& v, int B, int H, int W, in
 
 // The same view as the 4-D tensor (C, W, H, B) with box (64 channels, box_w, box_rows, 1) and 128-byte swizzle: a box row
 // is ONE 128-byte run per pixel and lands as the SWIZZLE_128B MN-major operand layout of the weight-gradient kernel.
-bool encode_nhwc_map_sw128(CUtensorMap* map, const rd_view& v, int B, int H, int W, int C, int box_w, int box_rows) {
+bool encode_nhwc_map_sw128(CUtensorMap* map, const rd_view& v, int B, int H, int W, int C, int box_w, int box_rows, int step = 1) {
     TmapEncodeFn enc = tmap_encoder();
-    if (!enc || box_w > 256 || box_rows > 256 || C % 64) return false;
+    if (!enc || box_w * step > 256 || box_rows * step > 256 || C % 64) return false;
     const cuuint64_t pitch_b = (cuuint64_t)v.pitch * 2;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {pitch_b, (cuuint64_t)W * pitch_b, (cuuint64_t)H * W * pitch_b};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(box_w * step), (cuuint32_t)(box_rows * step), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)step, (cuuint32_t)step, 1};
     void* base = (void*)((char*)v.ptr + (size_t)v.coff * 2);
     if (((uintptr_t)base & 15) || (pitch_b & 15)) return false;
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

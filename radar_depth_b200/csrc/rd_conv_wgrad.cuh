@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
     // shift (whole 128-byte rows).  Block strides: KS slots (gradient: copies, then 64-channel blocks) and x_plane_slots.
     const bool sw = (tma_mode & 4) != 0, sw_bo = (tma_mode & 8) != 0;
     const int g_blocks = p.Mc >> 6, x_blocks = p.Nc >> 6;
-    const uint32_t GB = (uint32_t)p.KS * 128u, XB = (uint32_t)p.x_plane_slots * 128u;
+    // Parity planes (stride-2 gradient of the sub-pixel programs / stride-2 source) are boxes with element stride 2 that land
+    // one after the other: gradient [plane][copy][block], source [block][plane].
+    const int x_npl = (p.Sx == 1) ? 1 : (p.x_planes > 0 ? p.x_planes : p.Sx * p.Sx);
+    const uint32_t GB = (uint32_t)p.KS * 128u, XPL = (uint32_t)p.x_plane_slots * 128u, XB = (uint32_t)x_npl * XPL;
     const bool g_async = (SPLIT == 1) && (sizeof(T) == 2) && !g_tma;
     const bool x_async = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale == nullptr) && !x_tma;
     const bool g_reg = !g_tma && !g_async, x_reg = !x_tma && !x_async;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         // (UMMA warp) after it has observed full[stage]: a producer-side fence would have to drain the copies.
         const int widx = any_tma ? warp - 5 : warp - 4;
         const int g_planes = p.Sg * p.Sg;
-        const uint32_t g_tx = (uint32_t)(g_planes * p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)(p.Wl * p.x_plane_rows * x_chunks * 16);
+        const uint32_t g_tx = (uint32_t)(g_planes * p.Wl * p.Ht * g_chunks * 16), x_tx = (uint32_t)((sw ? x_npl : 1) * p.Wl * p.x_plane_rows * x_chunks * 16);
         // in-place BatchNorm transform (x_bn): this thread's chunk, first slot and slot stride
         int bn_j = -1, bn_s0 = 0, bn_tpc = 1, bn_r0 = 0, bn_c0 = 0, bn_dr = 0, bn_dc = 0;
         float bn_sc[8], bn_sh[8];
@@ -186,12 +189,16 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                     if (!(p.dbg_flags & 2)) {
                         mbar_arrive_expect_tx(bar, (g_tma ? g_tx * (uint32_t)Rload : 0u) + (x_tma ? x_tx : 0u));
                         if (sw) {
-                            for (int r = 0; r < Rload; ++r)
-                                for (int b = 0; b < g_blocks; ++b)
-                                    tma_load_4d(sbase + (size_t)(r * g_blocks + b) * GB, &g_map, co0 + b * 64,
-                                                x0 + (Rload > 1 ? p.gcopy_dx[r] : 0), y0 + (Rload > 1 ? p.gcopy_dy[r] : 0), img, bar);
+                            for (int q = 0; q < g_planes; ++q)
+                                for (int r = 0; r < Rload; ++r)
+                                    for (int b = 0; b < g_blocks; ++b)
+                                        tma_load_4d(sbase + (size_t)((q * Rload + r) * g_blocks + b) * GB, &g_map, co0 + b * 64,
+                                                    x0 * p.Sg + (q & (p.Sg - 1)) + (Rload > 1 ? p.gcopy_dx[r] : 0),
+                                                    y0 * p.Sg + (q >> (p.Sg >> 1)) + (Rload > 1 ? p.gcopy_dy[r] : 0), img, bar);
                             for (int b = 0; b < x_blocks; ++b)
-                                tma_load_4d(sbase + p.g_bytes + (size_t)b * XB, &x_map, ci0 + b * 64, x0 + p.sx_min, y0 + p.sy_min, img, bar);
+                                for (int q = 0; q < x_npl; ++q)
+                                    tma_load_4d(sbase + p.g_bytes + (size_t)b * XB + (size_t)q * XPL, &x_map, ci0 + b * 64,
+                                                (x0 + p.sx_min) * p.Sx + (q & (p.Sx - 1)), (y0 + p.sy_min) * p.Sx + (q >> (p.Sx >> 1)), img, bar);
                         } else
                         if (g_tma && Rload > 1) {
                             for (int r = 0; r < Rload; ++r)          // copy r: the same box, (dy, dx) pixels further
