@@ -241,6 +241,16 @@ int rd_conv_wgrad(const rd_wgrad_params* p, void* stream);
  * x[:, :3] / x[:, 3:] slicing at models.py:633,643 and multistage_model.py:236-241. */
 int rd_input_pack(const float* x, void* out, int B, int C, int H, int W, int Cs, int act_dtype, void* stream);
 
+/* The same packing with channel c read from planes[c] (fp32 [H][W] plane of image 0, image b at + b * batch_strides[c]
+ * elements): replaces torch.cat((x_img, x_d_filtered, depth_stage1), dim=1) at multistage_model.py:78 -- the stage-2 input
+ * is never materialised.  planes / batch_strides are HOST arrays of C entries. */
+int rd_input_pack_parts(const float* const* planes, const long long* batch_strides, void* out, int B, int C, int H, int W, int Cs,
+                        int act_dtype, void* stream);
+
+/* Channel c of d(loss)/d(input), fp32 [B,1,H,W], from the stem's space-to-depth data gradient [B,ceil(H/2),ceil(W/2),4*Cs]:
+ * autograd's slice of the stage-2 input gradient that flows into stage 1 (multistage_model.py:75,78). */
+int rd_input_grad_channel(const void* dxs, float* out, int B, int H, int W, int Cs, int c, int act_dtype, void* stream);
+
 /* nn.BatchNorm2d statistics -> fused scale/shift (+ running-stat update in training).  models.py:540 etc. */
 int rd_bn_finalize(const double* sum, const double* sumsq, double count, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, long long* num_batches_tracked, int C, int training,

@@ -109,6 +109,8 @@ _PROTOS = {
     "rd_conv_fprop": ([C.POINTER(ConvParams), _P], _I),
     "rd_conv_wgrad": ([C.POINTER(WgradParams), _P], _I),
     "rd_input_pack": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "rd_input_pack_parts": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "rd_input_grad_channel": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "rd_bn_finalize": ([_P, _P, _D, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P], _I),
     "rd_bn_finalize_eval_multi": ([_P, _I, _F, _P], _I),
     "rd_bn_bwd_finalize": ([_P, _P, _D, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P], _I),

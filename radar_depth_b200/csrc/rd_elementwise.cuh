@@ -90,6 +90,53 @@ __global__ void input_pack_kernel(const float* __restrict__ x, T* __restrict__ o
     }
 }
 
+// input_pack_parts: the same packing with every input channel read from its own plane pointer / batch stride -- the
+// stage-2 input of ResNet_multistage, torch.cat((rgb, radar_filtered, depth_stage1), 1) (multistage_model.py:78), is packed
+// straight from its three sources and never materialised.
+struct PackSrc { const float* p[8]; long long bs[8]; };
+template <typename T>
+__global__ void input_pack_parts_kernel(const __grid_constant__ PackSrc src, T* __restrict__ out, int B, int C, int H, int W, int Cs) {
+    pdl_enter();
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+    const uint32_t total = (uint32_t)B * H2 * W2 * 4;
+    const FastDiv fdw((uint32_t)W2), fdh((uint32_t)H2);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int q = (int)(i & 3);
+        const uint32_t pix = i >> 2;
+        const uint32_t prow = fdw.div(pix);
+        const int ox = (int)(pix - prow * W2);
+        const int b = (int)fdh.div(prow);
+        const int oy = (int)(prow - (uint32_t)b * H2);
+        const int iy = oy * 2 + (q >> 1), ix = ox * 2 + (q & 1);
+        const bool ok = iy < H && ix < W;
+        T* o = out + pix * (size_t)(4 * Cs) + q * Cs;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= Cs) break;
+            float v = 0.f;
+            if (ok && c < C) v = __ldg(src.p[c] + (size_t)b * src.bs[c] + (size_t)iy * W + ix);
+            Act<T>::st(o + c, v);
+        }
+    }
+}
+// input_grad_channel: channel c of the gradient w.r.t. the network input, fp32 [B,1,H,W], from the space-to-depth data
+// gradient of the stem (only the stage-1 prediction inside the stage-2 input carries a gradient, multistage_model.py:75).
+template <typename T>
+__global__ void input_grad_channel_kernel(const T* __restrict__ dxs, float* __restrict__ out, int B, int H, int W, int Cs, int c) {
+    pdl_enter();
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1;
+    const uint32_t total = (uint32_t)B * H * W;
+    const FastDiv fdw((uint32_t)W), fdh((uint32_t)H);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t row = fdw.div(i);
+        const int ix = (int)(i - row * W);
+        const int b = (int)fdh.div(row);
+        const int iy = (int)(row - (uint32_t)b * H);
+        const size_t pix = ((size_t)b * H2 + (iy >> 1)) * W2 + (ix >> 1);
+        out[i] = Act<T>::ld(dxs + pix * (size_t)(4 * Cs) + ((iy & 1) * 2 + (ix & 1)) * Cs + c);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // bn_finalize: batch statistics -> fused scale/shift, saved mean/invstd, running-stat update.
 // nn.BatchNorm2d train/eval semantics (reference models.py:540 etc.): biased variance

@@ -937,11 +937,27 @@ class LatefusionEngine:
         """rd_input_pack straight from the caller's NCHW fp32 tensor (outside the captured graphs: its address varies).
         Without CUDA graphs (use_graphs = False: tools, debugging) the input is copied to x_in and the programs' own
         input_pack launch runs, so that every launch of a program can be replayed on its own afterwards."""
+        parts = x if isinstance(x, (tuple, list)) else None
         if not self.use_graphs:
-            self.x_in.copy_(x)
+            self.x_in.copy_(torch.cat([t.float() for t in parts], dim=1) if parts is not None else x)
             return
-        assert x.dtype == torch.float32 and x.is_contiguous()
-        rc = self.lib.rd_input_pack(x.data_ptr(), *self._ipack_tail, torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.current_stream().cuda_stream
+        if parts is not None:
+            # channel planes of several source tensors (rd_input_pack_parts): the concatenated input is never materialised
+            planes, strides = [], []
+            for t in parts:
+                assert t.dtype == torch.float32 and t.dim() == 4 and t.stride(3) == 1 and t.stride(2) == t.shape[3] and \
+                    t.stride(1) == t.shape[2] * t.shape[3], "input parts must be fp32 NCHW with dense channel planes"
+                for c in range(t.shape[1]):
+                    planes.append(t.data_ptr() + 4 * c * t.stride(1))
+                    strides.append(t.stride(0))
+            assert len(planes) == self.in_channels
+            pl = (C.c_void_p * len(planes))(*planes)
+            bs = (C.c_longlong * len(strides))(*strides)
+            rc = self.lib.rd_input_pack_parts(pl, bs, *self._ipack_tail, st)
+        else:
+            assert x.dtype == torch.float32 and x.is_contiguous()
+            rc = self.lib.rd_input_pack(x.data_ptr(), *self._ipack_tail, st)
         if rc != 0:
             raise _lib.RdError(f"input_pack failed ({rc}): {self.lib.rd_last_error().decode()}")
 
@@ -949,10 +965,16 @@ class LatefusionEngine:
         """inference = the pass will never be differentiated (torch.no_grad()): in eval mode it then runs the program with
         BatchNorm, residual add and activation folded into the conv epilogues, which overwrites the raw conv outputs the
         backward program would need."""
-        B, Cc, H, W = x.shape
+        if isinstance(x, (tuple, list)):                # channel groups of the input as separate tensors (see _pack_input)
+            B, _, H, W = x[0].shape
+            Cc = sum(int(t.shape[1]) for t in x)
+            dev = x[0].device
+        else:
+            B, Cc, H, W = x.shape
+            dev = x.device
         assert Cc == self.in_channels, (Cc, self.in_channels)
         if not self.params_adopted():
-            self.adopt(x.device)
+            self.adopt(dev)
         self.configure(B, H, W)
         self._pack_input(x)
         if training:
@@ -1111,3 +1133,15 @@ class LatefusionEngine:
         d = self.dxs.float().view(B, H2, W2, 2, 2, Cs)[..., : self.in_channels]      # [B,H2,W2,py,px,c]
         d = d.permute(0, 5, 1, 3, 2, 4).reshape(B, self.in_channels, 2 * H2, 2 * W2)
         return d[:, :, :H, :W].contiguous()
+
+    def input_grad_channel(self, c: int) -> torch.Tensor:
+        """Channel c of d(loss)/d(x), fp32 [B,1,H,W] (one kernel instead of the permute / slice chain above)."""
+        if self.dxs is None:
+            raise RuntimeError("input gradients are only produced for in_channels > 4")
+        B, H, W = self.cfg["B"], self.cfg["H"], self.cfg["W"]
+        out = torch.empty(B, 1, H, W, dtype=torch.float32, device=self.dxs.device)
+        rc = self.lib.rd_input_grad_channel(self.dxs.data_ptr(), out.data_ptr(), B, H, W, self.dxs.shape[-1] // 4, c, self.act_dtype,
+                                            torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise _lib.RdError(f"input_grad_channel failed ({rc}): {self.lib.rd_last_error().decode()}")
+        return out

@@ -223,6 +223,35 @@ class _LatefusionFn(torch.autograd.Function):
         return dx, None, None
 
 
+class _LatefusionPartsFn(torch.autograd.Function):
+    """forward() on an input given as channel groups (rgb, radar, stage-1 depth): the stage-2 call of ResNet_multistage
+    without torch.cat (multistage_model.py:78).  Only the last group (ONE channel) may carry a gradient."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, anchor, module):
+        eng = module._get_engine()
+        pred = eng.forward((a, b, c), module.training)
+        module._fwd_serial += 1
+        ctx.module, ctx.serial = module, module._fwd_serial
+        ctx.need_dc = c.requires_grad
+        ctx.c_index = int(a.shape[1] + b.shape[1])
+        ctx.training = module.training
+        return pred.clone()
+
+    @staticmethod
+    def backward(ctx, dpred):
+        module = ctx.module
+        if ctx.serial != module._fwd_serial:
+            raise RuntimeError("radar_depth_b200: the activations of this forward pass were overwritten by a later "
+                               "forward of the same model; call backward before the next forward")
+        eng = module._engine
+        accumulate = eng.grads_bound()
+        eng.backward(dpred.contiguous(), accumulate, ctx.training)
+        eng.bind_grads()
+        dc = eng.input_grad_channel(ctx.c_index) if ctx.need_dc else None
+        return None, None, dc, None, None
+
+
 class _RearFn(torch.autograd.Function):
     """pnp_forward_rear with a gradient w.r.t. its input feature (decoder parameters get no gradient on this path)."""
 
@@ -323,6 +352,26 @@ class ResNet_latefusion(nn.Module):
         eng = self._get_engine()
         self._fwd_serial += 1                        # the saved activations of an earlier grad-enabled forward are gone:
         return eng.forward(x, self.training, inference=True).clone()  # its backward() must raise, not differentiate the wrong pass
+
+    def forward_parts(self, rgb, radar, depth):
+        """forward(torch.cat((rgb, radar, depth), 1)) without the concatenation: every part is fp32 NCHW with dense channel
+        planes (a channel slice of a contiguous tensor qualifies); ``depth`` is one channel and may require grad, the other
+        parts are treated as constants (what ResNet_multistage passes, multistage_model.py:73-79)."""
+        assert depth.shape[1] == 1 and not rgb.requires_grad and not radar.requires_grad
+        parts = []
+        for t in (rgb, radar, depth):
+            if not t.is_cuda:
+                raise _lib.RdError("radar_depth_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+            t = t.float()
+            dense = t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) == t.shape[2] * t.shape[3]
+            parts.append(t if dense else t.contiguous())
+        if torch.is_grad_enabled():
+            if self._anchor is None or self._anchor.device != depth.device:
+                self._anchor = torch.zeros(1, device=depth.device, requires_grad=True)
+            return _LatefusionPartsFn.apply(parts[0], parts[1], parts[2], self._anchor, self)
+        eng = self._get_engine()
+        self._fwd_serial += 1
+        return eng.forward(tuple(parts), self.training, inference=True).clone()
 
     # API surface of models.py:669-707 (PnP-Depth refinement); main.py never calls them (SURVEY 8a-11).  front = encoder
     # + fusion 1x1s up to bn2's output, rear = decoder + head + bilinear.  rear(front(x)) == forward(x).  The usual PnP

@@ -76,6 +76,7 @@ class ResNet_multistage(nn.Module):
         x_d = x[:, 3:, :, :]
         depth_stage1 = self.stage1(x)
         x_d_filtered, mask = self.filter_layer(x_d, depth_stage1)
-        x_stage2 = torch.cat((x_img.float(), x_d_filtered, depth_stage1), dim=1)
-        depth_stage2 = self.stage2(x_stage2)
+        # multistage_model.py:78-79: stage2(cat(x_img, x_d_filtered, depth_stage1)); the three sources are packed by one
+        # kernel (rd_input_pack_parts) and the gradient of depth_stage1 comes back from rd_input_grad_channel
+        depth_stage2 = self.stage2.forward_parts(x_img, x_d_filtered, depth_stage1)
         return {"stage1": depth_stage1, "stage2": depth_stage2, "mask": mask, "radar_filtered": x_d_filtered}
