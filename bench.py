@@ -355,6 +355,7 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
     intensity (Launch.meta: algorithmic FLOPs / bytes) is above the ridge of the measured peaks count against the tensor
     roof, the others and every elementwise kernel against the HBM roof."""
     import torch
+    from radar_depth_b200.convplan import NUM_SMS as cp_num_sms
     peaks = _peaks()
     ridge = peaks["bf16_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
     saved = [e.use_graphs for e in engs]
@@ -426,7 +427,8 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
                     if meta.get("bytes"):
                         frac = (meta["flops"] / (t * 1e-3) / 1e12 / peaks["bf16_sustained"]) if key == "tensor_bound_convs" \
                             else (meta["bytes"] / (t * 1e-3) / 1e9 / peaks["hbm"])
-                        worst.append((t, L.name, key, round(frac, 3)))
+                        worst.append((t, L.name + (f" [lane 1: {eng._depth_sms} SMs]" if (in_par and L.lane == 1) else
+                                                   (f" [lane 0: {cp_num_sms - eng._depth_sms} SMs]" if in_par else "")), key, round(frac, 3)))
         conv_ms = sum(v[0] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
         conv_n = sum(v[1] for k, v in per.items() if k in ("conv_f", "conv_d", "wgrad"))
         total_ms = sum(v[0] for v in per.values())
@@ -463,22 +465,27 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
                         break
             except Exception:
                 continue
-        # In the step the depth encoder's chain (lane 1) runs on its own SMs BESIDE the RGB encoder's chain: what the step
-        # pays for it is only the part that outlasts the RGB chain.  `frac` stays the conservative serial figure (every
-        # launch timed alone, summed -- the quantity an ncu launch list also gives); `frac_critical_path` removes the hidden
-        # lane-1 convolution time, `frac_step` divides by the whole measured step.
+        # In the step the depth encoder's chain (lane 1) runs on its own SMs BESIDE the RGB encoder's chain (lane 0, the other
+        # SMs): the time the convolution programs occupy the GPU is the UNION of the two lanes' intervals, i.e. the serial sum
+        # minus the lane-1 convolution time that runs hidden beside lane 0.  `achieved` / `frac` = algorithmic conv FLOPs of
+        # the step / that union time, against the whole GPU's tensor peak; `frac_serial_sum` divides by the plain sum of every
+        # launch timed alone (double-counts the overlapped interval; what an ncu launch list adds up to), `frac_step` by the
+        # whole measured step.
         hidden = max(0.0, lanes["lane1_ms"] - lanes["exposed_lane1_ms"])
         hidden_conv = hidden * (lanes["lane1_conv_ms"] / lanes["lane1_ms"]) if lanes["lane1_ms"] > 0 else 0.0
         conv_crit = conv_ms - hidden_conv
+        achieved_serial = achieved
+        achieved = flops / (conv_crit * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                "frac_critical_path": flops / (conv_crit * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                "frac_serial_sum": achieved_serial / peaks["bf16_sustained"], "conv_ms_serial_sum": conv_ms,
+                "frac_note": "conv FLOPs / union of the conv launches' intervals (two encoder lanes run concurrently on disjoint SM sets)",
                 "conv_ms_critical_path": conv_crit, "lanes": {k: round(v, 4) for k, v in lanes.items()},
                 "depth_sms": int(getattr(engs[0], "_depth_sms", 0)) if getattr(engs[0], "_par", False) else 0,
                 "traffic_note": f"dram__bytes_read+write per conv launch, ncu launch list (cold cache per launch), bytes; profiles/{traffic_src}",
                 "peak_source": peaks["source"] + " (sustained bf16)",
                 "kernel": "conv_fprop_kernel + conv_wgrad_kernel (tcgen05 implicit-GEMM programs)",
-                "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "conv_ms_per_step": conv_ms,
+                "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1), "conv_ms_per_step": conv_crit,
                 "all_kernels_ms_per_step": total_ms, "conv_share_of_step": conv_ms / total_ms,
                 "by_kind_ms": {k: round(v[0], 4) for k, v in sorted(per.items())},
                 "algorithmic_flop_per_step": flops, "ridge_flop_per_byte": round(ridge, 1), "classes": classes,

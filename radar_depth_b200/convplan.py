@@ -49,6 +49,19 @@ def tuned_table() -> dict:
 
 def tune_key(kind: str, g: "GConv", B: int, src_hw, dst_hw, act_dtype: int) -> str:
     return f"{kind}|Cx{g.Cx}|N{g.N}|S{g.S}|OS{g.OS}|T{len(g.taps)}|{src_hw[0]}x{src_hw[1]}>{dst_hw[0]}x{dst_hw[1]}|B{B}|dt{act_dtype}"
+
+
+def tuned_lookup(key: str, sm_budget: int, suffix: str = ""):
+    """Measured entry for a launch that may use `sm_budget` SMs: the entry measured with exactly that budget (key + "|smNN",
+    the encoder chains that run side by side on disjoint SM sets) or, for budgets of at least half the GPU, the whole-GPU
+    entry.  A chain that owns a few SMs only is planned by the cost model when it has no entry of its own (measured,
+    multistage b=8: 12.4 vs 13.2 ms/step with the whole-GPU tiles on the small lane)."""
+    tab = tuned_table()
+    if sm_budget != NUM_SMS:
+        t = tab.get(key + f"|sm{sm_budget}" + suffix)
+        if t is not None or 2 * sm_budget < NUM_SMS:
+            return t
+    return tab.get(key + suffix)
 FPROP_HEADER = 16384
 WGRAD_HEADER = 10240
 NUM_SMS = 148
@@ -339,7 +352,7 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
     ntaps = len(taps)
     assert ntaps <= _lib.RD_MAX_TAPS
     if tile_override is None and use_tuned:
-        tile_override = tuned_table().get(tune_key("f", g, B, src_hw, dst_hw, act_dtype))
+        tile_override = tuned_lookup(tune_key("f", g, B, src_hw, dst_hw, act_dtype), sm_budget)
     if n_per_cta is None and tile_override and "N" in tile_override:
         n_per_cta = int(tile_override["N"])            # measured: output channels per CTA (tools/autotune.py)
     if n_per_cta is None:
@@ -525,7 +538,7 @@ def plan_wgrad(g: GConv, B: int, x_hw, g_hw, act_dtype: int = _lib.RD_BF16, ks_t
     assert g.Cx % 16 == 0 and g.N % 8 == 0
     if use_tuned and nc is None:
         key = tune_key("w", g, B, x_hw, g_hw, act_dtype)
-        t = (tuned_table().get(key + "|bn") if bn else None) or tuned_table().get(key)
+        t = (tuned_lookup(key, sm_budget, "|bn") if bn else None) or tuned_lookup(key, sm_budget)
         if t:
             nc, ks_target = t["nc"], t["ks"]
             if gcopy is None and "gc" in t:

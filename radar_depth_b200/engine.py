@@ -108,10 +108,12 @@ class LatefusionEngine:
         # tile shapes: measured table (tuned_tiles.json) or, with use_tuned = False, the analytic cost model only
         self.use_tuned = os.environ.get("RD_USE_TUNED", "1") != "0"
         # SMs given to the depth encoder while it runs next to the RGB encoder (0 = one stream, every launch owns the GPU).
-        # Measured on B200 (bench.py, same box): at b=16 the depth chain is throughput-bound on the SMs it gets (a 16-channel
-        # 3x3 conv takes 23 us on 148 SMs, 59 us on 24, 104 us on 12) and the split never pays: 9.24 ms/step with one
-        # stream, 9.39 (24 SMs), 9.44 (16), 10.9 (12), 13.4 (8).  At b=8 (multistage) every launch is half as long, fill and
-        # drain dominate the small layers, and the split wins: 13.81 -> 12.39 ms/step with 24 SMs.  Default: by batch size.
+        # Measured on B200 (bench.py, same box, after the round-2 kernels): 20 SMs for the depth chain leave the RGB chain
+        # 128 -- every N-block split of its launches (2 / 4 blocks -> 64 / 32 CTAs) then divides its tile counts evenly, which
+        # 127 or 126 do not (a 32-tile layer4 launch needs two rounds on 31 CTAs per block): latefusion b=16 8.20 ms/step on
+        # one stream, 8.42 (14), 7.96 (16), 7.84 (18), 7.65 (20), 8.05 (22), 8.12 (24); multistage b=8 12.13 on one stream,
+        # 10.86 (16), 10.64 (18), 10.48 (20), 11.36 (21 ... 24), 11.47 (32).  (Round 1/early round 2, slower small-layer kernels:
+        # the split only paid at b=8.)  Default: 20 at every batch size.
         env = os.environ.get("RD_DEPTH_SMS")
         self.depth_sms = int(env) if env not in (None, "") else None       # None = choose in configure()
         self._side = None
@@ -234,7 +236,7 @@ class LatefusionEngine:
         det_bytes = [8 << 20]
 
         # -------- helpers that register a conv and emit launches
-        depth_sms = self.depth_sms if self.depth_sms is not None else (24 if B <= 8 else 0)
+        depth_sms = self.depth_sms if self.depth_sms is not None else 20
         single = self.arch == "resnet"                    # one encoder over all input channels (models.py:233-303)
         par = depth_sms > 0 and not self.det and not single    # deterministic mode shares one scratch buffer: one stream
         self._par, self._depth_sms = par, depth_sms
@@ -242,9 +244,8 @@ class LatefusionEngine:
 
         def reg(name, g: cp.GConv, src_hw, dst_hw, need_dgrad=True, need_wgrad=True, lane=None):
             sms = sm_of[lane]
-            # the measured tile table was taken with the whole GPU per launch: a chain that owns a few SMs only is planned
-            # by the cost model for that many CTAs (measured, multistage b=8: 12.4 vs 13.2 ms/step with the table's tiles)
-            tuned = self.use_tuned and not (par and lane == 1)
+            # measured tile table: entries are keyed by the SM budget of the launch (convplan.tuned_lookup)
+            tuned = self.use_tuned
             fplan = cp.plan_fprop(g, B, src_hw, dst_hw, act, smem_reserve=det_reserve, use_tuned=tuned, sm_budget=sms)
             f_off = self._wpk_total
             self._wpk_tables.append(fplan.pack_idx)
@@ -318,7 +319,7 @@ class LatefusionEngine:
                 # layout does not depend on it)
                 if "wplan_bn" not in rec:
                     src_hw, dst_hw, tuned, sms = rec["wargs"]
-                    has = tuned and (cp.tune_key("w", rec["g"], B, src_hw, dst_hw, act) + "|bn") in cp.tuned_table()
+                    has = tuned and cp.tuned_lookup(cp.tune_key("w", rec["g"], B, src_hw, dst_hw, act), sms, "|bn") is not None
                     rec["wplan_bn"] = cp.plan_wgrad(rec["g"], B, src_hw, dst_hw, act, use_tuned=True, sm_budget=sms, bn=True) if has else None
                 if rec["wplan_bn"] is not None:
                     plan = rec["wplan_bn"]

@@ -81,11 +81,15 @@ for rec in eng.convs:
     g = rec["g"]
     fp = rec["fplan"].params
     src_hw, dst_hw = (fp.srcH, fp.srcW), (fp.dstH, fp.dstW)
+    sms = rec["wargs"][3]                                  # SM budget of the chain this layer runs in (engine lanes)
+    ksfx = f"|sm{sms}" if sms != cp.NUM_SMS else ""
+    if os.environ.get("RD_TUNE_LANES_ONLY") == "1" and not ksfx:
+        continue
     jobs = [("f", g, src_hw, dst_hw)]
     if rec["dplan"] is not None:
         jobs.append(("f", g.transposed(), dst_hw, src_hw))
     for kind, gg, s_hw, d_hw in (jobs if "f" in KINDS else []):
-        key = cp.tune_key(kind, gg, B, s_hw, d_hw, act)
+        key = cp.tune_key(kind, gg, B, s_hw, d_hw, act) + ksfx
         if key in seen:
             continue
         seen.add(key)
@@ -102,7 +106,7 @@ for rec in eng.convs:
             cands += fprop_candidates(gg, s_hw, d_hw, n_)
         for ov in cands:
             try:
-                plan = cp.plan_fprop(gg, B, s_hw, d_hw, act, tile_override=ov, use_tuned=False)
+                plan = cp.plan_fprop(gg, B, s_hw, d_hw, act, tile_override=ov, use_tuned=False, sm_budget=sms)
             except Exception:
                 continue
             wpk = ops.pack_weights(w, torch.from_numpy(plan.pack_idx).cuda())
@@ -130,7 +134,7 @@ for rec in eng.convs:
         table[key] = best[1]
         print(f"{rec['name']:42s} {key:70s} model {base * 1e3:7.1f} us -> best {best[0] * 1e3:7.1f} us {best[1]}", flush=True)
     if rec["wplan"] is not None and "w" in KINDS:
-        key = cp.tune_key("w", g, B, src_hw, dst_hw, act)
+        key = cp.tune_key("w", g, B, src_hw, dst_hw, act) + ksfx
         if key in seen:
             continue
         seen.add(key)
@@ -149,7 +153,7 @@ for rec in eng.convs:
                     if nc is not None and (nc > g.Cx or g.Cx % nc):
                         continue
                     try:
-                        plan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, ks_target=ks, nc=nc, use_tuned=False, gcopy=gc)
+                        plan = cp.plan_wgrad(g, B, src_hw, dst_hw, act, ks_target=ks, nc=nc, use_tuned=False, gcopy=gc, sm_budget=sms)
                     except Exception:
                         continue
                     if (not gc) and False:
