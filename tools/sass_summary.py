@@ -15,8 +15,9 @@ funcs = re.split(r"\n\s*Function : ", txt)
 out = ["# SASS evidence of the Blackwell-native paths in radar_depth_b200/libradar_depth_b200.so (sm_100a)",
        "# command: python tools/sass_summary.py  (cuobjdump -sass, per-function mnemonic counts)",
        "# UTCHMMA = tcgen05.mma (kind::f16), UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (TMA tile load),",
+       "# UTMALDG.4D = the 128-byte-swizzled [slot][64 channels] boxes of the weight-gradient kernel (SWIZZLE_128B MN-major operands), .5D = 16-byte chunk planes,",
        "# UBLKCP = cp.async.bulk (weight tiles), SYNCS = mbarrier ops, UTCATOMSWS = TMEM allocation, REDG = fp32 vector reductions", ""]
-keys = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UBLKCP", "SYNCS", "UTCATOMSWS", "LDGSTS", "REDG", "HMMA", "ATOMG"]
+keys = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMALDG.4D", "UTMALDG.5D", "UBLKCP", "SYNCS", "UTCATOMSWS", "LDGSTS", "REDG", "HMMA", "ATOMG"]
 tot = collections.Counter()
 for f in funcs[1:]:
     name = f.split("\n", 1)[0].strip()
