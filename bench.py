@@ -369,7 +369,9 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
             loss.backward()
         torch.cuda.synchronize()
         reps = 6
-        cls = {"tensor_bound_convs": [0.0, 0, 0.0, 0.0], "hbm_bound_convs": [0.0, 0, 0.0, 0.0], "elementwise": [0.0, 0, 0.0, 0.0]}
+        # depth_lane_convs: the depth encoder's conv programs, timed alone on their lane's SMs (hidden beside lane 0 in the step)
+        cls = {"tensor_bound_convs": [0.0, 0, 0.0, 0.0], "hbm_bound_convs": [0.0, 0, 0.0, 0.0], "depth_lane_convs": [0.0, 0, 0.0, 0.0],
+               "elementwise": [0.0, 0, 0.0, 0.0]}
         worst = []
         lanes = {"lane1_ms": 0.0, "lane0_ms_beside_lane1": 0.0, "exposed_lane1_ms": 0.0, "lane1_conv_ms": 0.0}
         from radar_depth_b200 import determinism
@@ -415,7 +417,9 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
                             lanes["lane1_conv_ms"] += t if is_conv else 0.0
                         else:
                             reg0 += t
-                    if is_conv:
+                    if is_conv and in_par and L.lane == 1:
+                        key = "depth_lane_convs"
+                    elif is_conv:
                         key = "tensor_bound_convs" if meta["flops"] / meta["bytes"] >= ridge else "hbm_bound_convs"
                     else:
                         key = "elementwise"
@@ -437,6 +441,8 @@ def kernel_roofline(model, engs, d_in, d_tg, loss_fn, b, arch, dump_path=None):
         classes = {}
         for k, (ms, n, fl, by) in cls.items():
             ent = {"launches": n, "ms_per_step": round(ms, 4), "algorithmic_gflop": round(fl / 1e9, 2), "algorithmic_gbytes": round(by / 1e9, 3)}
+            if k == "depth_lane_convs":
+                ent["note"] = "each launch timed alone on the lane's SMs (depth_sms of 148); in the step this time runs beside lane 0 (roofline.lanes)"
             if ms > 0:
                 if k == "tensor_bound_convs":
                     ent.update(bound="tensor", achieved=fl / (ms * 1e-3) / 1e12, unit="TFLOP/s", peak=peaks["bf16_sustained"])
