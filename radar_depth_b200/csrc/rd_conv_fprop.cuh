@@ -11,7 +11,7 @@
 // zero-stuffed Unpool output (models.py:13-27,191,198) and stride-2 data gradients run as 4 output phases,
 // each with its own tap list, on the UN-stuffed source.
 //
-// Warp roles (448 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11 source-tile loaders
+// Warp roles (512 threads; warps 14-15 are extra transform workers, see bn_epi2): warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-11 source-tile loaders
 // (fused BatchNorm affine + ReLU/LeakyReLU + bf16 cast, optional hi/lo split for parity mode), warp 12 lane 0
 // UMMA issuer, warp 13 lane 0 weight bulk-copy issuer.  Two mbarrier rings (source tile stages, weight
 // stages) plus a TMEM full/empty pair; the kernel is persistent over tiles.
@@ -23,7 +23,7 @@
 namespace rd {
 
 constexpr int kFpropLoaderWarps = 8;
-constexpr int kFpropThreads = (4 + kFpropLoaderWarps + 2) * 32;   // epilogue x4, loaders, UMMA issuer, weight copier
+constexpr int kFpropThreads = (4 + kFpropLoaderWarps + 2 + 2) * 32;   // epilogue x4, loaders, UMMA issuer, weight copier, 2 extra transform warps (512 x 128 registers = the register file)
 constexpr int kSmemHeader = 16384;      // barriers, tmem slot, stats, BN vectors
 constexpr int kOffTmemSlot = 384;      // (the barrier block below occupies bytes [0, 352))
 constexpr int kOffTapTable = 512;       // int[3][32]: a_shift, accumulator column, first-of-phase flag
@@ -280,14 +280,24 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // bf16 stride-1 tiles with a fused BatchNorm+activation: the raw box lands by TMA on tma_full[stage], seven worker
     // warps apply the transform IN PLACE in shared memory (no global latency on their path) and arrive on in_full[stage]
     const bool src_tma_bn = (SPLIT == 1) && (sizeof(T) == 2) && (p.ld_scale != nullptr) && use_tma;
+    // Transform mode with >= 4 taps per stage: warps 8-11 form the second epilogue group as in the raw-TMA mode and the
+    // transform runs on warps 5-7 + 14-15 (five workers; three were measured too few: 74.5 vs 67.6 us on layer1).  With four
+    // epilogue warps that program spent 74.9 kcycles per CTA in its epilogue against 58.7 in its UMMAs (tools/bench_fprop.py
+    // l1 bn).  1-tap programs keep seven workers (5-11).
+    const bool bn_epi2 = src_tma_bn && p.ntaps >= 4 && !(p.dbg_flags & 64);
+    const int bn_workers = bn_epi2 ? 5 : kFpropLoaderWarps - 1;
+    // cp.async / register staging (stride-2 parity planes, fp32 parity mode): six loader warps (4-7, 14-15) and the second
+    // epilogue group instead of eight loaders and one group
+    const bool ld_epi2 = !src_tma && !src_tma_bn && !(p.dbg_flags & 64);
+    const int ld_warps = ld_epi2 ? 6 : kFpropLoaderWarps;
     if (tid == 0) {
         for (int i = 0; i < p.IS; ++i) {
-            mbar_init(&in_full[i], src_tma ? 1 : (src_tma_bn ? kFpropLoaderWarps - 1 : (src_async ? 32 * kFpropLoaderWarps : kFpropLoaderWarps)));
+            mbar_init(&in_full[i], src_tma ? 1 : (src_tma_bn ? bn_workers : (src_async ? 32 * ld_warps : ld_warps)));
             mbar_init(&in_empty[i], 1);
             mbar_init(&tma_full[i], 1);
         }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], src_tma ? 8 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (src_tma || bn_epi2 || ld_epi2) ? 8 : 4); }
         fence_mbar_init();
     }
     if (tid < p.ntaps) {
@@ -318,8 +328,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
 
     // With raw TMA staging seven of the eight loader warps have nothing to load: warps 8-11 (TMEM lane quarters 0-3 again)
     // become a second epilogue group that takes the odd 16-column chunks.
-    const bool epi2 = src_tma;
-    if (warp >= 4 && warp < kWarpMma && !(epi2 && warp >= 8 && warp < 12)) {
+    const bool epi2 = src_tma || bn_epi2 || ld_epi2;
+    if ((warp >= 4 && warp < kWarpMma && !(epi2 && warp >= 8 && warp < 12)) || ((bn_epi2 || ld_epi2) && warp >= 14)) {
         // ================= source tile loaders =================
         PipeState st(p.IS);
         TileSrc ts;
@@ -331,12 +341,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         if (tl_mode && !gt_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
+        const int ld_idx = warp >= 14 ? warp - 10 : warp - 4;          // loader index in the cp.async / register modes
         if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
         else if (src_tma_bn && warp != 4) {
             // ---- transform workers (warps 5..11)
             // A worker thread owns ONE of the two 8-channel chunks of every stage and walks the tile's slots with a fixed
             // stride: the chunk's scale / shift are read once per stage (not per item), row / column follow incrementally
-            const int t = (warp - 5) * 32 + lane, nthr = (kFpropLoaderWarps - 1) * 32;
+            const int t = (warp >= 14 ? warp - 11 : warp - 5) * 32 + lane, nthr = bn_workers * 32;      // workers 5-7, 14-15 or 5-11
             const int cs = p.chunk_stride;                 // = plane_rows * Wl in this mode
             const int nslots = p.plane_rows * p.Wl;
             const int j = t & 1, s0 = t >> 1, tpc = nthr >> 1;
@@ -403,10 +414,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
                     else { __syncwarp(); if (lane == 0) mbar_arrive(&in_full[st.stage]); }
                 } else
                 if (src_async) {
-                    stage_tile_async<T>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
+                    stage_tile_async<T>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, ld_idx, ld_warps, lane);
                     cp_async_mbar_arrive_noinc(&in_full[st.stage]);
                 } else {
-                    stage_tile<T, SPLIT>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, warp - 4, kFpropLoaderWarps, lane);
+                    stage_tile<T, SPLIT>(ts, sbase, p.chunk_stride, img, y0, x0, c * 16, 2, ld_idx, ld_warps, lane);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&in_full[st.stage]);
                 }
@@ -464,8 +475,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
 #undef RD_ISSUE
         }
         __syncwarp();
+    } else if (warp >= 14) {
+        // (extra transform warps: idle outside the five-worker transform mode)
     } else {
-        // ================= epilogue (warps 0-3, and warps 8-11 in raw-TMA mode) =================
+        // ================= epilogue (warps 0-3, and warps 8-11 in the raw-TMA and five-worker transform modes) =================
         const int wq = warp & 3, eg = warp >> 3, neg = epi2 ? 2 : 1;
         T* dst = reinterpret_cast<T*>(p.dst.ptr);
         const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
