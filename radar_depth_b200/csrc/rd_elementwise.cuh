@@ -538,7 +538,7 @@ __global__ void maxpool_fwd_kernel(VView z, const float* __restrict__ sc, const 
 // with the same rule (strictly greater or NaN replaces: first maximum in window order wins, out-of-image taps are -inf).
 constexpr int kMpTileW = 16, kMpInW = 2 * kMpTileW + 1;
 template <int TH>
-__global__ void maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int H, int W, int C,
+__global__ void __launch_bounds__(320, 3) maxpool_fwd_tile_kernel(VView z, const float* __restrict__ sc, const float* __restrict__ sh, int H, int W, int C,
                                         int split, float slope_a, float slope_b, VView outa, VView outb,
                                         uint8_t* __restrict__ amax, int Ho, int Wo, bf16* __restrict__ zarg) {
     pdl_enter();
