@@ -336,6 +336,14 @@ int rd_sid_filter(const float* radar, const float* depth, long long n, float* ra
 /* Packed bf16 weights from the flat fp32 parameter arena via a gather table; gradient scatter back; fused SGD
  * (torch.optim.SGD as configured at main.py:285-290). */
 int rd_pack_weights(const float* src, const int32_t* idx, void* out, long long n, void* stream);
+
+/* Inference program (model.eval() + torch.no_grad(), main.py:584-595: the weights do not change between forwards):
+ * rd_weights_hash compares a content hash of the fp32 parameter arena (nchunks 64-bit values in `state`, zero-initialised by the
+ * caller; splitmix64 of every word and its index, summed per chunk) with the stored one, stores the new hash and sets
+ * *dirty = 1 if any chunk changed (0 otherwise); rd_pack_weights_if is rd_pack_weights that returns at once when *dirty == 0.
+ * No host-side bookkeeping of "who touched the weights" is involved: in-place updates through .data are seen as well. */
+int rd_weights_hash(const float* w, long long n, unsigned long long* state, int nchunks, int* dirty, void* stream);
+int rd_pack_weights_if(const float* src, const int32_t* idx, void* out, long long n, const int* dirty, void* stream);
 int rd_unpack_grads(const float* dw, const int32_t* idx, float* grad, long long n, void* stream);
 int rd_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first, void* stream);
 /* Same with the gradient multiplied by grad_scale first: the 1/world of a data-parallel SUM all-reduce folded into

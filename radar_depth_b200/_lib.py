@@ -133,6 +133,8 @@ _PROTOS = {
     "rd_depth_metrics": ([_P, _P, _LL, _F, _F, _P, _P], _I),
     "rd_sid_filter": ([_P, _P, _LL, _P, _P, _P], _I),
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
+    "rd_weights_hash": ([_P, _LL, _P, _I, _P, _P], _I),
+    "rd_pack_weights_if": ([_P, _P, _P, _LL, _P, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),
     "rd_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _I, _P], _I),
     "rd_sgd_scaled": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),

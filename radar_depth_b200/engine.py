@@ -838,6 +838,17 @@ class LatefusionEngine:
                                        (_p(self.bn_eval_table), len(self._bn_eval_rows), BN_EPS)))
         # inference program: same two head launches; decoders without the folded program fall back to the eval program
         self.fwd_infer = (self.fwd_eval[:2] + self.fwd_infer_body) if self.fwd_infer_body is not None else self.fwd_eval
+        if self.fwd_infer_body is not None and os.environ.get("RD_INFER_PACK_HASH", "1") != "0":
+            # the weights rarely change between inference forwards: re-pack only when the arena's content hash changed
+            nchunks = 1184                                    # 8 blocks per SM
+            self._whash = self.hold(torch.zeros(nchunks, dtype=torch.int64, device=self.device))
+            self._wdirty = self.hold(torch.zeros(1, dtype=torch.int32, device=self.device))
+            hashl = Launch("weights_hash", lib.rd_weights_hash, (_p(self.flat), self.nparams, _p(self._whash), nchunks, _p(self._wdirty)),
+                           dict(bytes=self.nparams * 4))
+            packif = Launch("pack_weights_if", lib.rd_pack_weights_if,
+                            (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel(), _p(self._wdirty)),
+                            dict(bytes=self.pack_idx.numel() * (4 + 4 + 2)))
+            self.fwd_infer = [hashl, packif, self.fwd_eval[1]] + self.fwd_infer_body
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams),
                          dict(bytes=self.nparams * (4 + 4 + 8))))
         self._grad_buckets(cut_enc, cut_l4, single)
@@ -901,6 +912,15 @@ class LatefusionEngine:
 
     # ------------------------------------------------------------------ execution
     def _run(self, prog: List[Launch]):
+        # Any program that re-packs the weights unconditionally makes the inference program's stored content hash (which
+        # describes the weights of ITS last re-packing) meaningless: it is cleared before the next hashed forward.
+        names = prog[0].name if prog else ""
+        if names == "weights_hash":
+            if getattr(self, "_whash_stale", False):
+                self._whash.zero_()
+                self._whash_stale = False
+        elif any(L.name == "pack_weights" for L in prog[:2]):
+            self._whash_stale = True
         # (Weight-gradient launches on a second, event-forked stream were tried: 10.91 vs 10.92 ms/step on B200 --
         # full-grid kernels with ~200 KB of shared memory per CTA do not overlap; the program stays single-stream.)
         main = torch.cuda.current_stream()
@@ -1103,6 +1123,13 @@ class LatefusionEngine:
     # The launch programs are static per input shape, so after one eager (warm-up) execution each program is
     # captured into a CUDA graph and replayed: ~360 kernel launches per step cost one cudaGraphLaunch each way.
     def _replay(self, which: str, body) -> None:
+        # (see _run: graph replays do not pass through it, so the hash bookkeeping is repeated here, outside any capture)
+        if which == "fwd_infer":
+            if getattr(self, "_whash_stale", False) and getattr(self, "_whash", None) is not None:
+                self._whash.zero_()
+                self._whash_stale = False
+        elif which in ("fwd", "fwd_eval"):
+            self._whash_stale = True
         if not self.use_graphs:
             body()
             return
