@@ -45,6 +45,33 @@ def test_input_pack(name, act, td, C, H, W):
     torch.testing.assert_close(out.float(), ref.to(td).float(), rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("name,act,td", ACTS)
+@pytest.mark.parametrize("H,W", [(12, 16), (13, 17)])
+def test_input_pack_parts_equals_input_pack_of_the_concatenation(name, act, td, H, W):
+    """multistage_model.py:78: cat((x[:, :3], radar_filtered, depth_stage1), 1) packed straight from its three sources (a
+    channel slice of a 4-channel tensor, two 1-channel tensors), and the gradient slice that flows back into depth_stage1."""
+    import ctypes as C
+    x4 = torch.randn(2, 4, H, W, device="cuda")
+    parts = [x4[:, :3], torch.randn(2, 1, H, W, device="cuda"), torch.randn(2, 1, H, W, device="cuda")]
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    ref = torch.full((2, H2, W2, 32), float("nan"), device="cuda", dtype=td)
+    call("rd_input_pack", ptr(torch.cat(parts, 1).contiguous()), ptr(ref), 2, 5, H, W, 8, act, stream_ptr())
+    planes, strides = [], []
+    for t in parts:
+        for c in range(t.shape[1]):
+            planes.append(t.data_ptr() + 4 * c * t.stride(1))
+            strides.append(t.stride(0))
+    out = torch.full((2, H2, W2, 32), float("nan"), device="cuda", dtype=td)
+    call("rd_input_pack_parts", (C.c_void_p * 5)(*planes), (C.c_longlong * 5)(*strides), ptr(out), 2, 5, H, W, 8, act, stream_ptr())
+    torch.testing.assert_close(out.float(), ref.float(), rtol=0, atol=0)
+    # channel 4 of a gradient in the same space-to-depth layout
+    g = torch.randn(2, H2, W2, 32, device="cuda").to(td)
+    dc = torch.empty(2, 1, H, W, device="cuda")
+    call("rd_input_grad_channel", ptr(g), ptr(dc), 2, H, W, 8, 4, act, stream_ptr())
+    full = g.float().view(2, H2, W2, 2, 2, 8).permute(0, 5, 1, 3, 2, 4).reshape(2, 8, 2 * H2, 2 * W2)[:, 4:5, :H, :W]
+    torch.testing.assert_close(dc, full.contiguous(), rtol=0, atol=0)
+
+
 def test_bn_finalize_train_and_eval_match_torch_batchnorm():
     C, n = 48, 2 * 7 * 9
     x = torch.randn(2, C, 7, 9, device="cuda", dtype=torch.float64) * 2 + 1
