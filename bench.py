@@ -303,6 +303,19 @@ def main():
         torch.cuda.current_stream().synchronize()
         state["i"] += 1
 
+    # what the host link delivers for exactly these two copies, alone (an e2e step cannot be shorter than this)
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d_alone = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(copy_stream):
+            ce0.record(copy_stream)
+            dev[0][0].copy_(h_in, non_blocking=True)
+            dev[0][1].copy_(h_tg, non_blocking=True)
+            ce1.record(copy_stream)
+        torch.cuda.synchronize()
+        h2d_alone.append(ce0.elapsed_time(ce1))
+    h2d_alone_ms = min(h2d_alone)
     for ev in freed:
         ev.record()
     prefetch(0)
@@ -332,7 +345,9 @@ def main():
                        "collectives_per_step": collectives[0], "allreduce_overlapped_with_backward": bool(overlap), "loss_after_warmup": loss0,
                        "loss_after_timed_steps": float(last["loss"])},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / K},
+                    "ms_per_step": ms_e2e / K, "h2d_copy_alone_ms": h2d_alone_ms,
+                    "h2d_gbs_alone": (h_in.numel() + h_tg.numel()) * 4 / (h2d_alone_ms * 1e-3) / 1e9,
+                    "note": "the copy of step i+1 runs on a copy stream beside step i; when h2d_copy_alone_ms exceeds the device step the host link, not the GPU, sets e2e"},
             "gpu_launches": launches * K, "clocks": clocks}
 
     # ---- roofline of the tcgen05 convolution programs: per-launch CUDA-event timing on the launch stream
