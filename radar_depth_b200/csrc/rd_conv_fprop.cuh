@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // cp.async / register staging (stride-2 parity planes, fp32 parity mode): six loader warps (4-7, 14-15) and the second
     // epilogue group instead of eight loaders and one group
     const bool ld_epi2 = !src_tma && !src_tma_bn && !(p.dbg_flags & 64);
+    const bool epi3_pre = src_tma && det_part == nullptr && !(p.dbg_flags & 64);   // three epilogue groups in the raw-TMA mode (see below;
+                                                                                       // the deterministic mode's per-warp arrays are sized for two)
     const int ld_warps = ld_epi2 ? 6 : kFpropLoaderWarps;
     if (tid == 0) {
         for (int i = 0; i < p.IS; ++i) {
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             mbar_init(&tma_full[i], 1);
         }
         for (int i = 0; i < p.WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (src_tma || bn_epi2 || ld_epi2) ? 8 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], epi3_pre ? 12 : ((src_tma || bn_epi2 || ld_epi2) ? 8 : 4)); }
         fence_mbar_init();
     }
     if (tid < p.ntaps) {
@@ -329,7 +331,12 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
     // With raw TMA staging seven of the eight loader warps have nothing to load: warps 8-11 (TMEM lane quarters 0-3 again)
     // become a second epilogue group that takes the odd 16-column chunks.
     const bool epi2 = src_tma || bn_epi2 || ld_epi2;
-    if ((warp >= 4 && warp < kWarpMma && !(epi2 && warp >= 8 && warp < 12)) || ((bn_epi2 || ld_epi2) && warp >= 14)) {
+    // Raw-TMA mode: the box loads are issued by warp 14 and warps 4-7 (TMEM lane quarters 0-3 once more) are a THIRD epilogue
+    // group: the 16-column chunks are dealt to three groups (5 chunks of the stem: 2/2/1 instead of 3/2; 8 chunks: 3/3/2).
+    const bool epi3 = epi3_pre;
+    const int tma_warp = epi3 ? 14 : 4;
+    if ((warp >= 4 && warp < kWarpMma && !(epi2 && warp >= 8 && warp < 12) && !(epi3 && warp < 8)) ||
+        ((bn_epi2 || ld_epi2 || epi3) && warp == 14) || ((bn_epi2 || ld_epi2) && warp == 15)) {
         // ================= source tile loaders =================
         PipeState st(p.IS);
         TileSrc ts;
@@ -338,11 +345,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         ts.vrows = p.plane_rows; ts.vcols = p.Wl;
         ts.sc = p.ld_scale ? ld_sc : nullptr; ts.sh = ld_sh; ts.slope = p.ld_slope;
         ts.prepare();
-        if (tl_mode && !gt_mode && warp == 4 && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
+        if (tl_mode && !gt_mode && warp == tma_warp && lane == 0) p.dbg[0 * ((size_t)gridDim.x * gridDim.y) + blockIdx.x + (size_t)gridDim.x * blockIdx.y] = clock64() - t_entry;
         // Raw tiles: fire-and-forget cp.async, each loader thread arrives through cp.async.mbarrier.arrive.noinc
         // when its copies have landed (see rd_conv_wgrad.cuh); transformed tiles: registers + one arrival per warp.
         const int ld_idx = warp >= 14 ? warp - 10 : warp - 4;          // loader index in the cp.async / register modes
-        if (src_tma && !(warp == 4 && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
+        if (src_tma && !(warp == tma_warp && lane == 0)) { /* one thread drives the TMA unit; the other loader threads have nothing to do */ }
         else if (src_tma_bn && warp != 4) {
             // ---- transform workers (warps 5..11)
             // A worker thread owns ONE of the two 8-channel chunks of every stage and walks the tile's slots with a fixed
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
         // (extra transform warps: idle outside the five-worker transform mode)
     } else {
         // ================= epilogue (warps 0-3, and warps 8-11 in the raw-TMA and five-worker transform modes) =================
-        const int wq = warp & 3, eg = warp >> 3, neg = epi2 ? 2 : 1;
+        const int wq = warp & 3, eg = warp < 4 ? 0 : (warp >= 8 ? 1 : 2), neg = epi3 ? 3 : (epi2 ? 2 : 1);
         T* dst = reinterpret_cast<T*>(p.dst.ptr);
         const T* addend = reinterpret_cast<const T*>(p.addend.ptr);
         const T* zsrc = reinterpret_cast<const T*>(p.zsrc.ptr);
@@ -589,7 +596,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) conv_fprop_kernel(const __gr
             }
         }
         if (want_stats) {
-            if (neg == 2) asm volatile("bar.sync 1, 256;\n" ::: "memory");      // both epilogue groups have added their partials
+            if (neg == 3) asm volatile("bar.sync 1, 384;\n" ::: "memory");      // all epilogue groups have added their partials
+            else if (neg == 2) asm volatile("bar.sync 1, 256;\n" ::: "memory");
             else asm volatile("bar.sync 1, 128;\n" ::: "memory");
             if (eg == 0) {
                 if (det_part) {
