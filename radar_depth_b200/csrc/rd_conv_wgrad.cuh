@@ -358,13 +358,18 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
             umma_commit(tmem_full);
         }
         __syncwarp();
-    } else {
-        // ================= epilogue (warps 0-3): TMEM -> fp32 reductions into dw =================
+    }
+    if (warp < 4 + kWgLoaderWarps && (warp < 4 || det_part == nullptr)) {
+        // ================= epilogue: TMEM -> fp32 reductions into dw.  Warps 0-3 and, once their tile loop has ended, the
+        // loader warps 4-15 (TMEM lane quarter = warp & 3): four groups that take every fourth accumulator (non-deterministic
+        // mode; the ordered per-CTA copies of the deterministic mode are written by warps 0-3 alone, as before)
         const bool has_work = (int)blockIdx.x < ntiles;
+        const bool det_mode = det_part != nullptr;
+        const int eg = warp >> 2, neg = det_mode ? 1 : (4 + kWgLoaderWarps) / 4;
         mbar_wait(tmem_full, 0, 0x600);
         tc_fence_after();
         if (tl_mode && tid == 0) p.dbg[2 * dbg_ncta + dbg_cta] = clock64() - t_entry;
-        const int arow = warp * 32 + lane;                // accumulator row: copy * Mc + output channel within the block
+        const int arow = (warp & 3) * 32 + lane;          // accumulator row: copy * Mc + output channel within the block
         const int copy = R > 1 ? arow / p.Mc : 0;
         const int row = arow - copy * p.Mc;
         const bool valid = has_work && copy < R && row < p.Mc && (co0 + row) < p.Cout;
@@ -373,13 +378,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
         if ((SPLIT == 1) && p.fold_len > 0) {
             // folded accumulators: job (row, chunk jx) holds columns [tap-in-row][8 channels of chunk jx]
             const int njobs = p.fold_rows * x_chunks;
-            for (int jb = 0; jb < njobs; ++jb) {
+            for (int jb = eg; jb < njobs; jb += neg) {
                 const int jx = jb & 1;
                 // first tap of the tap row this accumulator row belongs to (gradient copies: one job row covers several)
                 const int tap0 = R > 1 ? (copy < R ? (int)p.job_tap[jb >> 1][copy] : -1) : (jb >> 1) * p.fold_len;
                 for (int cc = 0; cc < 2; ++cc) {
                     float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(jb * 32 + cc * 16), v);
+                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(jb * 32 + cc * 16), v);
                     if (valid && tap0 >= 0) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -394,12 +399,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
                 }
             }
         } else
-        for (int tl = 0; tl < T_n; ++tl) {
+        for (int tl = eg; tl < T_n; tl += neg) {
             const int tap = R > 1 ? (copy < R ? (int)p.job_tap[t0 + tl][copy] : -1) : t0 + tl;
             float* out = dwo + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + (co0 + row)) * p.Cin + ci0;
             for (int cc = 0; cc < (p.Nc >> 4); ++cc) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tl * p.Nc + cc * 16), v);
+                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tl * p.Nc + cc * 16), v);
                 if (valid && tap >= 0) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) acc_out_v4(det, out + cc * 16 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
