@@ -187,3 +187,30 @@ def test_wgrad_planner_prefers_tiles_that_are_one_dense_tma_box():
     for co, ci, hw in ((128, 128, (44, 152)), (256, 256, (22, 76)), (512, 512, (11, 38))):
         w = cp.plan_wgrad(cp.gconv_standard(0, co, ci, 3, 1, 1), 16, hw, hw, use_tuned=False)
         assert w.params.KS == w.params.Ht * w.params.Wl and w.params.KS % 16 == 0, (co, w.info)
+
+
+def test_tuned_lookup_is_keyed_by_the_sm_budget_of_the_launch(monkeypatch):
+    """The measured tile table holds entries per SM budget (the encoder chains run side by side on disjoint SM sets):
+    a launch gets the entry measured with exactly its budget, the whole-GPU entry when its budget is at least half the
+    GPU, and NO entry (cost model) when it owns a few SMs only and was never measured there."""
+    tab = {"k": {"Ht": 1}, "k|sm128": {"Ht": 2}, "k|bn": {"Ht": 3}, "k|sm128|bn": {"Ht": 4}, "j": {"Ht": 5}}
+    monkeypatch.setattr(cp, "_TUNED", tab, raising=False)
+    monkeypatch.setattr(cp, "tuned_table", lambda: tab)
+    assert cp.tuned_lookup("k", cp.NUM_SMS) == {"Ht": 1}
+    assert cp.tuned_lookup("k", 128) == {"Ht": 2}
+    assert cp.tuned_lookup("k", 128, "|bn") == {"Ht": 4}
+    assert cp.tuned_lookup("k", cp.NUM_SMS, "|bn") == {"Ht": 3}
+    assert cp.tuned_lookup("j", 128) == {"Ht": 5}            # no entry for this budget: whole-GPU entry (>= half the GPU)
+    assert cp.tuned_lookup("j", 20) is None                  # a small lane without its own entry: cost model
+    assert cp.tuned_lookup("missing", 128) is None
+
+
+def test_wgrad_plans_with_and_without_the_source_transform_share_the_dw_layout():
+    """engine.emit_wgrad swaps in the '|bn' blocking for launches that transform their source tile: the weight-gradient
+    buffer layout (taps x Cout x Cin) and the scatter table must not depend on the blocking."""
+    g = cp.gconv_standard(0, 128, 128, 3, 1, 1)
+    a = cp.plan_wgrad(g, 16, (44, 152), (44, 152), use_tuned=False, nc=128, ks_target=256)
+    b = cp.plan_wgrad(g, 16, (44, 152), (44, 152), use_tuned=False, nc=64, ks_target=512, sm_budget=128)
+    assert a.dw_elems == b.dw_elems
+    assert all((x == y).all() for x, y in zip(a.scatter, b.scatter))
+    assert b.params.max_ctas * b.params.ncob * b.params.ncib * b.params.ntg <= 128
