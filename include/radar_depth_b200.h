@@ -343,6 +343,12 @@ int rd_pack_weights(const float* src, const int32_t* idx, void* out, long long n
  * *dirty = 1 if any chunk changed (0 otherwise); rd_pack_weights_if is rd_pack_weights that returns at once when *dirty == 0.
  * No host-side bookkeeping of "who touched the weights" is involved: in-place updates through .data are seen as well. */
 int rd_weights_hash(const float* w, long long n, unsigned long long* state, int nchunks, int* dirty, void* stream);
+
+/* rd_pack_weights with a compact table: groups[g] = (base, stride) describes outputs 8g .. 8g+7 = src[base + i*stride] (bit 30 of
+ * base = lo part of the bf16 split, base < 0 = eight zeros); stride < 0 marks a group with holes whose eight rd_pack_weights
+ * indices are fallback[8*base .. 8*base+7].  dirty: NULL, or the flag of rd_weights_hash (returns at once when *dirty == 0). */
+int rd_pack_weights_g8(const float* src, const int32_t* groups, const int32_t* fallback, void* out, long long ngroups, const int* dirty,
+                       void* stream);
 int rd_pack_weights_if(const float* src, const int32_t* idx, void* out, long long n, const int* dirty, void* stream);
 int rd_unpack_grads(const float* dw, const int32_t* idx, float* grad, long long n, void* stream);
 int rd_sgd(float* p, const float* g, float* mom, long long n, float lr, float momentum, float wd, int first, void* stream);

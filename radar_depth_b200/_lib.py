@@ -134,6 +134,7 @@ _PROTOS = {
     "rd_sid_filter": ([_P, _P, _LL, _P, _P, _P], _I),
     "rd_pack_weights": ([_P, _P, _P, _LL, _P], _I),
     "rd_weights_hash": ([_P, _LL, _P, _I, _P, _P], _I),
+    "rd_pack_weights_g8": ([_P, _P, _P, _P, _LL, _P, _P], _I),
     "rd_pack_weights_if": ([_P, _P, _P, _LL, _P, _P], _I),
     "rd_unpack_grads": ([_P, _P, _P, _LL, _P], _I),
     "rd_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _I, _P], _I),

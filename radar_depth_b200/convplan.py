@@ -455,6 +455,33 @@ def plan_fprop(g: GConv, B: int, src_hw, dst_hw, act_dtype: int = _lib.RD_BF16, 
                      info=dict(geo=geo, IS=IS, WS=WS, grp_n=grp_n, P=P, N=N, nblk=nblk))
 
 
+def compact_pack_table(idx: np.ndarray):
+    """(groups [G,2] int32, fallback [F,8] int32) for rd_pack_weights_g8 from a rd_pack_weights index table (length 8 G).
+    A group of 8 consecutive outputs whose indices form an arithmetic progression with one hi/lo flag becomes (base, stride);
+    eight invalid entries become (-1, 0); anything else (holes: zero-padded stem taps, channel counts that are no
+    multiple of 8) keeps its eight indices in the fallback table and becomes (row, -1)."""
+    assert idx.size % 8 == 0
+    t = idx.reshape(-1, 8).astype(np.int64)
+    valid = t >= 0
+    allneg = ~valid.any(axis=1)
+    allpos = valid.all(axis=1)
+    raw = t & 0x3FFFFFFF
+    flag = t & 0x40000000
+    d = np.diff(raw, axis=1)
+    ap = allpos & (d == d[:, :1]).all(axis=1) & (d[:, 0] >= 0) & (flag == flag[:, :1]).all(axis=1)
+    groups = np.zeros((t.shape[0], 2), dtype=np.int32)
+    groups[ap, 0] = t[ap, 0].astype(np.int32)
+    groups[ap, 1] = d[ap, 0].astype(np.int32)
+    groups[allneg, 0] = -1
+    other = ~(ap | allneg)
+    fb = idx.reshape(-1, 8)[other].astype(np.int32)
+    groups[other, 0] = np.arange(int(other.sum()), dtype=np.int32)
+    groups[other, 1] = -1
+    if fb.shape[0] == 0:
+        fb = np.full((1, 8), -1, dtype=np.int32)
+    return np.ascontiguousarray(groups), np.ascontiguousarray(fb)
+
+
 # ------------------------------------------------------------------------------------------ wgrad planning
 @dataclass
 class WgradPlan:

@@ -1380,6 +1380,51 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, const int* __
         out[i] = __float2bfloat16_rn(v);
     }
 }
+// Compact form of the same packing: the packed layout keeps the 8 input channels of one (tap, output channel) adjacent, and
+// in the parameter arena those 8 weights are an arithmetic progression (stride = kernel area for OIHW weights) for 99.9 % of
+// the groups.  One (base, stride) pair per 8 outputs replaces eight int32 indices: base < 0 = eight zeros, stride < 0 = a
+// group with holes, whose eight indices sit in the small fallback table at row `base`.  A thread packs one group and stores
+// 16 bytes (the index-per-element form read 4 table bytes and stored 2 bytes per thread: 97 us per step for 29.4 M elements).
+__global__ void __launch_bounds__(256) pack_weights_g8_kernel(const float* __restrict__ src, const int2* __restrict__ tab,
+                                                              const int* __restrict__ fb, uint4* __restrict__ out, size_t ngroups,
+                                                              const int* __restrict__ dirty) {
+    pdl_enter();
+    if (dirty != nullptr && *dirty == 0) return;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
+        const int2 e = tab[g];
+        float v[8];
+        if (e.y >= 0) {
+            if (e.x < 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            } else {
+                const float* q = src + (e.x & 0x3FFFFFFF);
+                const bool lo = (e.x & 0x40000000) != 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float w = __ldg(q + (size_t)i * e.y);
+                    v[i] = lo ? (w - __bfloat162float(__float2bfloat16_rn(w))) : w;
+                }
+            }
+        } else {
+            const int* f = fb + (size_t)e.x * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = f[i];
+                float w = 0.f;
+                if (k >= 0) {
+                    w = src[k & 0x3FFFFFFF];
+                    if (k & 0x40000000) w -= __bfloat162float(__float2bfloat16_rn(w));
+                }
+                v[i] = w;
+            }
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        out[g] = u;
+    }
+}
+
 // Content hash of the parameter arena, one 64-bit value per block-sized chunk: every 32-bit word is mixed with its index
 // (splitmix64 finaliser) and the mixes are summed, so the hash does not depend on the summation order.  A chunk whose hash
 // differs from the stored one sets *dirty and stores the new hash.  The inference program (model.eval() + no_grad, the

@@ -818,7 +818,12 @@ class LatefusionEngine:
         self.det_scratch = torch.zeros(max(det_bytes), dtype=torch.uint8, device=self.device) if self.det else None
         self.wpk = torch.zeros(self._wpk_total, dtype=torch.bfloat16, device=self.device)
         self.dw = torch.zeros(max(self._dw_total, 1), dtype=torch.float32, device=self.device)
-        self.pack_idx = torch.from_numpy(np.concatenate(self._wpk_tables)).to(self.device)
+        pack_np = np.concatenate(self._wpk_tables)
+        # compact (base, stride) table of rd_pack_weights_g8: 8 bytes per 8 outputs instead of 32
+        grp, fbk = cp.compact_pack_table(pack_np)
+        self.pack_groups = self.hold(torch.from_numpy(grp).to(self.device))
+        self.pack_fallback = self.hold(torch.from_numpy(fbk).to(self.device))
+        self.pack_elems = int(pack_np.size)
         unpack = np.full(self.nparams, -1, dtype=np.int32)
         unpack[np.concatenate(self._scatter_p)] = np.concatenate(self._scatter_d).astype(np.int32)
         self.unpack_idx = torch.from_numpy(unpack).to(self.device)
@@ -829,8 +834,9 @@ class LatefusionEngine:
                 p.dw = _p(self.dw, off)
         self._pending = []
         self._wpk_tables = []
-        pack = Launch("pack_weights", lib.rd_pack_weights, (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel()),
-                      dict(bytes=self.pack_idx.numel() * (4 + 4 + 2)))
+        pack = Launch("pack_weights", lib.rd_pack_weights_g8,
+                      (_p(self.flat), _p(self.pack_groups), _p(self.pack_fallback), _p(self.wpk), self.pack_elems // 8, None),
+                      dict(bytes=self.pack_elems * (1 + 4 + 2)))
         self.fwd.insert(0, pack)
         self.fwd_eval.insert(0, pack)
         self.bn_eval_table = self.hold(torch.tensor(self._bn_eval_rows, dtype=torch.int64, device=self.device))
@@ -845,9 +851,9 @@ class LatefusionEngine:
             self._wdirty = self.hold(torch.zeros(1, dtype=torch.int32, device=self.device))
             hashl = Launch("weights_hash", lib.rd_weights_hash, (_p(self.flat), self.nparams, _p(self._whash), nchunks, _p(self._wdirty)),
                            dict(bytes=self.nparams * 4))
-            packif = Launch("pack_weights_if", lib.rd_pack_weights_if,
-                            (_p(self.flat), _p(self.pack_idx), _p(self.wpk), self.pack_idx.numel(), _p(self._wdirty)),
-                            dict(bytes=self.pack_idx.numel() * (4 + 4 + 2)))
+            packif = Launch("pack_weights_if", lib.rd_pack_weights_g8,
+                            (_p(self.flat), _p(self.pack_groups), _p(self.pack_fallback), _p(self.wpk), self.pack_elems // 8, _p(self._wdirty)),
+                            dict(bytes=self.pack_elems * (1 + 4 + 2)))
             self.fwd_infer = [hashl, packif, self.fwd_eval[1]] + self.fwd_infer_body
         bw.append(Launch("unpack_grads", lib.rd_unpack_grads, (_p(self.dw), _p(self.unpack_idx), _p(self.gflat), self.nparams),
                          dict(bytes=self.nparams * (4 + 4 + 8))))

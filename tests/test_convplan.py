@@ -214,3 +214,28 @@ def test_wgrad_plans_with_and_without_the_source_transform_share_the_dw_layout()
     assert a.dw_elems == b.dw_elems
     assert all((x == y).all() for x, y in zip(a.scatter, b.scatter))
     assert b.params.max_ctas * b.params.ncob * b.params.ncib * b.params.ntg <= 128
+
+
+def test_compact_pack_table_reproduces_the_index_table():
+    """rd_pack_weights_g8's (base, stride) groups + fallback rows must describe exactly the gather of the per-element table:
+    checked on real plans (standard, stride-2 data gradient, stem with zero-padded taps, fused UpProj) in both precisions."""
+    tables = []
+    for act in (_lib.RD_BF16, _lib.RD_F32):
+        for g, s_hw, d_hw in ((cp.gconv_standard(0, 64, 64, 3, 1, 1), (20, 37), (20, 37)),
+                              (cp.gconv_standard(0, 128, 64, 3, 2, 1).transposed(), (11, 19), (22, 38)),
+                              (cp.gconv_stem(0, 64 * 3 * 49, 1), (24, 40), (24, 40)),
+                              (cp.gconv_upproj(0, 16 * 32 * 25, 32, 16), (20, 33), (40, 66))):
+            tables.append(cp.plan_fprop(g, 2, s_hw, d_hw, act, use_tuned=False).pack_idx)
+    idx = np.concatenate(tables)
+    grp, fb = cp.compact_pack_table(idx)
+    assert grp.shape == (idx.size // 8, 2) and fb.shape[1] == 8
+    rebuilt = np.empty((grp.shape[0], 8), dtype=np.int64)
+    ap = grp[:, 1] >= 0
+    zero = ap & (grp[:, 0] < 0)
+    flag = grp[:, 0].astype(np.int64) & 0x40000000
+    base = grp[:, 0].astype(np.int64) & 0x3FFFFFFF
+    rebuilt[ap] = (base[ap, None] + np.arange(8)[None, :] * grp[ap, 1].astype(np.int64)[:, None]) | flag[ap, None]
+    rebuilt[zero] = -1
+    rebuilt[~ap] = fb[grp[~ap, 0]]
+    assert (rebuilt.reshape(-1) == idx.astype(np.int64)).all()
+    assert (~ap).mean() < 0.2 and ap.mean() > 0.8            # the compact form is the common case

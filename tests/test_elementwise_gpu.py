@@ -428,3 +428,43 @@ def test_pack_unpack_and_sgd():
         opt.step()
         call("rd_sgd", ptr(p), ptr(g), ptr(m), 777, 0.01, 0.9, 1e-4, 1 if step == 0 else 0, stream_ptr())
     torch.testing.assert_close(p, pr.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_pack_weights_g8_equals_the_per_element_gather():
+    """Compact (base, stride) table + fallback rows (convplan.compact_pack_table) against rd_pack_weights on a table with
+    arithmetic-progression groups, all-invalid groups, groups with holes and lo-part (bit 30) groups; also the `dirty` switch."""
+    import numpy as np
+    from radar_depth_b200 import convplan as cp
+    rng = np.random.default_rng(7)
+    n_src = 5000
+    rows = []
+    for _ in range(300):
+        kind = rng.integers(0, 4)
+        if kind == 0:                                           # arithmetic progression (stride 0..9)
+            b, st = int(rng.integers(0, n_src - 80)), int(rng.integers(0, 10))
+            r = b + st * np.arange(8)
+        elif kind == 1:
+            r = np.full(8, -1)
+        elif kind == 2:                                         # holes
+            r = rng.integers(0, n_src, 8)
+            r[rng.integers(0, 8, 3)] = -1
+        else:                                                   # lo part of the split
+            b, st = int(rng.integers(0, n_src - 80)), int(rng.integers(1, 10))
+            r = (b + st * np.arange(8)) | (1 << 30)
+        rows.append(r)
+    idx_np = np.concatenate(rows).astype(np.int32)
+    src = torch.randn(n_src, device="cuda")
+    idx = torch.from_numpy(idx_np).cuda()
+    ref = ops.pack_weights(src, idx)
+    grp, fb = cp.compact_pack_table(idx_np)
+    g_t, f_t = torch.from_numpy(grp).cuda(), torch.from_numpy(fb).cuda()
+    out = torch.full_like(ref, float("nan"))
+    call("rd_pack_weights_g8", ptr(src), ptr(g_t), ptr(f_t), ptr(out), grp.shape[0], None, stream_ptr())
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+    dirty = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out2 = torch.zeros_like(ref)
+    call("rd_pack_weights_g8", ptr(src), ptr(g_t), ptr(f_t), ptr(out2), grp.shape[0], ptr(dirty), stream_ptr())
+    assert not out2.float().abs().sum().item()                  # *dirty == 0: nothing written
+    dirty.fill_(1)
+    call("rd_pack_weights_g8", ptr(src), ptr(g_t), ptr(f_t), ptr(out2), grp.shape[0], ptr(dirty), stream_ptr())
+    assert torch.equal(out2.view(torch.int16), ref.view(torch.int16))
