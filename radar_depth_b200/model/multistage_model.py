@@ -78,5 +78,10 @@ class ResNet_multistage(nn.Module):
         x_d_filtered, mask = self.filter_layer(x_d, depth_stage1)
         # multistage_model.py:78-79: stage2(cat(x_img, x_d_filtered, depth_stage1)); the three sources are packed by one
         # kernel (rd_input_pack_parts) and the gradient of depth_stage1 comes back from rd_input_grad_channel
-        depth_stage2 = self.stage2.forward_parts(x_img, x_d_filtered, depth_stage1)
+        if x.requires_grad and torch.is_grad_enabled():
+            # a caller that differentiates w.r.t. the network INPUT (saliency, adversarial probes): the general path, whose
+            # autograd node returns the gradient of all five stage-2 input channels
+            depth_stage2 = self.stage2(torch.cat((x_img.float(), x_d_filtered, depth_stage1), dim=1))
+        else:
+            depth_stage2 = self.stage2.forward_parts(x_img, x_d_filtered, depth_stage1)
         return {"stage1": depth_stage1, "stage2": depth_stage2, "mask": mask, "radar_filtered": x_d_filtered}
