@@ -65,3 +65,42 @@ def test_eval_mode_backward_switches_every_batchnorm_job():
     assert all(float(j.count) == float("inf") for j, _ in eng._bwd_jobs)
     eng._bn_backward_mode(True)
     assert [float(j.count) for j, _ in eng._bwd_jobs] == counts
+
+
+@pytest.mark.parametrize("cin,b", [(4, 16), (5, 8)])
+def test_encoder_lanes_own_disjoint_sm_sets(cin, b):
+    """Between the stem and the fusion convolution the depth encoder (lane 1) and the RGB encoder (lane 0) run at the same
+    time; every launch of a lane is planned for that lane's CTA budget, the budgets add up to the GPU, and the launches
+    outside the two-lane region may use all of it.  (A conv CTA owns its SM: > half the shared memory + all TMEM columns.)"""
+    from radar_depth_b200 import convplan as cp
+    hw = (352, 1216)
+    m = ResNet_latefusion(18, "upproj", hw, cin, pretrained=False)
+    eng = LatefusionEngine(m, cin, hw, _lib.RD_BF16)
+    eng.det = False
+    eng.adopt("cpu")
+    eng.configure(b, *hw)
+    assert eng._par and eng._depth_sms == 20
+    budgets = {rec["wargs"][3] for rec in eng.convs}
+    assert budgets == {cp.NUM_SMS, cp.NUM_SMS - 20, 20}
+    for rec in eng.convs:
+        sms = rec["wargs"][3]
+        plans = [rec["fplan"]] + ([rec["dplan"]] if rec["dplan"] is not None else [])
+        for pl in plans:
+            ctas = min(int(pl.params.max_ctas), pl.ntiles) * int(pl.params.nblk)
+            assert ctas <= sms, (rec["name"], ctas, sms)
+        for key in ("wplan", "wplan_bn"):
+            w = rec.get(key)
+            if w is not None:
+                q = w.params
+                assert int(q.max_ctas) * int(q.ncob) * int(q.ncib) * int(q.ntg) <= sms, (rec["name"], key, sms)
+    # the launch programs: one fork and one join per direction, lane-1 launches only between them
+    for prog in (eng.fwd, eng.bwd):
+        syncs = [L.sync for L in prog if L.sync]
+        assert syncs == ["fork", "join"], syncs
+        inside = False
+        for L in prog:
+            if L.sync == "fork":
+                inside = True
+            elif L.sync == "join":
+                inside = False
+            assert L.lane == 0 or inside, L.name
